@@ -1,0 +1,111 @@
+/*
+ * opencorr_b200.h -- C ABI of the B200-native FFT-CC -> IC-GN correlation engine.
+ *
+ * This is the drop-in boundary for ONE hot path of vincentjzy/OpenCorr: the per-POI
+ * FFT-CC integer-pixel initial guess followed by inverse-compositional Gauss-Newton
+ * registration.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference repo root).  Plain pointers and sizes only; no
+ * C++/torch types.  The C++ shim in include/opencorr/ (same class names as the
+ * reference) and the Python mirror in opencorr_b200/ are thin layers over this file.
+ *
+ * Conventions
+ *   - POI arrays are the reference's own records, passed verbatim:
+ *       POI2D  (src/oc_poi.h:102-136) = 25 floats / 100 bytes
+ *         { x, y | u ux uy uxx uxy uyy v vx vy vxx vxy vyy | u0 v0 zncc iteration
+ *           convergence feature | exx eyy exy | subset_radius.x subset_radius.y }
+ *       POI3D  (src/oc_poi.h:187-222) = 31 floats / 124 bytes
+ *         { x, y, z | u ux uy uz v vx vy vz w wx wy wz | u0 v0 w0 zncc iteration
+ *           convergence feature | e[6] | subset_radius.x .y .z }
+ *     They are mutated in place exactly as the reference's compute(std::vector<POI>&) does,
+ *     including the sentinel ZNCC codes of src/oc_dic.h:28-34 (-3 rejected / left the image,
+ *     -4 not converged, -5 NaN; a POI arriving with zncc < 0 is skipped).
+ *   - Images: float32.  2D row-major [height][width] (col_major=1 accepts the reference's
+ *     Eigen::MatrixXf storage, src/oc_image.h:36); volumes [z][y][x] contiguous, the payload
+ *     of the reference's float*** (src/oc_array.h:56-74).
+ *   - Every function returns OCB_OK (0) or a negative OCB_ERR_* code; the message is
+ *     available from ocb_last_error().  There is NO CPU fallback: without a usable CUDA
+ *     device ocb_create() fails (returns NULL) and says why.
+ *   - Functions taking host POI arrays copy host->device, run, copy back and synchronise
+ *     (the reference's blocking compute()).  The *_dev variants take a device pointer,
+ *     enqueue on the context's stream and return without synchronising.
+ */
+#ifndef OPENCORR_B200_H_
+#define OPENCORR_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCB_OK 0
+#define OCB_ERR_CUDA (-1)        /* CUDA runtime / driver error (message has the CUDA string) */
+#define OCB_ERR_ARG (-2)         /* bad argument (null pointer, radius < 1, size mismatch ...) */
+#define OCB_ERR_STATE (-3)       /* call order: images not set / prepare() not called */
+#define OCB_ERR_UNSUPPORTED (-4) /* subset too large for the on-chip design */
+
+#define OCB_POI2D_FLOATS 25
+#define OCB_POI3D_FLOATS 31
+
+typedef struct ocb_ctx ocb_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Number of CUDA devices visible, or a negative OCB_ERR_CUDA. */
+int ocb_device_count(void);
+/* One context = one GPU + one stream + the device copies the reference keeps per DIC/DVC
+ * object (images, gradient / B-spline tables, scratch).  Replaces the constructors
+ * FFTCC2D/FFTCC3D (src/oc_fftcc.cpp:151-163,300-313) and ICGN2D1/ICGN2D2/ICGN3D1
+ * (src/oc_icgn.cpp:71-88,612-629,1197-1215): no per-thread pools are needed on the GPU.
+ * Returns NULL on failure (see ocb_last_error(NULL)). */
+ocb_ctx* ocb_create(int device);
+void ocb_destroy(ocb_ctx* ctx);
+/* Last error message of this context (or of the process when ctx == NULL). Never NULL. */
+const char* ocb_last_error(const ocb_ctx* ctx);
+/* Use an external cudaStream_t (e.g. PyTorch's current stream); NULL restores the own stream. */
+int ocb_set_stream(ocb_ctx* ctx, void* cuda_stream);
+/* Block until everything enqueued on the context's stream has finished. */
+int ocb_sync(ocb_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py "gpu_launches"). */
+long long ocb_launch_count(const ocb_ctx* ctx);
+
+/* ---- images: DIC::setImages / DVC::setImages (src/oc_dic.cpp:22-26,44-48) ----------------- */
+/* Host buffers; copied to the device (H2D on the context's stream). */
+int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int width, int height, int col_major);
+int ocb_set_images_3d(ocb_ctx* ctx, const float* ref, const float* tar, int dim_x, int dim_y, int dim_z);
+/* Device buffers (row-major / [z][y][x]); BORROWED like the reference borrows Image2D*. */
+int ocb_set_images_2d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int width, int height);
+int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int dim_x, int dim_y, int dim_z);
+
+/* ---- FFT-CC: FFTCC2D::compute(std::vector<POI2D>&) src/oc_fftcc.cpp:277-285 (per POI
+ *      :177-275) and FFTCC3D::compute(std::vector<POI3D>&) :429-437 (per POI :327-427) ------- */
+int ocb_fftcc2d(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry);
+int ocb_fftcc3d(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz);
+int ocb_fftcc2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry);
+int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz);
+
+/* ---- IC-GN prepare(): ICGN2D1::prepare src/oc_icgn.cpp:138-142, ICGN2D2::prepare :679-683,
+ *      ICGN3D1::prepare :1264-1268.  2D: nothing is materialised (gradients and bicubic
+ *      weights are recomputed on chip); 3D: gradient volumes + tricubic B-spline coefficient
+ *      volume are built on the device (src/oc_gradient.cpp:143-231, oc_cubic_bspline.cpp:214-351). */
+int ocb_icgn2d_prepare(ocb_ctx* ctx);
+int ocb_icgn3d_prepare(ocb_ctx* ctx);
+
+/* ---- IC-GN compute(): ICGN2D1::compute(std::vector<POI2D>&) src/oc_icgn.cpp:343-351 (per POI
+ *      :144-341); ICGN2D2 :900-908 (:685-898); ICGN3D1 :1492-1500 (:1270-1490).
+ *      conv = conv_criterion, stop = stop_condition (a float in the reference, oc_icgn.h:52). */
+int ocb_icgn2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, float stop);
+int ocb_icgn2d2(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, float stop);
+int ocb_icgn3d1(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz, float conv, float stop);
+int ocb_icgn2d1_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop);
+int ocb_icgn2d2_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop);
+int ocb_icgn3d1_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz, float conv, float stop);
+
+/* ---- inspection (parity tests of the prepare() products) ----------------------------------- */
+/* Copy the device tables built by ocb_icgn3d_prepare() to host buffers of dim_x*dim_y*dim_z
+ * floats each; any pointer may be NULL. */
+int ocb_get_tables_3d(ocb_ctx* ctx, float* gx, float* gy, float* gz, float* coefficient);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENCORR_B200_H_ */

@@ -1,0 +1,308 @@
+"""Host-side mirror of the reference's operator interface for the FFT-CC -> IC-GN path.
+
+Class names, constructor arguments and method meaning follow the reference (C++):
+  FFTCC2D(int rx, int ry, int threads)                        src/oc_fftcc.h:61
+  FFTCC3D(int rx, int ry, int rz, int threads)                src/oc_fftcc.h:82
+  ICGN2D1 / ICGN2D2(int rx, int ry, float conv, float stop, int threads)   src/oc_icgn.h:58,113
+  ICGN3D1(int rx, int ry, int rz, float conv, float stop, int threads)     src/oc_icgn.h:168
+  setImages / setSubset / prepare / compute / setIteration    src/oc_dic.h:56-84, oc_icgn.h:61-76
+Python spellings (set_images, ...) are provided next to the reference's camelCase names.
+
+POI queues are numpy float32 arrays [n, 25] (POI2D) or [n, 31] (POI3D) -- the reference's
+records viewed as floats (src/oc_poi.h:102-136,187-222) -- mutated in place like
+compute(std::vector<POI>&).  Everything runs through the C ABI (include/opencorr_b200.h); the
+`thread_number` argument is accepted for signature compatibility and ignored (no CPU threads).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+
+# ---- POI record layout (reference src/oc_poi.h) ------------------------------------------------
+POI2D_FLOATS = 25
+POI3D_FLOATS = 31
+P2 = dict(x=0, y=1, u=2, ux=3, uy=4, uxx=5, uxy=6, uyy=7, v=8, vx=9, vy=10, vxx=11, vxy=12, vyy=13,
+          u0=14, v0=15, zncc=16, iteration=17, convergence=18, feature=19, exx=20, eyy=21, exy=22,
+          subset_rx=23, subset_ry=24)
+P3 = dict(x=0, y=1, z=2, u=3, ux=4, uy=5, uz=6, v=7, vx=8, vy=9, vz=10, w=11, wx=12, wy=13, wz=14,
+          u0=15, v0=16, w0=17, zncc=18, iteration=19, convergence=20, feature=21,
+          exx=22, eyy=23, ezz=24, exy=25, eyz=26, ezx=27, subset_rx=28, subset_ry=29, subset_rz=30)
+
+
+def make_poi2d(xy):
+    """POI2D(Point2D) for every row of xy: location set, everything else cleared (oc_poi.h:112-135)."""
+    xy = np.asarray(xy, dtype=np.float32).reshape(-1, 2)
+    q = np.zeros((xy.shape[0], POI2D_FLOATS), np.float32)
+    q[:, 0:2] = xy
+    return q
+
+
+def make_poi3d(xyz):
+    xyz = np.asarray(xyz, dtype=np.float32).reshape(-1, 3)
+    q = np.zeros((xyz.shape[0], POI3D_FLOATS), np.float32)
+    q[:, 0:3] = xyz
+    return q
+
+
+def _vp(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _check_queue(q, floats):
+    if not isinstance(q, np.ndarray) or q.dtype != np.float32 or q.ndim != 2 or q.shape[1] != floats \
+            or not q.flags.c_contiguous:
+        raise ValueError("POI queue must be a C-contiguous float32 array of shape [n, %d]" % floats)
+
+
+class Engine:
+    """One GPU context (ocb_ctx).  Raises OpenCorrB200Error when no B200-class GPU is usable."""
+
+    def __init__(self, device=0):
+        self._lib = _capi.load()
+        self._ctx = self._lib.ocb_create(int(device))
+        if not self._ctx:
+            raise _capi.OpenCorrB200Error(_capi.OCB_ERR_CUDA, _capi.last_error(None))
+        self.device = int(device)
+        self._keep = []  # host arrays referenced by the last upload
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.ocb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _capi.check(rc, self._ctx)
+
+    # images ------------------------------------------------------------------------------------
+    def set_images_2d(self, ref, tar):
+        ref = np.ascontiguousarray(ref, dtype=np.float32)
+        tar = np.ascontiguousarray(tar, dtype=np.float32)
+        if ref.ndim != 2 or ref.shape != tar.shape:
+            raise ValueError("ref/tar must be 2-D arrays of equal shape")
+        h, w = ref.shape
+        self._ck(self._lib.ocb_set_images_2d(self._ctx, _vp(ref), _vp(tar), w, h, 0))
+        self._ck(self._lib.ocb_sync(self._ctx))
+
+    def set_images_3d(self, ref, tar):
+        ref = np.ascontiguousarray(ref, dtype=np.float32)
+        tar = np.ascontiguousarray(tar, dtype=np.float32)
+        if ref.ndim != 3 or ref.shape != tar.shape:
+            raise ValueError("ref/tar must be 3-D arrays [z, y, x] of equal shape")
+        dz, dy, dx = ref.shape
+        self._ck(self._lib.ocb_set_images_3d(self._ctx, _vp(ref), _vp(tar), dx, dy, dz))
+        self._ck(self._lib.ocb_sync(self._ctx))
+
+    def set_images_2d_dev(self, d_ref, d_tar, width, height):
+        self._ck(self._lib.ocb_set_images_2d_dev(self._ctx, int(d_ref), int(d_tar), width, height))
+
+    def set_images_3d_dev(self, d_ref, d_tar, dim_x, dim_y, dim_z):
+        self._ck(self._lib.ocb_set_images_3d_dev(self._ctx, int(d_ref), int(d_tar), dim_x, dim_y, dim_z))
+
+    def set_stream(self, cuda_stream):
+        self._ck(self._lib.ocb_set_stream(self._ctx, int(cuda_stream) if cuda_stream else None))
+
+    def sync(self):
+        self._ck(self._lib.ocb_sync(self._ctx))
+
+    def launch_count(self):
+        return int(self._lib.ocb_launch_count(self._ctx))
+
+    # hot path, host POI queues -------------------------------------------------------------------
+    def fftcc2d(self, q, rx, ry):
+        _check_queue(q, POI2D_FLOATS)
+        self._ck(self._lib.ocb_fftcc2d(self._ctx, _vp(q), q.shape[0], rx, ry))
+
+    def fftcc3d(self, q, rx, ry, rz):
+        _check_queue(q, POI3D_FLOATS)
+        self._ck(self._lib.ocb_fftcc3d(self._ctx, _vp(q), q.shape[0], rx, ry, rz))
+
+    def icgn2d_prepare(self):
+        self._ck(self._lib.ocb_icgn2d_prepare(self._ctx))
+
+    def icgn3d_prepare(self):
+        self._ck(self._lib.ocb_icgn3d_prepare(self._ctx))
+
+    def icgn2d1(self, q, rx, ry, conv, stop):
+        _check_queue(q, POI2D_FLOATS)
+        self._ck(self._lib.ocb_icgn2d1(self._ctx, _vp(q), q.shape[0], rx, ry, conv, stop))
+
+    def icgn2d2(self, q, rx, ry, conv, stop):
+        _check_queue(q, POI2D_FLOATS)
+        self._ck(self._lib.ocb_icgn2d2(self._ctx, _vp(q), q.shape[0], rx, ry, conv, stop))
+
+    def icgn3d1(self, q, rx, ry, rz, conv, stop):
+        _check_queue(q, POI3D_FLOATS)
+        self._ck(self._lib.ocb_icgn3d1(self._ctx, _vp(q), q.shape[0], rx, ry, rz, conv, stop))
+
+    # hot path, device-resident POI queues (pointers as ints, e.g. torch.Tensor.data_ptr()) --------
+    def fftcc2d_dev(self, d_q, n, rx, ry):
+        self._ck(self._lib.ocb_fftcc2d_dev(self._ctx, int(d_q), n, rx, ry))
+
+    def fftcc3d_dev(self, d_q, n, rx, ry, rz):
+        self._ck(self._lib.ocb_fftcc3d_dev(self._ctx, int(d_q), n, rx, ry, rz))
+
+    def icgn2d1_dev(self, d_q, n, rx, ry, conv, stop):
+        self._ck(self._lib.ocb_icgn2d1_dev(self._ctx, int(d_q), n, rx, ry, conv, stop))
+
+    def icgn2d2_dev(self, d_q, n, rx, ry, conv, stop):
+        self._ck(self._lib.ocb_icgn2d2_dev(self._ctx, int(d_q), n, rx, ry, conv, stop))
+
+    def icgn3d1_dev(self, d_q, n, rx, ry, rz, conv, stop):
+        self._ck(self._lib.ocb_icgn3d1_dev(self._ctx, int(d_q), n, rx, ry, rz, conv, stop))
+
+
+_default_engines = {}
+
+
+def default_engine(device=0):
+    """Process-wide engine per device, shared by the operator objects below (the reference's
+    objects all borrow the same Image2D/Image3D; here they share one device copy)."""
+    eng = _default_engines.get(device)
+    if eng is None or not eng._ctx:
+        eng = Engine(device)
+        _default_engines[device] = eng
+    return eng
+
+
+class _DIC:
+    def __init__(self, rx, ry, thread_number=0, engine=None):
+        self.subset_radius_x = int(rx)
+        self.subset_radius_y = int(ry)
+        self.thread_number = int(thread_number)
+        self.self_adaptive = False
+        self.engine = engine if engine is not None else default_engine()
+        self.ref_img = None
+        self.tar_img = None
+
+    def set_images(self, ref_img, tar_img):
+        self.ref_img, self.tar_img = ref_img, tar_img
+        self.engine.set_images_2d(ref_img, tar_img)
+        self._images_set()
+
+    def _images_set(self):
+        pass
+
+    def set_subset(self, radius_x, radius_y):
+        self.subset_radius_x, self.subset_radius_y = int(radius_x), int(radius_y)
+
+    setImages = set_images
+    setSubset = set_subset
+
+
+class _DVC:
+    def __init__(self, rx, ry, rz, thread_number=0, engine=None):
+        self.subset_radius_x = int(rx)
+        self.subset_radius_y = int(ry)
+        self.subset_radius_z = int(rz)
+        self.thread_number = int(thread_number)
+        self.engine = engine if engine is not None else default_engine()
+        self.ref_img = None
+        self.tar_img = None
+
+    def set_images(self, ref_img, tar_img):
+        self.ref_img, self.tar_img = ref_img, tar_img
+        self.engine.set_images_3d(ref_img, tar_img)
+        self._images_set()
+
+    def _images_set(self):
+        pass
+
+    def set_subset(self, radius_x, radius_y, radius_z):
+        self.subset_radius_x, self.subset_radius_y, self.subset_radius_z = int(radius_x), int(radius_y), int(radius_z)
+
+    setImages = set_images
+    setSubset = set_subset
+
+
+class FFTCC2D(_DIC):
+    def prepare(self):
+        pass
+
+    def compute(self, poi_queue):
+        self.engine.fftcc2d(poi_queue, self.subset_radius_x, self.subset_radius_y)
+        return poi_queue
+
+
+class FFTCC3D(_DVC):
+    def prepare(self):
+        pass
+
+    def compute(self, poi_queue):
+        self.engine.fftcc3d(poi_queue, self.subset_radius_x, self.subset_radius_y, self.subset_radius_z)
+        return poi_queue
+
+
+class _ICGN2D(_DIC):
+    _order = 1
+
+    def __init__(self, rx, ry, conv_criterion, stop_condition, thread_number=0, engine=None):
+        super().__init__(rx, ry, thread_number, engine)
+        self.conv_criterion = float(conv_criterion)
+        self.stop_condition = float(stop_condition)
+
+    def set_iteration(self, conv_criterion, stop_condition):
+        self.conv_criterion, self.stop_condition = float(conv_criterion), float(stop_condition)
+
+    def prepare_ref(self):
+        self.engine.icgn2d_prepare()
+
+    def prepare_tar(self):
+        self.engine.icgn2d_prepare()
+
+    def prepare(self):
+        self.engine.icgn2d_prepare()
+
+    def compute(self, poi_queue):
+        fn = self.engine.icgn2d1 if self._order == 1 else self.engine.icgn2d2
+        fn(poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion, self.stop_condition)
+        return poi_queue
+
+    setIteration = set_iteration
+    prepareRef = prepare_ref
+    prepareTar = prepare_tar
+
+
+class ICGN2D1(_ICGN2D):
+    _order = 1
+
+
+class ICGN2D2(_ICGN2D):
+    _order = 2
+
+
+class ICGN3D1(_DVC):
+    def __init__(self, rx, ry, rz, conv_criterion, stop_condition, thread_number=0, engine=None):
+        super().__init__(rx, ry, rz, thread_number, engine)
+        self.conv_criterion = float(conv_criterion)
+        self.stop_condition = float(stop_condition)
+
+    def set_iteration(self, conv_criterion, stop_condition):
+        self.conv_criterion, self.stop_condition = float(conv_criterion), float(stop_condition)
+
+    def prepare(self):
+        self.engine.icgn3d_prepare()
+
+    prepare_ref = prepare_tar = prepare
+
+    def compute(self, poi_queue):
+        self.engine.icgn3d1(poi_queue, self.subset_radius_x, self.subset_radius_y, self.subset_radius_z,
+                            self.conv_criterion, self.stop_condition)
+        return poi_queue
+
+    def tables(self):
+        """(gx, gy, gz, coefficient) volumes built by prepare() -- for parity tests."""
+        dz, dy, dx = np.asarray(self.ref_img).shape
+        out = [np.empty((dz, dy, dx), np.float32) for _ in range(4)]
+        eng = self.engine
+        eng._ck(eng._lib.ocb_get_tables_3d(eng._ctx, _vp(out[0]), _vp(out[1]), _vp(out[2]), _vp(out[3])))
+        return out
+
+    setIteration = set_iteration
+    prepareRef = prepareTar = prepare

@@ -1,0 +1,344 @@
+// icgn3d.cu -- DVC: ICGN3D1 (first-order shape function, 12 parameters) and the device-side
+// ICGN3D1::prepare() products, for sm_100a.
+//
+// Replaces ICGN3D1::compute(POI3D*) (reference src/oc_icgn.cpp:1270-1490), Gradient3D4
+// (src/oc_gradient.cpp:143-231) and TricubicBspline::prepare/compute
+// (src/oc_cubic_bspline.cpp:214-405).
+//
+// Mapping: ONE CTA (256 threads) PER POI; the (2r+1)^3 samples are strided over the CTA with x
+// fastest, so the reference-volume reads (value + 3 gradient volumes) are coalesced.  Per-iteration
+// single-pass sums as in icgn2d.cu; the 12x12 Cholesky factor and the running 3x4 warp live in
+// shared memory and are updated by one thread between two barriers.
+#include "ocb_kernels.h"
+
+namespace ocb {
+
+constexpr int ICGN3D_THREADS = 256;
+constexpr int ICGN3D_WARPS = ICGN3D_THREADS / 32;
+
+// ---- ICGN3D1::prepareRef: Gradient3D4::getGradientX/Y/Z, src/oc_gradient.cpp:143-231 ----------
+__global__ void gradient3d_kernel(const float* __restrict__ f, float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gz,
+	int dx, int dy, int dz) {
+	const size_t total = (size_t)dx * dy * dz;
+	const size_t sy = (size_t)dx, sz = (size_t)dx * dy;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int k = (int)(i % dx), j = (int)((i / dx) % dy), ii = (int)(i / sz);
+		float vx = 0.f, vy = 0.f, vz = 0.f; // borders stay zero (calloc in new3D, src/oc_array.h:60)
+		if (k >= 2 && k < dx - 2) vx = grad4(f[i - 2], f[i - 1], f[i + 1], f[i + 2]);
+		if (j >= 2 && j < dy - 2) vy = grad4(f[i - 2 * sy], f[i - sy], f[i + sy], f[i + 2 * sy]);
+		if (ii >= 2 && ii < dz - 2) vz = grad4(f[i - 2 * sz], f[i - sz], f[i + sz], f[i + 2 * sz]);
+		gx[i] = vx;
+		gy[i] = vy;
+		gz[i] = vz;
+	}
+}
+
+// ---- ICGN3D1::prepareTar: one 15-tap FIR pass of TricubicBspline::prepare -----------------------
+// (src/oc_cubic_bspline.cpp:224-348; taps src/oc_cubic_bspline.h:80-90).  The reference's interior
+// and edge branches are the same expression with the indices clamped to [0, dim-1]; the operation
+// order b0*x + b1*(..) + b2*(..) ... is kept and evaluated without FMA so the coefficient volume
+// is bit-identical to the CPU result.
+__constant__ float c_prefilter[8] = { 1.732176555412860f, -0.464135309171000f, 0.124364681271139f, -0.033323415913556f,
+	0.008928982383084f, -0.002392513618779f, 0.000641072092032f, -0.000171774749350f };
+
+__global__ void prefilter3d_kernel(const float* __restrict__ in, float* __restrict__ out, int dx, int dy, int dz, int axis) {
+	const size_t total = (size_t)dx * dy * dz;
+	const size_t sy = (size_t)dx, sz = (size_t)dx * dy;
+	const size_t stride = axis == 0 ? 1 : (axis == 1 ? sy : sz);
+	const int dim = axis == 0 ? dx : (axis == 1 ? dy : dz);
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const int k = (int)(i % dx), j = (int)((i / dx) % dy), ii = (int)(i / sz);
+		const int pos = axis == 0 ? k : (axis == 1 ? j : ii);
+		const float* line = in + (i - (size_t)pos * stride);
+		float v = __fmul_rn(c_prefilter[0], line[(size_t)pos * stride]);
+#pragma unroll
+		for (int t = 1; t <= 7; t++) {
+			const int lo = pos - t < 0 ? 0 : pos - t;
+			const int hi = pos + t > dim - 1 ? dim - 1 : pos + t;
+			v = __fadd_rn(v, __fmul_rn(c_prefilter[t], __fadd_rn(line[(size_t)lo * stride], line[(size_t)hi * stride])));
+		}
+		out[i] = v;
+	}
+}
+
+void gradient3d_launch(const float* ref, float* gx, float* gy, float* gz, int dx, int dy, int dz, int sm_count, cudaStream_t s) {
+	gradient3d_kernel<<<sm_count * 8, 256, 0, s>>>(ref, gx, gy, gz, dx, dy, dz);
+}
+void prefilter3d_launch(const float* in, float* out, int dx, int dy, int dz, int axis, int sm_count, cudaStream_t s) {
+	prefilter3d_kernel<<<sm_count * 8, 256, 0, s>>>(in, out, dx, dy, dz, axis);
+}
+
+// ---- ICGN3D1::compute ---------------------------------------------------------------------------
+constexpr int NP3 = 12;
+constexpr int NH3 = NP3 * (NP3 + 1) / 2; // 78
+constexpr int NSETUP = NH3 + 2 * NP3 + 1; // Hessian + S + SF + f2 = 103
+constexpr int NITER = 3 + NP3;            // d1, d2, fd, SD[12]
+
+struct Icgn3dShared {
+	float part[ICGN3D_WARPS][NSETUP]; // per-warp partial sums
+	float tot[NSETUP];
+	float L[NH3];   // packed Cholesky factor (diag = 1/L_ii)
+	float S[NP3], SF[NP3];
+	float A[12];    // running warp rows: [1+ux uy uz u | vx 1+vy vz v | wx wy 1+wz w]
+	float f2, ref_mean;
+	float dp_norm, zncc;
+	int keep_going;
+};
+
+__device__ __forceinline__ float tricubic_sample(const float* __restrict__ coef, int dx, int dy, float X, float Y, float Z) {
+	const float xf = floorf(X), yf = floorf(Y), zf = floorf(Z);
+	float bx[4], by[4], bz[4];
+	bspline_basis(X - xf, bx);
+	bspline_basis(Y - yf, by);
+	bspline_basis(Z - zf, bz);
+	const float* base = coef + ((size_t)((int)zf - 1) * dy + ((int)yf - 1)) * dx + ((int)xf - 1);
+	float value = 0.f;
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		float sy_acc = 0.f;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const float* row = base + ((size_t)i * dy + j) * dx;
+			float sx_acc = __ldg(row) * bx[0];
+			sx_acc = fmaf(__ldg(row + 1), bx[1], sx_acc);
+			sx_acc = fmaf(__ldg(row + 2), bx[2], sx_acc);
+			sx_acc = fmaf(__ldg(row + 3), bx[3], sx_acc);
+			sy_acc = fmaf(sx_acc, by[j], sy_acc);
+		}
+		value = fmaf(sy_acc, bz[i], value);
+	}
+	return value;
+}
+
+__global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, float* __restrict__ pois, int n_poi, int rx, int ry, int rz,
+	float conv_criterion, float stop_condition) {
+	__shared__ Icgn3dShared sh;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int sx = 2 * rx + 1, sy = 2 * ry + 1, sz = 2 * rz + 1;
+	const int slice = sx * sy, N = slice * sz;
+	const int dx = img.dx, dy = img.dy, dz = img.dz;
+	const float inv_n = 1.0f / (float)N;
+
+	for (int poi = blockIdx.x; poi < n_poi; poi += gridDim.x) {
+		float* P = pois + (size_t)poi * P3_N;
+		const float px = P[P3_X], py = P[P3_Y], pz = P[P3_Z];
+		const float u_in = P[P3_DEF + 0], v_in = P[P3_DEF + 4], w_in = P[P3_DEF + 8];
+		const float zncc_in = P[P3_ZNCC];
+		__syncthreads(); // everyone has read the record before thread 0 may overwrite it
+		// guard, src/oc_icgn.cpp:1279-1286
+		if ((px - rx) < 0 || (py - ry) < 0 || (pz - rz) < 0 || (px + rx) > (dx - 1) || (py + ry) > (dy - 1) || (pz + rz) > (dz - 1)
+			|| fabsf(u_in) >= dx || fabsf(v_in) >= dy || fabsf(w_in) >= dz || zncc_in < 0
+			|| is_nan_f(u_in) || is_nan_f(v_in) || is_nan_f(w_in) || is_nan_f(px) || is_nan_f(py) || is_nan_f(pz)) {
+			if (tid == 0) P[P3_ZNCC] = zncc_in >= 0 ? -3.f : zncc_in;
+			continue;
+		}
+		const int x0 = (int)px - rx, y0 = (int)py - ry, z0 = (int)pz - rz;
+		const float* refb = img.ref + ((size_t)z0 * dy + y0) * dx + x0;
+		const size_t goff = ((size_t)z0 * dy + y0) * dx + x0;
+
+		// ---- reference subset mean (Subset3D::zeroMeanNorm, src/oc_subset.cpp:104-117)
+		float s1 = 0.f;
+		for (int i = tid; i < N; i += ICGN3D_THREADS) {
+			const int ii = i / slice, rem = i - ii * slice, j = rem / sx, k = rem - j * sx;
+			s1 += __ldg(refb + ((size_t)ii * dy + j) * dx + k);
+		}
+		s1 = warp_sum(s1);
+		if (lane == 0) sh.part[warp][0] = s1;
+		__syncthreads();
+		if (tid == 0) {
+			float t = 0.f;
+			for (int i = 0; i < ICGN3D_WARPS; i++) t += sh.part[i][0];
+			sh.ref_mean = t * inv_n;
+		}
+		__syncthreads();
+		const float ref_mean = sh.ref_mean;
+
+		// ---- steepest-descent images + Hessian (src/oc_icgn.cpp:1298-1337)
+		{
+			float acc[NSETUP];
+#pragma unroll
+			for (int k = 0; k < NSETUP; k++) acc[k] = 0.f;
+			for (int i = tid; i < N; i += ICGN3D_THREADS) {
+				const int ii = i / slice, rem = i - ii * slice, j = rem / sx, k = rem - j * sx;
+				const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
+				const float f = __ldg(img.ref + o) - ref_mean;
+				const float gx = __ldg(img.gx + o), gy = __ldg(img.gy + o), gz = __ldg(img.gz + o);
+				const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
+				float sd[NP3];
+				sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl; sd[3] = gx * zl;
+				sd[4] = gy; sd[5] = gy * xl; sd[6] = gy * yl; sd[7] = gy * zl;
+				sd[8] = gz; sd[9] = gz * xl; sd[10] = gz * yl; sd[11] = gz * zl;
+#pragma unroll
+				for (int a = 0; a < NP3; a++) {
+					acc[NH3 + a] += sd[a];
+					acc[NH3 + NP3 + a] = fmaf(sd[a], f, acc[NH3 + NP3 + a]);
+#pragma unroll
+					for (int b = 0; b <= a; b++) acc[a * (a + 1) / 2 + b] = fmaf(sd[a], sd[b], acc[a * (a + 1) / 2 + b]);
+				}
+				acc[NSETUP - 1] = fmaf(f, f, acc[NSETUP - 1]);
+			}
+#pragma unroll
+			for (int k = 0; k < NSETUP; k++) {
+				float v = warp_sum(acc[k]);
+				if (lane == 0) sh.part[warp][k] = v;
+			}
+		}
+		__syncthreads();
+		if (tid < NSETUP) {
+			float t = 0.f;
+			for (int i = 0; i < ICGN3D_WARPS; i++) t += sh.part[i][tid];
+			sh.tot[tid] = t;
+		}
+		__syncthreads();
+		if (tid == 0) {
+			float Hh[NH3];
+#pragma unroll
+			for (int k = 0; k < NH3; k++) Hh[k] = sh.tot[k];
+			cholesky_packed<NP3>(Hh);
+#pragma unroll
+			for (int k = 0; k < NH3; k++) sh.L[k] = Hh[k];
+			for (int k = 0; k < NP3; k++) { sh.S[k] = sh.tot[NH3 + k]; sh.SF[k] = sh.tot[NH3 + NP3 + k]; }
+			sh.f2 = sh.tot[NSETUP - 1];
+			// initial warp (Deformation3D1::setWarp, src/oc_deformation.cpp:495-516)
+			sh.A[0] = 1.f + P[P3_DEF + 1]; sh.A[1] = P[P3_DEF + 2]; sh.A[2] = P[P3_DEF + 3]; sh.A[3] = u_in;
+			sh.A[4] = P[P3_DEF + 5]; sh.A[5] = 1.f + P[P3_DEF + 6]; sh.A[6] = P[P3_DEF + 7]; sh.A[7] = v_in;
+			sh.A[8] = P[P3_DEF + 9]; sh.A[9] = P[P3_DEF + 10]; sh.A[10] = 1.f + P[P3_DEF + 11]; sh.A[11] = w_in;
+		}
+		__syncthreads();
+
+		// ---- IC-GN iterations (src/oc_icgn.cpp:1355-1447)
+		const float xmax = (float)(dx - 2), ymax = (float)(dy - 2), zmax = (float)(dz - 2);
+		int iteration = 0;
+		bool left_image = false;
+		while (true) {
+			iteration++;
+			float A[12];
+#pragma unroll
+			for (int k = 0; k < 12; k++) A[k] = sh.A[k];
+			float acc[NITER];
+#pragma unroll
+			for (int k = 0; k < NITER; k++) acc[k] = 0.f;
+			int invalid = 0;
+			for (int i = tid; i < N; i += ICGN3D_THREADS) {
+				const int ii = i / slice, rem = i - ii * slice, j = rem / sx, k = rem - j * sx;
+				const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
+				// Deformation3D1::warp, src/oc_deformation.cpp:518-530; centre + warped (:1376)
+				const float X = px + fmaf(A[0], xl, fmaf(A[1], yl, fmaf(A[2], zl, A[3])));
+				const float Y = py + fmaf(A[4], xl, fmaf(A[5], yl, fmaf(A[6], zl, A[7])));
+				const float Z = pz + fmaf(A[8], xl, fmaf(A[9], yl, fmaf(A[10], zl, A[11])));
+				// TricubicBspline::compute validity, src/oc_cubic_bspline.cpp:356-361
+				const bool ok = (X >= 1.f) && (Y >= 1.f) && (Z >= 1.f) && (X < xmax) && (Y < ymax) && (Z < zmax);
+				if (!ok) {
+					invalid = 1;
+					continue;
+				}
+				const float t = tricubic_sample(img.coef, dx, dy, X, Y, Z);
+				const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
+				const float f = __ldg(img.ref + o) - ref_mean;
+				const float d = (t - ref_mean) - f;
+				acc[0] += d;
+				acc[1] = fmaf(d, d, acc[1]);
+				acc[2] = fmaf(f, d, acc[2]);
+				const float gxd = __ldg(img.gx + o) * d, gyd = __ldg(img.gy + o) * d, gzd = __ldg(img.gz + o) * d;
+				acc[3] += gxd; acc[4] = fmaf(gxd, xl, acc[4]); acc[5] = fmaf(gxd, yl, acc[5]); acc[6] = fmaf(gxd, zl, acc[6]);
+				acc[7] += gyd; acc[8] = fmaf(gyd, xl, acc[8]); acc[9] = fmaf(gyd, yl, acc[9]); acc[10] = fmaf(gyd, zl, acc[10]);
+				acc[11] += gzd; acc[12] = fmaf(gzd, xl, acc[12]); acc[13] = fmaf(gzd, yl, acc[13]); acc[14] = fmaf(gzd, zl, acc[14]);
+			}
+#pragma unroll
+			for (int k = 0; k < NITER; k++) {
+				float v = warp_sum(acc[k]);
+				if (lane == 0) sh.part[warp][k] = v;
+			}
+			if (__syncthreads_or(invalid)) { // src/oc_icgn.cpp:1386-1390
+				left_image = true;
+				break;
+			}
+			if (tid == 0) {
+				float tot[NITER];
+#pragma unroll
+				for (int k = 0; k < NITER; k++) {
+					float t = 0.f;
+					for (int i = 0; i < ICGN3D_WARPS; i++) t += sh.part[i][k];
+					tot[k] = t;
+				}
+				const float f2 = sh.f2;
+				const float d1 = tot[0], d2 = tot[1], fd = tot[2];
+				const float dbar = d1 * inv_n;
+				const float g2 = f2 + 2.f * fd + (d2 - d1 * dbar);
+				const float ref_norm = sqrtf(f2), tar_norm = sqrtf(g2);
+				const float factor = ref_norm / tar_norm;
+				sh.zncc = (f2 + fd) / (ref_norm * tar_norm);
+				float b[NP3], dp[NP3], Lr[NH3];
+#pragma unroll
+				for (int k = 0; k < NP3; k++) b[k] = factor * (sh.SF[k] + tot[3 + k] - dbar * sh.S[k]) - sh.SF[k];
+#pragma unroll
+				for (int k = 0; k < NH3; k++) Lr[k] = sh.L[k];
+				cholesky_solve<NP3>(Lr, b, dp);
+				// W <- W * W(dp)^-1 (src/oc_icgn.cpp:1439): affine 4x4, inverse = [B^-1 | -B^-1 t]
+				const float m00 = 1.f + dp[1], m01 = dp[2], m02 = dp[3], t0 = dp[0];
+				const float m10 = dp[5], m11 = 1.f + dp[6], m12 = dp[7], t1 = dp[4];
+				const float m20 = dp[9], m21 = dp[10], m22 = 1.f + dp[11], t2 = dp[8];
+				const float c00 = m11 * m22 - m12 * m21, c01 = m12 * m20 - m10 * m22, c02 = m10 * m21 - m11 * m20;
+				const float det = m00 * c00 + m01 * c01 + m02 * c02;
+				const float id = 1.0f / det;
+				float I[9];
+				I[0] = c00 * id; I[1] = (m02 * m21 - m01 * m22) * id; I[2] = (m01 * m12 - m02 * m11) * id;
+				I[3] = c01 * id; I[4] = (m00 * m22 - m02 * m20) * id; I[5] = (m02 * m10 - m00 * m12) * id;
+				I[6] = c02 * id; I[7] = (m01 * m20 - m00 * m21) * id; I[8] = (m00 * m11 - m01 * m10) * id;
+				const float it0 = -(I[0] * t0 + I[1] * t1 + I[2] * t2);
+				const float it1 = -(I[3] * t0 + I[4] * t1 + I[5] * t2);
+				const float it2 = -(I[6] * t0 + I[7] * t1 + I[8] * t2);
+#pragma unroll
+				for (int r = 0; r < 3; r++) {
+					const float a0 = sh.A[r * 4 + 0], a1 = sh.A[r * 4 + 1], a2 = sh.A[r * 4 + 2], a3 = sh.A[r * 4 + 3];
+					sh.A[r * 4 + 0] = a0 * I[0] + a1 * I[3] + a2 * I[6];
+					sh.A[r * 4 + 1] = a0 * I[1] + a1 * I[4] + a2 * I[7];
+					sh.A[r * 4 + 2] = a0 * I[2] + a1 * I[5] + a2 * I[8];
+					sh.A[r * 4 + 3] = a0 * it0 + a1 * it1 + a2 * it2 + a3;
+				}
+				const float dn = sqrtf(dp[0] * dp[0] + dp[4] * dp[4] + dp[8] * dp[8]); // translation only, :1445
+				sh.dp_norm = dn;
+				sh.keep_going = ((float)iteration < stop_condition && dn >= conv_criterion) ? 1 : 0;
+			}
+			__syncthreads();
+			if (!sh.keep_going) break;
+		}
+		if (left_image) {
+			if (tid == 0) P[P3_ZNCC] = -3.f;
+			__syncthreads();
+			continue;
+		}
+		// ---- results, src/oc_icgn.cpp:1450-1489
+		if (tid == 0) {
+			const float u = sh.A[3], v = sh.A[7], wv = sh.A[11];
+			P[P3_DEF + 0] = u; P[P3_DEF + 1] = sh.A[0] - 1.f; P[P3_DEF + 2] = sh.A[1]; P[P3_DEF + 3] = sh.A[2];
+			P[P3_DEF + 4] = v; P[P3_DEF + 5] = sh.A[4]; P[P3_DEF + 6] = sh.A[5] - 1.f; P[P3_DEF + 7] = sh.A[6];
+			P[P3_DEF + 8] = wv; P[P3_DEF + 9] = sh.A[8]; P[P3_DEF + 10] = sh.A[9]; P[P3_DEF + 11] = sh.A[10] - 1.f;
+			P[P3_U0] = u_in; P[P3_V0] = v_in; P[P3_W0] = w_in;
+			float zout = sh.zncc;
+			const float dn = sh.dp_norm;
+			P[P3_ITER] = (float)iteration;
+			P[P3_CONV] = dn;
+			P[P3_RX] = (float)rx; P[P3_RY] = (float)ry; P[P3_RZ] = (float)rz;
+			if (dn >= conv_criterion && (float)iteration >= stop_condition) zout = -4.f;
+			if (is_nan_f(zout) || is_nan_f(u) || is_nan_f(v) || is_nan_f(wv)) {
+				P[P3_DEF + 0] = u_in; P[P3_DEF + 4] = v_in; P[P3_DEF + 8] = w_in;
+				zout = -5.f;
+			}
+			P[P3_ZNCC] = zout;
+		}
+		__syncthreads();
+	}
+}
+
+int icgn3d1_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, int rz, float conv, float stop, int sm_count,
+	cudaStream_t stream, cudaError_t* err) {
+	long long grid = (long long)sm_count * 4;
+	if (grid > (long long)n) grid = (long long)n;
+	if (grid < 1) grid = 1;
+	icgn3d1_kernel<<<(int)grid, ICGN3D_THREADS, 0, stream>>>(img, d_pois, (int)n, rx, ry, rz, conv, stop);
+	*err = cudaGetLastError();
+	return *err == cudaSuccess ? 0 : -2;
+}
+
+} // namespace ocb

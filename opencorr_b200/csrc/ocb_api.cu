@@ -1,0 +1,461 @@
+// ocb_api.cu -- host side of the C ABI declared in include/opencorr_b200.h.
+// Owns the per-GPU context (device images, DVC tables, FFT twiddles/scratch, POI staging buffer)
+// and forwards to the sm_100a kernels.  No CPU compute path exists here by design.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/opencorr_b200.h"
+#include "ocb_kernels.h"
+
+namespace ocb {
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int w, int h) {
+	// in: column-major [w][h] (element (r,c) at c*h + r)  ->  out: row-major [h][w]
+	__shared__ float t[32][33];
+	const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+	for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+		const int c = c0 + j, r = r0 + threadIdx.x;
+		if (c < w && r < h) t[j][threadIdx.x] = in[(size_t)c * h + r];
+	}
+	__syncthreads();
+	for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+		const int r = r0 + j, c = c0 + threadIdx.x;
+		if (c < w && r < h) out[(size_t)r * w + c] = t[threadIdx.x][j];
+	}
+}
+} // namespace ocb
+
+static thread_local std::string g_last_error = "";
+
+struct ocb_ctx {
+	int device = 0;
+	int sm_count = 0;
+	size_t smem_optin = 0;
+	cudaStream_t own_stream = nullptr;
+	cudaStream_t stream = nullptr;
+	std::string last_error;
+	long long launches = 0;
+
+	// 2D images
+	float* own_ref2 = nullptr;
+	float* own_tar2 = nullptr;
+	size_t own2_elems = 0;
+	ocb::Image2D img2{ nullptr, nullptr, 0, 0 };
+	bool prepared2 = false;
+
+	// 3D images + tables
+	float* own_ref3 = nullptr;
+	float* own_tar3 = nullptr;
+	size_t own3_elems = 0;
+	float* tab3[4] = { nullptr, nullptr, nullptr, nullptr }; // gx gy gz coef
+	float* tmp3 = nullptr;
+	size_t tab3_elems = 0;
+	ocb::Image3D img3{ nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0 };
+	bool prepared3 = false;
+
+	// FFT
+	std::map<int, float2*> twiddles;
+	float2* fft_scratch = nullptr;
+	size_t fft_scratch_elems = 0;
+
+	// POI staging
+	float* d_poi = nullptr;
+	size_t d_poi_bytes = 0;
+};
+
+static int set_error(ocb_ctx* ctx, int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	if (ctx) ctx->last_error = buf;
+	return code;
+}
+
+#define OCB_CUDA(ctx, call)                                                                                   \
+	do {                                                                                                      \
+		cudaError_t e_ = (call);                                                                              \
+		if (e_ != cudaSuccess) return set_error(ctx, OCB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+static int ensure_device(ocb_ctx* ctx) {
+	OCB_CUDA(ctx, cudaSetDevice(ctx->device));
+	return OCB_OK;
+}
+
+static int get_twiddles(ocb_ctx* ctx, int n, const float2** out) {
+	auto it = ctx->twiddles.find(n);
+	if (it != ctx->twiddles.end()) {
+		*out = it->second;
+		return OCB_OK;
+	}
+	std::vector<float2> h(n);
+	for (int k = 0; k < n; k++) {
+		double a = -2.0 * M_PI * (double)k / (double)n;
+		h[k] = make_float2((float)cos(a), (float)sin(a));
+	}
+	float2* d = nullptr;
+	OCB_CUDA(ctx, cudaMalloc(&d, sizeof(float2) * n));
+	OCB_CUDA(ctx, cudaMemcpy(d, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+	ctx->twiddles[n] = d;
+	*out = d;
+	return OCB_OK;
+}
+
+static int stage_pois(ocb_ctx* ctx, const void* host, size_t bytes) {
+	if (bytes > ctx->d_poi_bytes) {
+		if (ctx->d_poi) cudaFree(ctx->d_poi);
+		ctx->d_poi = nullptr;
+		ctx->d_poi_bytes = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->d_poi, bytes));
+		ctx->d_poi_bytes = bytes;
+	}
+	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_poi, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return OCB_OK;
+}
+
+static int unstage_pois(ocb_ctx* ctx, void* host, size_t bytes) {
+	OCB_CUDA(ctx, cudaMemcpyAsync(host, ctx->d_poi, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return OCB_OK;
+}
+
+extern "C" {
+
+int ocb_device_count(void) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) return set_error(nullptr, OCB_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+	return n;
+}
+
+ocb_ctx* ocb_create(int device) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		set_error(nullptr, OCB_ERR_CUDA, "no usable CUDA device (%s); this engine has no CPU fallback",
+			e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+		return nullptr;
+	}
+	if (device < 0 || device >= n) {
+		set_error(nullptr, OCB_ERR_ARG, "device %d out of range [0,%d)", device, n);
+		return nullptr;
+	}
+	ocb_ctx* ctx = new ocb_ctx;
+	ctx->device = device;
+	cudaDeviceProp prop;
+	if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess
+		|| (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+		set_error(nullptr, OCB_ERR_CUDA, "context creation on device %d failed: %s", device, cudaGetErrorString(e));
+		delete ctx;
+		return nullptr;
+	}
+	if (prop.major < 10) {
+		set_error(nullptr, OCB_ERR_CUDA, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+		cudaStreamDestroy(ctx->own_stream);
+		delete ctx;
+		return nullptr;
+	}
+	ctx->stream = ctx->own_stream;
+	ctx->sm_count = prop.multiProcessorCount;
+	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	return ctx;
+}
+
+void ocb_destroy(ocb_ctx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(ctx->own_ref2);
+	cudaFree(ctx->own_tar2);
+	cudaFree(ctx->own_ref3);
+	cudaFree(ctx->own_tar3);
+	for (int i = 0; i < 4; i++) cudaFree(ctx->tab3[i]);
+	cudaFree(ctx->tmp3);
+	for (auto& kv : ctx->twiddles) cudaFree(kv.second);
+	cudaFree(ctx->fft_scratch);
+	cudaFree(ctx->d_poi);
+	cudaStreamDestroy(ctx->own_stream);
+	delete ctx;
+}
+
+const char* ocb_last_error(const ocb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+int ocb_set_stream(ocb_ctx* ctx, void* cuda_stream) {
+	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+	return OCB_OK;
+}
+
+int ocb_sync(ocb_ctx* ctx) {
+	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return OCB_OK;
+}
+
+long long ocb_launch_count(const ocb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- images ----------------------------------------------------------------------------------
+int ocb_set_images_2d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int width, int height) {
+	if (!ctx || !d_ref || !d_tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d: bad arguments");
+	ctx->img2 = ocb::Image2D{ d_ref, d_tar, width, height };
+	ctx->prepared2 = false;
+	return OCB_OK;
+}
+
+int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int width, int height, int col_major) {
+	if (!ctx || !ref || !tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d: bad arguments");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const size_t elems = (size_t)width * height;
+	if (elems > ctx->own2_elems) {
+		cudaFree(ctx->own_ref2);
+		cudaFree(ctx->own_tar2);
+		ctx->own_ref2 = ctx->own_tar2 = nullptr;
+		ctx->own2_elems = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_ref2, elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_tar2, elems * sizeof(float)));
+		ctx->own2_elems = elems;
+	}
+	if (!col_major) {
+		OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_ref2, ref, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_tar2, tar, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	} else {
+		float* tmp = nullptr;
+		OCB_CUDA(ctx, cudaMalloc(&tmp, elems * sizeof(float)));
+		dim3 grid((width + 31) / 32, (height + 31) / 32), block(32, 8);
+		const float* src[2] = { ref, tar };
+		float* dst[2] = { ctx->own_ref2, ctx->own_tar2 };
+		for (int i = 0; i < 2; i++) {
+			OCB_CUDA(ctx, cudaMemcpyAsync(tmp, src[i], elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+			ocb::transpose_kernel<<<grid, block, 0, ctx->stream>>>(tmp, dst[i], width, height);
+			ctx->launches++;
+		}
+		OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(tmp);
+	}
+	return ocb_set_images_2d_dev(ctx, ctx->own_ref2, ctx->own_tar2, width, height);
+}
+
+int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int dim_x, int dim_y, int dim_z) {
+	if (!ctx || !d_ref || !d_tar || dim_x < 15 || dim_y < 15 || dim_z < 15) // TricubicBspline needs >= 15 (src/oc_cubic_bspline.cpp:201)
+		return set_error(ctx, OCB_ERR_ARG, "set_images_3d: bad arguments (each dimension must be >= 15)");
+	ctx->img3 = ocb::Image3D{ d_ref, d_tar, nullptr, nullptr, nullptr, nullptr, dim_x, dim_y, dim_z };
+	ctx->prepared3 = false;
+	return OCB_OK;
+}
+
+int ocb_set_images_3d(ocb_ctx* ctx, const float* ref, const float* tar, int dim_x, int dim_y, int dim_z) {
+	if (!ctx || !ref || !tar || dim_x < 15 || dim_y < 15 || dim_z < 15)
+		return set_error(ctx, OCB_ERR_ARG, "set_images_3d: bad arguments (each dimension must be >= 15)");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const size_t elems = (size_t)dim_x * dim_y * dim_z;
+	if (elems > ctx->own3_elems) {
+		cudaFree(ctx->own_ref3);
+		cudaFree(ctx->own_tar3);
+		ctx->own_ref3 = ctx->own_tar3 = nullptr;
+		ctx->own3_elems = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_ref3, elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_tar3, elems * sizeof(float)));
+		ctx->own3_elems = elems;
+	}
+	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_ref3, ref, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_tar3, tar, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	return ocb_set_images_3d_dev(ctx, ctx->own_ref3, ctx->own_tar3, dim_x, dim_y, dim_z);
+}
+
+// ---- FFT-CC ----------------------------------------------------------------------------------
+int ocb_fftcc2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry) {
+	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: bad arguments");
+	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "fftcc2d: images not set");
+	if (n == 0) return OCB_OK;
+	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: too many POIs in one call");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	ocb::FftAxis ax, ay;
+	if (!ocb::fft_plan_axis(2 * rx, &ax) || !ocb::fft_plan_axis(2 * ry, &ay))
+		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc2d: window size %dx%d has a prime factor > 31", 2 * rx, 2 * ry);
+	if (ocb::fftcc2d_smem_bytes(rx, ry) > ctx->smem_optin)
+		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc2d: %dx%d window needs %zu B of shared memory (> %zu)", 2 * rx, 2 * ry,
+			ocb::fftcc2d_smem_bytes(rx, ry), ctx->smem_optin);
+	const float2 *twx, *twy;
+	int rc;
+	if ((rc = get_twiddles(ctx, 2 * rx, &twx)) || (rc = get_twiddles(ctx, 2 * ry, &twy))) return rc;
+	cudaError_t err;
+	if (ocb::fftcc2d_launch(ctx->img2, (float*)d_poi2d, n, rx, ry, ax, ay, twx, twy, ctx->sm_count, ctx->stream, &err))
+		return set_error(ctx, OCB_ERR_CUDA, "fftcc2d launch failed: %s", cudaGetErrorString(err));
+	ctx->launches++;
+	return OCB_OK;
+}
+
+int ocb_fftcc2d(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry) {
+	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
+	if ((rc = ocb_fftcc2d_dev(ctx, ctx->d_poi, n, rx, ry))) return rc;
+	return unstage_pois(ctx, poi2d, bytes);
+}
+
+int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz) {
+	if (!ctx || (!d_poi3d && n) || rx < 1 || ry < 1 || rz < 1) return set_error(ctx, OCB_ERR_ARG, "fftcc3d: bad arguments");
+	if (!ctx->img3.ref) return set_error(ctx, OCB_ERR_STATE, "fftcc3d: images not set");
+	if (n == 0) return OCB_OK;
+	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "fftcc3d: too many POIs in one call");
+	if ((size_t)8 * rx * ry * rz > 0x7fffffffull) return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc3d: window too large");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	ocb::FftAxis ax, ay, az;
+	if (!ocb::fft_plan_axis(2 * rx, &ax) || !ocb::fft_plan_axis(2 * ry, &ay) || !ocb::fft_plan_axis(2 * rz, &az))
+		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc3d: window size has a prime factor > 31");
+	if (ocb::fftcc3d_smem_bytes(rx, ry, rz) > ctx->smem_optin)
+		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc3d: window needs %zu B of shared memory (> %zu)", ocb::fftcc3d_smem_bytes(rx, ry, rz),
+			ctx->smem_optin);
+	const float2 *twx, *twy, *twz;
+	int rc;
+	if ((rc = get_twiddles(ctx, 2 * rx, &twx)) || (rc = get_twiddles(ctx, 2 * ry, &twy)) || (rc = get_twiddles(ctx, 2 * rz, &twz))) return rc;
+	int grid = ocb::fftcc3d_grid(rx, ry, rz, ctx->sm_count);
+	if ((size_t)grid > n) grid = (int)n;
+	const size_t need = (size_t)grid * 8 * rx * ry * rz;
+	if (need > ctx->fft_scratch_elems) {
+		OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->fft_scratch);
+		ctx->fft_scratch = nullptr;
+		ctx->fft_scratch_elems = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->fft_scratch, need * sizeof(float2)));
+		ctx->fft_scratch_elems = need;
+	}
+	cudaError_t err;
+	if (ocb::fftcc3d_launch(ctx->img3, (float*)d_poi3d, n, rx, ry, rz, ax, ay, az, twx, twy, twz, ctx->fft_scratch, grid, ctx->stream, &err))
+		return set_error(ctx, OCB_ERR_CUDA, "fftcc3d launch failed: %s", cudaGetErrorString(err));
+	ctx->launches++;
+	return OCB_OK;
+}
+
+int ocb_fftcc3d(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz) {
+	if (!ctx || (!poi3d && n)) return set_error(ctx, OCB_ERR_ARG, "fftcc3d: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * OCB_POI3D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi3d, bytes))) return rc;
+	if ((rc = ocb_fftcc3d_dev(ctx, ctx->d_poi, n, rx, ry, rz))) return rc;
+	return unstage_pois(ctx, poi3d, bytes);
+}
+
+// ---- IC-GN -----------------------------------------------------------------------------------
+int ocb_icgn2d_prepare(ocb_ctx* ctx) {
+	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "icgn2d_prepare: images not set");
+	ctx->prepared2 = true; // gradients and bicubic weights are recomputed on chip per POI
+	return OCB_OK;
+}
+
+static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop) {
+	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
+	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "icgn2d: images not set");
+	if (!ctx->prepared2) return set_error(ctx, OCB_ERR_STATE, "icgn2d: prepare() has not been called since setImages()");
+	if (n == 0) return OCB_OK;
+	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "icgn2d: too many POIs in one call");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	cudaError_t err = cudaSuccess;
+	int rc = ocb::icgn2d_launch(np, ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+	if (rc == -1) return set_error(ctx, OCB_ERR_UNSUPPORTED, "icgn2d: subset radius (%d,%d) exceeds the shared-memory design limit", rx, ry);
+	if (rc) return set_error(ctx, OCB_ERR_CUDA, "icgn2d launch failed: %s", cudaGetErrorString(err));
+	ctx->launches++;
+	return OCB_OK;
+}
+
+int ocb_icgn2d1_dev(ocb_ctx* ctx, void* d, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_dev(ctx, 6, d, n, rx, ry, conv, stop); }
+int ocb_icgn2d2_dev(ocb_ctx* ctx, void* d, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_dev(ctx, 12, d, n, rx, ry, conv, stop); }
+
+static int icgn2d_host(ocb_ctx* ctx, int np, void* poi2d, size_t n, int rx, int ry, float conv, float stop) {
+	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
+	if ((rc = icgn2d_dev(ctx, np, ctx->d_poi, n, rx, ry, conv, stop))) return rc;
+	return unstage_pois(ctx, poi2d, bytes);
+}
+int ocb_icgn2d1(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 6, p, n, rx, ry, conv, stop); }
+int ocb_icgn2d2(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 12, p, n, rx, ry, conv, stop); }
+
+int ocb_icgn3d_prepare(ocb_ctx* ctx) {
+	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	if (!ctx->img3.ref) return set_error(ctx, OCB_ERR_STATE, "icgn3d_prepare: images not set");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const int dx = ctx->img3.dx, dy = ctx->img3.dy, dz = ctx->img3.dz;
+	const size_t elems = (size_t)dx * dy * dz;
+	if (elems > ctx->tab3_elems) {
+		for (int i = 0; i < 4; i++) { cudaFree(ctx->tab3[i]); ctx->tab3[i] = nullptr; }
+		cudaFree(ctx->tmp3);
+		ctx->tmp3 = nullptr;
+		ctx->tab3_elems = 0;
+		for (int i = 0; i < 4; i++) OCB_CUDA(ctx, cudaMalloc(&ctx->tab3[i], elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->tmp3, elems * sizeof(float)));
+		ctx->tab3_elems = elems;
+	}
+	ocb::gradient3d_launch(ctx->img3.ref, ctx->tab3[0], ctx->tab3[1], ctx->tab3[2], dx, dy, dz, ctx->sm_count, ctx->stream);
+	// TricubicBspline::prepare: x -> coefficient, y -> conv_buffer, z -> coefficient
+	ocb::prefilter3d_launch(ctx->img3.tar, ctx->tab3[3], dx, dy, dz, 0, ctx->sm_count, ctx->stream);
+	ocb::prefilter3d_launch(ctx->tab3[3], ctx->tmp3, dx, dy, dz, 1, ctx->sm_count, ctx->stream);
+	ocb::prefilter3d_launch(ctx->tmp3, ctx->tab3[3], dx, dy, dz, 2, ctx->sm_count, ctx->stream);
+	ctx->launches += 4;
+	OCB_CUDA(ctx, cudaGetLastError());
+	ctx->img3.gx = ctx->tab3[0];
+	ctx->img3.gy = ctx->tab3[1];
+	ctx->img3.gz = ctx->tab3[2];
+	ctx->img3.coef = ctx->tab3[3];
+	ctx->prepared3 = true;
+	return OCB_OK;
+}
+
+int ocb_icgn3d1_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz, float conv, float stop) {
+	if (!ctx || (!d_poi3d && n) || rx < 1 || ry < 1 || rz < 1) return set_error(ctx, OCB_ERR_ARG, "icgn3d1: bad arguments");
+	if (!ctx->img3.ref) return set_error(ctx, OCB_ERR_STATE, "icgn3d1: images not set");
+	if (!ctx->prepared3) return set_error(ctx, OCB_ERR_STATE, "icgn3d1: prepare() has not been called since setImages()");
+	if (n == 0) return OCB_OK;
+	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "icgn3d1: too many POIs in one call");
+	if ((size_t)(2 * rx + 1) * (2 * ry + 1) * (2 * rz + 1) > 0x3fffffffull) return set_error(ctx, OCB_ERR_UNSUPPORTED, "icgn3d1: subset too large");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	cudaError_t err = cudaSuccess;
+	if (ocb::icgn3d1_launch(ctx->img3, (float*)d_poi3d, n, rx, ry, rz, conv, stop, ctx->sm_count, ctx->stream, &err))
+		return set_error(ctx, OCB_ERR_CUDA, "icgn3d1 launch failed: %s", cudaGetErrorString(err));
+	ctx->launches++;
+	return OCB_OK;
+}
+
+int ocb_icgn3d1(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz, float conv, float stop) {
+	if (!ctx || (!poi3d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn3d1: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * OCB_POI3D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi3d, bytes))) return rc;
+	if ((rc = ocb_icgn3d1_dev(ctx, ctx->d_poi, n, rx, ry, rz, conv, stop))) return rc;
+	return unstage_pois(ctx, poi3d, bytes);
+}
+
+int ocb_get_tables_3d(ocb_ctx* ctx, float* gx, float* gy, float* gz, float* coefficient) {
+	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	if (!ctx->prepared3) return set_error(ctx, OCB_ERR_STATE, "get_tables_3d: prepare() has not been called");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const size_t bytes = (size_t)ctx->img3.dx * ctx->img3.dy * ctx->img3.dz * sizeof(float);
+	float* dst[4] = { gx, gy, gz, coefficient };
+	for (int i = 0; i < 4; i++)
+		if (dst[i]) OCB_CUDA(ctx, cudaMemcpyAsync(dst[i], ctx->tab3[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return OCB_OK;
+}
+
+} // extern "C"

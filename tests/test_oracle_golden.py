@@ -1,0 +1,86 @@
+"""Pins the CPU oracle (oracle/oc_oracle.cpp) to the reference's own regression fixtures:
+the result tables committed next to its example data.
+
+2D  examples/2d_dic/oht_cfrp_4_fftcc_icgn1_r16{,_deformation}.csv  (FFTCC2D -> ICGN2D1, r=16)
+DVC examples/dvc/al_foam4_1_fftcc_icgn1_r30.csv (reference CPU, stop=20) and
+    examples/dvc/al_foam4_1_fftcc_icgn1(gpu)_r30.csv (reference GPU DLL, stop=10)
+Fixtures: tests/golden/ (made by tests/golden/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle2D, Oracle3D
+from opencorr_b200 import make_poi2d, make_poi3d
+import util
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_2d_golden_table(exact):
+    ref, tar = util.oht_cfrp_pair()
+    g = util.oht_cfrp_golden()
+    tab, dtab = g["table"], g["deformation"]
+    q = make_poi2d(tab[:, 0:2])
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, 16, 16, exact=exact)
+    # integer-pixel initial guess: exact match required
+    fft_u0, fft_v0 = q[:, 2].copy(), q[:, 8].copy()
+    o.icgn2d1(q, 16, 16, 0.001, 10, exact=exact)
+    # the shipped table stores the FFT-CC result in u0, v0
+    mism = (q[:, 14] != tab[:, 4]) | (q[:, 15] != tab[:, 5])
+    assert mism.mean() < 0.002, "FFT-CC guess differs on %d POIs" % mism.sum()
+    assert np.array_equal(fft_u0, q[:, 14]) and np.array_equal(fft_v0, q[:, 15])
+    # The shipped table predates the -4 (not converged) code: its non-converged rows keep a ZNCC.
+    conv = (tab[:, 7] < 10) & ~mism
+    same_it = q[:, 17] == tab[:, 7]
+    assert (same_it | ~conv).mean() > 0.995
+    ok = conv & same_it
+    assert ok.sum() > 0.9 * len(tab)
+    d = np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max()
+    dz = np.abs(q[ok, 16] - tab[ok, 6]).max()
+    dg = np.abs(q[ok][:, [3, 4, 9, 10]] - dtab[ok][:, [3, 4, 6, 7]]).max()
+    assert d < 5e-5, d          # table is printed with 8 decimals
+    assert dz < 2e-6, dz
+    assert dg < 5e-6, dg
+    assert np.abs(q[ok, 18] - tab[ok, 8]).max() < 1e-4
+    # rows the reference left unconverged at iteration 10 carry -4 under the current source
+    nonconv = (tab[:, 7] >= 10) & (tab[:, 8] >= 0.001) & ~mism
+    assert np.all(q[nonconv & (q[:, 17] >= 10), 16] == -4)
+
+
+def test_dvc_golden_tables():
+    ref, tar, z0, cpu, gpu = util.al_foam_crop()
+    xyz = cpu[:, 0:3].copy()
+    xyz[:, 2] -= z0
+    sel = np.arange(0, len(xyz), 7)  # 28 POIs keep the CPU suite short
+    for exact, tab, zc, itc, tol_d, tol_z in ((0, cpu, 9, 10, 5e-6, 1e-6), (1, gpu, 9, 10, 5e-6, 2e-6)):
+        q = make_poi3d(xyz[sel])
+        o = Oracle3D(ref, tar)
+        o.fftcc3d(q, 30, 30, 30, exact=exact)
+        o.icgn3d1(q, 30, 30, 30, 0.001, 20 if exact == 0 else 10, exact=exact)
+        t = tab[sel]
+        assert np.array_equal(q[:, 15:18], t[:, 6:9]), "FFT-CC guess differs"
+        same = q[:, 19] == t[:, itc]
+        assert same.all()
+        d = np.abs(q[:, [3, 7, 11]] - t[:, 3:6]).max()
+        dz = np.abs(q[:, 18] - t[:, zc]).max()
+        assert d < tol_d, (exact, d)
+        assert dz < tol_z, (exact, dz)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples/2d_dic"), reason="reference checkout not mounted")
+def test_2d_full_table_against_reference_checkout():
+    """All 30 000 POIs of the shipped table (only where the reference checkout is available)."""
+    tab = np.genfromtxt("/root/reference/examples/2d_dic/oht_cfrp_4_fftcc_icgn1_r16.csv", delimiter=",", skip_header=1)
+    ref, tar = util.oht_cfrp_pair()
+    q = make_poi2d(tab[:, 0:2])
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, 16, 16)
+    o.icgn2d1(q, 16, 16, 0.001, 10)
+    guess_same = (q[:, 14] == tab[:, 4]) & (q[:, 15] == tab[:, 5])
+    assert guess_same.mean() > 0.9995
+    ok = guess_same & (tab[:, 7] < 10) & (q[:, 17] == tab[:, 7])
+    assert ok.sum() >= 28000
+    assert np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max() < 5e-5
+    assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 2e-6

@@ -1,0 +1,79 @@
+"""Shared helpers for the test-suite (not product code)."""
+import os
+import struct
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def read_bmp8(path):
+    """8-bit palettised BMP with identity grey palette -> float32 [h, w] (== cv::imread GRAYSCALE
+    for the reference's example images)."""
+    b = open(path, "rb").read()
+    assert b[:2] == b"BM"
+    off = struct.unpack("<I", b[10:14])[0]
+    w, h = struct.unpack("<ii", b[18:26])
+    bpp = struct.unpack("<H", b[28:30])[0]
+    assert bpp == 8
+    stride = (w + 3) // 4 * 4
+    a = np.frombuffer(b, dtype=np.uint8, count=stride * abs(h), offset=off).reshape(abs(h), stride)[:, :w]
+    if h > 0:
+        a = a[::-1]
+    return np.ascontiguousarray(a).astype(np.float32)
+
+
+def oht_cfrp_pair():
+    return read_bmp8(os.path.join(GOLDEN, "oht_cfrp_0.bmp")), read_bmp8(os.path.join(GOLDEN, "oht_cfrp_4.bmp"))
+
+
+def oht_cfrp_golden():
+    return np.load(os.path.join(GOLDEN, "oht_cfrp_4_fftcc_icgn1_r16.npz"))
+
+
+def al_foam_crop():
+    d = np.load(os.path.join(GOLDEN, "al_foam4_crop.npz"))
+    return d["ref"].astype(np.float32), d["tar"].astype(np.float32), int(d["z_offset"]), d["cpu_table"], d["gpu_table"]
+
+
+def compare_2d(a, b, label="", tol_disp=1e-4, tol_zncc=1e-5, max_iter_mismatch_frac=0.01, order=1):
+    """a, b: POI2D arrays [n,25].  Sentinel codes and integer outputs must agree exactly on every POI;
+    displacement/ZNCC tolerances (north_star: 1e-4 px, 1e-5) apply to POIs whose iteration counts
+    agree; POIs whose ||dp|| sits within float noise of the convergence threshold may differ by one
+    iteration and are counted, bounded by max_iter_mismatch_frac (SURVEY.md section 7 'Iteration-count parity')."""
+    assert a.shape == b.shape
+    za, zb = a[:, 16], b[:, 16]
+    neg_a, neg_b = za < 0, zb < 0
+    it_same = a[:, 17] == b[:, 17]
+    # sentinel parity: same failure code, except -4 flips that come with an iteration flip at `stop`
+    code_mismatch = (neg_a | neg_b) & (za != zb) & ~(((za == -4) | (zb == -4)) & ~it_same)
+    assert not code_mismatch.any(), "%s sentinel mismatch at %s: %s vs %s" % (
+        label, np.where(code_mismatch)[0][:10], za[code_mismatch][:10], zb[code_mismatch][:10])
+    assert np.array_equal(a[:, 14:16], b[:, 14:16]), label + " u0/v0 differ"
+    ok = ~neg_a & ~neg_b & it_same
+    frac = 1.0 - it_same.mean() if len(a) else 0.0
+    assert frac <= max_iter_mismatch_frac, "%s iteration mismatch fraction %.4f" % (label, frac)
+    cols = [2, 8] if order == 1 else [2, 8]
+    d = np.abs(a[ok][:, cols] - b[ok][:, cols]).max() if ok.any() else 0.0
+    dz = np.abs(za[ok] - zb[ok]).max() if ok.any() else 0.0
+    assert d <= tol_disp, "%s max |du,dv| = %.3g > %.3g" % (label, d, tol_disp)
+    assert dz <= tol_zncc, "%s max |dZNCC| = %.3g > %.3g" % (label, dz, tol_zncc)
+    return dict(n=len(a), n_compared=int(ok.sum()), iter_mismatch_frac=float(frac), max_disp=float(d), max_zncc=float(dz))
+
+
+def compare_3d(a, b, label="", tol_disp=1e-4, tol_zncc=1e-5, max_iter_mismatch_frac=0.01):
+    assert a.shape == b.shape
+    za, zb = a[:, 18], b[:, 18]
+    neg_a, neg_b = za < 0, zb < 0
+    it_same = a[:, 19] == b[:, 19]
+    code_mismatch = (neg_a | neg_b) & (za != zb) & ~(((za == -4) | (zb == -4)) & ~it_same)
+    assert not code_mismatch.any(), "%s sentinel mismatch at %s" % (label, np.where(code_mismatch)[0][:10])
+    assert np.array_equal(a[:, 15:18], b[:, 15:18]), label + " u0/v0/w0 differ"
+    ok = ~neg_a & ~neg_b & it_same
+    frac = 1.0 - it_same.mean() if len(a) else 0.0
+    assert frac <= max_iter_mismatch_frac, "%s iteration mismatch fraction %.4f" % (label, frac)
+    d = np.abs(a[ok][:, [3, 7, 11]] - b[ok][:, [3, 7, 11]]).max() if ok.any() else 0.0
+    dz = np.abs(za[ok] - zb[ok]).max() if ok.any() else 0.0
+    assert d <= tol_disp, "%s max |du,dv,dw| = %.3g > %.3g" % (label, d, tol_disp)
+    assert dz <= tol_zncc, "%s max |dZNCC| = %.3g > %.3g" % (label, dz, tol_zncc)
+    return dict(n=len(a), n_compared=int(ok.sum()), iter_mismatch_frac=float(frac), max_disp=float(d), max_zncc=float(dz))
