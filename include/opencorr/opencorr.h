@@ -1,0 +1,749 @@
+/*
+ * opencorr.h -- API-compatible C++ shim for the FFT-CC -> IC-GN path of OpenCorr, running on the
+ * B200 engine behind include/opencorr_b200.h.  Header-only; link with -lopencorr_b200.
+ *
+ * It re-declares (same names, same signatures, same public members, same POI record layout) the
+ * part of the reference's `namespace opencorr` that examples/test_2d_dic_fftcc_icgn1.cpp and
+ * examples/test_dvc_fftcc_icgn1.cpp use, so that those two programs compile and run UNCHANGED:
+ *     Point2D / Point3D (+ operators)            reference src/oc_point.h:25-210
+ *     POI2D / POI3D and their unions             src/oc_poi.h:25-222
+ *     Image2D / Image3D                          src/oc_image.h:28-65 (file loading: 8-bit BMP, .bin)
+ *     DIC / DVC bases                            src/oc_dic.h:43-84
+ *     FFTCC2D / FFTCC3D                          src/oc_fftcc.h:56-90
+ *     ICGN2D1 / ICGN2D2 / ICGN3D1                src/oc_icgn.h:45-181
+ *     IO2D / IO3D (setters + the 4 writers used) src/oc_io.h:25-149, src/oc_io.cpp:318-504,1004-1089
+ * Nothing else of OpenCorr is provided (see DESIGN.md "out of scope").  No Eigen / OpenCV / FFTW.
+ *
+ * Error behaviour follows the reference: per-POI failures are sentinel ZNCC codes (src/oc_dic.h:28-34),
+ * per-call failures throw std::string (src/oc_icgn.cpp:65, src/oc_image.cpp:43).
+ */
+#pragma once
+#ifndef _OPENCORR_B200_SHIM_H_
+#define _OPENCORR_B200_SHIM_H_
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <iterator>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../opencorr_b200.h"
+
+namespace opencorr
+{
+	// ------------------------------------------------------------------ src/oc_point.h
+	class Point2D
+	{
+	public:
+		float x, y;
+		inline Point2D() { x = 0.f; y = 0.f; }
+		inline Point2D(float x, float y) { this->x = x; this->y = y; }
+		inline Point2D(int x, int y) { this->x = (float)x; this->y = (float)y; }
+		inline ~Point2D() {}
+		inline float vectorNorm() const { return std::sqrt(x * x + y * y); }
+		inline friend std::ostream& operator<<(std::ostream& output, const Point2D& point)
+		{
+			output << point.x << "," << point.y;
+			return output;
+		}
+	};
+	inline Point2D operator+(Point2D point, Point2D offset) { return Point2D(point.x + offset.x, point.y + offset.y); }
+	inline Point2D operator-(Point2D point, Point2D offset) { return point + Point2D(-offset.x, -offset.y); }
+	inline Point2D operator*(float factor, Point2D point) { return Point2D(factor * point.x, factor * point.y); }
+	inline Point2D operator*(int factor, Point2D point) { return float(factor) * point; }
+	inline Point2D operator*(Point2D point, float factor) { return factor * point; }
+	inline Point2D operator*(Point2D point, int factor) { return float(factor) * point; }
+	inline float operator*(Point2D point1, Point2D point2) { return (point1.x * point2.x + point1.y * point2.y); }
+	inline Point2D operator/(Point2D point, float factor) { return Point2D(point.x / factor, point.y / factor); }
+	inline Point2D operator/(Point2D point, int factor) { return point / float(factor); }
+	inline float operator/(Point2D point1, Point2D point2) { return (point1.x * point2.y - point1.y * point2.x); }
+
+	class Point3D
+	{
+	public:
+		float x, y, z;
+		inline Point3D() { x = 0.f; y = 0.f; z = 0.f; }
+		inline Point3D(float x, float y, float z) { this->x = x; this->y = y; this->z = z; }
+		inline Point3D(int x, int y, int z) { this->x = (float)x; this->y = (float)y; this->z = (float)z; }
+		inline ~Point3D() {}
+		inline float vectorNorm() const { return std::sqrt(x * x + y * y + z * z); }
+		inline friend std::ostream& operator<<(std::ostream& output, const Point3D& point)
+		{
+			output << point.x << "," << point.y << "," << point.z;
+			return output;
+		}
+	};
+	inline Point3D operator+(Point3D point, Point3D offset) { return Point3D(point.x + offset.x, point.y + offset.y, point.z + offset.z); }
+	inline Point3D operator-(Point3D point, Point3D offset) { return point + Point3D(-offset.x, -offset.y, -offset.z); }
+	inline Point3D operator*(float factor, Point3D point) { return Point3D(factor * point.x, factor * point.y, factor * point.z); }
+	inline Point3D operator*(int factor, Point3D point) { return float(factor) * point; }
+	inline Point3D operator*(Point3D point, float factor) { return factor * point; }
+	inline Point3D operator*(Point3D point, int factor) { return float(factor) * point; }
+	inline float operator*(Point3D point1, Point3D point2) { return (point1.x * point2.x + point1.y * point2.y + point1.z * point2.z); }
+	inline Point3D operator/(Point3D point, float factor) { return Point3D(point.x / factor, point.y / factor, point.z / factor); }
+	inline Point3D operator/(Point3D point, int factor) { return point / float(factor); }
+	inline Point3D operator/(Point3D point1, Point3D point2)
+	{
+		return Point3D((point1.y * point2.z - point1.z * point2.y), (point1.z * point2.x - point1.x * point2.z), (point1.x * point2.y - point1.y * point2.x));
+	}
+
+	// ------------------------------------------------------------------ src/oc_poi.h (wire format of the boundary)
+	union DeformationVector2D
+	{
+		struct { float u, ux, uy, uxx, uxy, uyy; float v, vx, vy, vxx, vxy, vyy; };
+		float p[12];
+	};
+	union StrainVector2D
+	{
+		struct { float exx, eyy, exy; };
+		float e[3];
+	};
+	union Result2D
+	{
+		struct { float u0, v0, zncc, iteration, convergence, feature; };
+		float r[6];
+	};
+	union DeformationVector3D
+	{
+		struct { float u, ux, uy, uz; float v, vx, vy, vz; float w, wx, wy, wz; };
+		float p[12];
+	};
+	union StrainVector3D
+	{
+		struct { float exx, eyy, ezz; float exy, eyz, ezx; };
+		float e[6];
+	};
+	union Result3D
+	{
+		struct { float u0, v0, w0, zncc, iteration, convergence, feature; };
+		float r[7];
+	};
+
+	class POI2D : public Point2D
+	{
+	public:
+		DeformationVector2D deformation;
+		Result2D result;
+		StrainVector2D strain;
+		Point2D subset_radius;
+		inline POI2D(int x, int y) : Point2D(x, y) { clear(); }
+		inline POI2D(float x, float y) : Point2D(x, y) { clear(); }
+		inline POI2D(Point2D location) : Point2D(location) { clear(); }
+		inline ~POI2D() {}
+		inline void clear()
+		{
+			std::fill(std::begin(deformation.p), std::end(deformation.p), 0.f);
+			std::fill(std::begin(result.r), std::end(result.r), 0.f);
+			std::fill(std::begin(strain.e), std::end(strain.e), 0.f);
+			subset_radius.x = 0.f;
+			subset_radius.y = 0.f;
+		}
+	};
+
+	class POI3D : public Point3D
+	{
+	public:
+		DeformationVector3D deformation;
+		Result3D result;
+		StrainVector3D strain;
+		Point3D subset_radius;
+		inline POI3D(int x, int y, int z) : Point3D(x, y, z) { clear(); }
+		inline POI3D(float x, float y, float z) : Point3D(x, y, z) { clear(); }
+		inline POI3D(Point3D location) : Point3D(location) { clear(); }
+		inline ~POI3D() {}
+		inline void clear()
+		{
+			std::fill(std::begin(deformation.p), std::end(deformation.p), 0.f);
+			std::fill(std::begin(result.r), std::end(result.r), 0.f);
+			std::fill(std::begin(strain.e), std::end(strain.e), 0.f);
+			subset_radius.x = 0.f;
+			subset_radius.y = 0.f;
+			subset_radius.z = 0.f;
+		}
+	};
+	static_assert(sizeof(POI2D) == OCB_POI2D_FLOATS * sizeof(float), "POI2D must be the 100-byte record of the C ABI");
+	static_assert(sizeof(POI3D) == OCB_POI3D_FLOATS * sizeof(float), "POI3D must be the 124-byte record of the C ABI");
+
+	// ------------------------------------------------------------------ src/oc_image.h
+	// Row-major float matrix standing in for the reference's Eigen::MatrixXf member `eg_mat`.
+	class MatrixXf
+	{
+	public:
+		int n_rows = 0, n_cols = 0;
+		std::vector<float> data; // row-major [rows][cols]
+		inline void resize(int rows, int cols) { n_rows = rows; n_cols = cols; data.assign((size_t)rows * cols, 0.f); }
+		inline float& operator()(int r, int c) { return data[(size_t)r * n_cols + c]; }
+		inline float operator()(int r, int c) const { return data[(size_t)r * n_cols + c]; }
+		inline int rows() const { return n_rows; }
+		inline int cols() const { return n_cols; }
+	};
+
+	class Image2D
+	{
+	public:
+		int height, width;
+		unsigned int size;
+		std::string file_path;
+		MatrixXf eg_mat;
+		unsigned long long generation = 0; // bumped on every load(); lets the engine know when to re-upload
+
+		inline Image2D(int width, int height)
+		{
+			eg_mat.resize(height, width);
+			this->width = width;
+			this->height = height;
+			size = height * width;
+		}
+		inline Image2D(std::string file_path) : height(0), width(0), size(0) { load(file_path); }
+		~Image2D() = default;
+
+		// cv::imread(path, IMREAD_GRAYSCALE) for what the reference's examples feed it: uncompressed
+		// 8-bit palettised / 24-bit / 32-bit BMP (src/oc_image.cpp:37-57).  Binary PGM (P5) is accepted too.
+		inline void load(std::string file_path)
+		{
+			std::ifstream in(file_path, std::ios::binary);
+			if (!in.is_open()) throw std::string("Fail to load file: " + file_path);
+			std::vector<unsigned char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+			if (buf.size() > 54 && buf[0] == 'B' && buf[1] == 'M') {
+				auto rd32 = [&](size_t o) { return (int32_t)(buf[o] | (buf[o + 1] << 8) | (buf[o + 2] << 16) | ((uint32_t)buf[o + 3] << 24)); };
+				auto rd16 = [&](size_t o) { return (int)(buf[o] | (buf[o + 1] << 8)); };
+				const int off = rd32(10), dib = rd32(14), w = rd32(18), hraw = rd32(22), bpp = rd16(28), comp = rd32(30);
+				const int h = hraw < 0 ? -hraw : hraw;
+				if (comp != 0 || (bpp != 8 && bpp != 24 && bpp != 32)) throw std::string("Fail to load file (unsupported BMP flavour): " + file_path);
+				const size_t stride = ((size_t)w * bpp / 8 + 3) / 4 * 4;
+				if (buf.size() < (size_t)off + stride * h) throw std::string("Fail to load file (truncated BMP): " + file_path);
+				float pal[256];
+				for (int i = 0; i < 256; i++) pal[i] = (float)i;
+				if (bpp == 8) {
+					int ncol = rd32(46);
+					if (ncol <= 0 || ncol > 256) ncol = 256;
+					const size_t po = 14 + (size_t)dib;
+					for (int i = 0; i < ncol && po + 4 * (size_t)i + 3 < buf.size(); i++) {
+						const float b = buf[po + 4 * i], g = buf[po + 4 * i + 1], r = buf[po + 4 * i + 2];
+						pal[i] = (b == g && g == r) ? b : std::floor(0.299f * r + 0.587f * g + 0.114f * b + 0.5f);
+					}
+				}
+				width = w; height = h; size = (unsigned int)(w * h);
+				eg_mat.resize(h, w);
+				for (int r = 0; r < h; r++) {
+					const unsigned char* row = &buf[(size_t)off + stride * (size_t)(hraw > 0 ? h - 1 - r : r)];
+					for (int c = 0; c < w; c++) {
+						if (bpp == 8) eg_mat(r, c) = pal[row[c]];
+						else {
+							const unsigned char* px = row + (size_t)c * (bpp / 8);
+							eg_mat(r, c) = std::floor(0.299f * px[2] + 0.587f * px[1] + 0.114f * px[0] + 0.5f);
+						}
+					}
+				}
+			} else if (buf.size() > 10 && buf[0] == 'P' && buf[1] == '5') {
+				size_t pos = 2;
+				int vals[3], nv = 0;
+				while (nv < 3 && pos < buf.size()) {
+					while (pos < buf.size() && (buf[pos] == ' ' || buf[pos] == '\n' || buf[pos] == '\r' || buf[pos] == '\t')) pos++;
+					if (pos < buf.size() && buf[pos] == '#') { while (pos < buf.size() && buf[pos] != '\n') pos++; continue; }
+					int v = 0;
+					while (pos < buf.size() && buf[pos] >= '0' && buf[pos] <= '9') v = v * 10 + (buf[pos++] - '0');
+					vals[nv++] = v;
+				}
+				pos++;
+				if (nv < 3 || vals[2] > 255 || buf.size() < pos + (size_t)vals[0] * vals[1]) throw std::string("Fail to load file (bad PGM): " + file_path);
+				width = vals[0]; height = vals[1]; size = (unsigned int)(width * height);
+				eg_mat.resize(height, width);
+				for (size_t i = 0; i < (size_t)width * height; i++) eg_mat.data[i] = (float)buf[pos + i];
+			} else {
+				throw std::string("Fail to load file: " + file_path);
+			}
+			this->file_path = file_path;
+			generation++;
+		}
+	};
+
+	class Image3D
+	{
+	public:
+		int dim_x, dim_y, dim_z;
+		unsigned long size;
+		std::string file_path;
+		float*** vol_mat = nullptr; // [z][y][x]; payload is one contiguous block at vol_mat[0][0] (src/oc_array.h:56-74)
+		unsigned long long generation = 0;
+
+		inline Image3D(int dim_x, int dim_y, int dim_z) { allocate(dim_x, dim_y, dim_z); }
+		inline Image3D(std::string file_path) : dim_x(0), dim_y(0), dim_z(0), size(0) { load(file_path); }
+		~Image3D() = default; // like the reference, the volume is released explicitly with release()
+
+		inline void allocate(int dx, int dy, int dz)
+		{
+			release();
+			dim_x = dx; dim_y = dy; dim_z = dz;
+			size = (unsigned long)dz * dy * dx;
+			float* p1 = (float*)calloc(size, sizeof(float));
+			float** p2 = (float**)malloc((size_t)dz * dy * sizeof(float*));
+			vol_mat = (float***)malloc((size_t)dz * sizeof(float**));
+			for (int i = 0; i < dz; i++) {
+				for (int j = 0; j < dy; j++) p2[(size_t)i * dy + j] = p1 + ((size_t)i * dy + j) * dx;
+				vol_mat[i] = p2 + (size_t)i * dy;
+			}
+			generation++;
+		}
+		// binary volume: int32[3] header (dim_x, dim_y, dim_z) + float32 payload (src/oc_image.cpp:76-110)
+		inline void loadBin(std::string file_path)
+		{
+			std::ifstream in(file_path, std::ios::in | std::ios::binary);
+			if (!in.is_open()) throw std::string("Failed to open bin file: " + file_path);
+			int dims[3];
+			in.read((char*)dims, sizeof(int) * 3);
+			allocate(dims[0], dims[1], dims[2]);
+			in.read((char*)**vol_mat, sizeof(float) * size);
+			if (!in) throw std::string("Failed to read bin file: " + file_path);
+		}
+		inline void load(std::string file_path)
+		{
+			this->file_path = file_path;
+			size_t dot_pos = file_path.find_last_of(".");
+			std::string ext = file_path.substr(dot_pos + 1);
+			if (ext == "bin" || ext == "BIN") loadBin(file_path);
+			else throw std::string("Only .bin volumes are supported by this build (multi-page TIFF needs OpenCV): " + file_path);
+		}
+		inline void release()
+		{
+			if (vol_mat != nullptr) {
+				free(vol_mat[0][0]);
+				free(vol_mat[0]);
+				free(vol_mat);
+				vol_mat = nullptr;
+			}
+		}
+	};
+
+	// ------------------------------------------------------------------ engine plumbing (not in the reference)
+	namespace b200
+	{
+		// One process-wide GPU context shared by every DIC/DVC object, so that FFTCC and ICGN objects
+		// set up on the same Image pair share ONE device copy (the reference's objects share the host
+		// Image2D through borrowed pointers, src/oc_dic.cpp:22-26).
+		struct Engine
+		{
+			ocb_ctx* ctx = nullptr;
+			std::mutex lock;
+			const void* ref_key = nullptr;
+			const void* tar_key = nullptr;
+			unsigned long long ref_gen = 0, tar_gen = 0;
+			bool prepared = false;
+
+			static Engine& get()
+			{
+				static Engine e;
+				return e;
+			}
+			ocb_ctx* context()
+			{
+				if (!ctx) {
+					int dev = 0;
+					if (const char* s = std::getenv("OPENCORR_B200_DEVICE")) dev = std::atoi(s);
+					ctx = ocb_create(dev);
+					if (!ctx) throw std::string(std::string("opencorr_b200: ") + ocb_last_error(nullptr));
+				}
+				return ctx;
+			}
+			void check(int rc)
+			{
+				if (rc != OCB_OK) throw std::string(std::string("opencorr_b200: ") + ocb_last_error(ctx));
+			}
+			~Engine()
+			{
+				if (ctx) ocb_destroy(ctx);
+			}
+			void useImages(Image2D* ref, Image2D* tar)
+			{
+				if (!ref || !tar) throw std::string("opencorr_b200: setImages() has not been called");
+				if (ref_key == ref && tar_key == tar && ref_gen == ref->generation && tar_gen == tar->generation) return;
+				if (ref->width != tar->width || ref->height != tar->height) throw std::string("opencorr_b200: reference and target image sizes differ");
+				check(ocb_set_images_2d(context(), ref->eg_mat.data.data(), tar->eg_mat.data.data(), ref->width, ref->height, 0));
+				ref_key = ref; tar_key = tar; ref_gen = ref->generation; tar_gen = tar->generation;
+				prepared = false;
+			}
+			void useImages(Image3D* ref, Image3D* tar)
+			{
+				if (!ref || !tar || !ref->vol_mat || !tar->vol_mat) throw std::string("opencorr_b200: setImages() has not been called");
+				if (ref_key == ref && tar_key == tar && ref_gen == ref->generation && tar_gen == tar->generation) return;
+				if (ref->dim_x != tar->dim_x || ref->dim_y != tar->dim_y || ref->dim_z != tar->dim_z) throw std::string("opencorr_b200: reference and target volume sizes differ");
+				check(ocb_set_images_3d(context(), **ref->vol_mat, **tar->vol_mat, ref->dim_x, ref->dim_y, ref->dim_z));
+				ref_key = ref; tar_key = tar; ref_gen = ref->generation; tar_gen = tar->generation;
+				prepared = false;
+			}
+		};
+	} // namespace b200
+
+	// ------------------------------------------------------------------ src/oc_dic.h
+	class DIC
+	{
+	public:
+		Image2D* ref_img = nullptr;
+		Image2D* tar_img = nullptr;
+		int subset_radius_x, subset_radius_y;
+		int thread_number; // kept for signature compatibility; the GPU path has no CPU worker threads
+		bool self_adaptive;
+
+		DIC() : subset_radius_x(0), subset_radius_y(0), thread_number(1), self_adaptive(false) {}
+		virtual ~DIC() = default;
+		void setImages(Image2D& ref_img, Image2D& tar_img) { this->ref_img = &ref_img; this->tar_img = &tar_img; }
+		void setSubset(int radius_x, int radius_y) { subset_radius_x = radius_x; subset_radius_y = radius_y; }
+		void setSelfAdaptive(bool is_self_adaptive) { self_adaptive = is_self_adaptive; }
+		virtual void prepare() = 0;
+		virtual void compute(POI2D* poi) = 0;
+		virtual void compute(std::vector<POI2D>& poi_queue) = 0;
+	};
+
+	class DVC
+	{
+	public:
+		Image3D* ref_img = nullptr;
+		Image3D* tar_img = nullptr;
+		int subset_radius_x, subset_radius_y, subset_radius_z;
+		int thread_number;
+
+		DVC() : subset_radius_x(0), subset_radius_y(0), subset_radius_z(0), thread_number(1) {}
+		virtual ~DVC() = default;
+		void setImages(Image3D& ref_img, Image3D& tar_img) { this->ref_img = &ref_img; this->tar_img = &tar_img; }
+		void setSubset(int radius_x, int radius_y, int radius_z) { subset_radius_x = radius_x; subset_radius_y = radius_y; subset_radius_z = radius_z; }
+		virtual void prepare() = 0;
+		virtual void compute(POI3D* POI) = 0;
+		virtual void compute(std::vector<POI3D>& poi_queue) = 0;
+	};
+
+	inline bool sortByZNCC(const POI2D& p1, const POI2D& p2) { return p1.result.zncc > p2.result.zncc; }
+
+	// ------------------------------------------------------------------ src/oc_fftcc.h
+	class FFTCC2D : public DIC
+	{
+	public:
+		FFTCC2D(int subset_radius_x, int subset_radius_y, int thread_number)
+		{
+			this->subset_radius_x = subset_radius_x;
+			this->subset_radius_y = subset_radius_y;
+			this->thread_number = thread_number;
+		}
+		~FFTCC2D() {}
+		void prepare() {}
+		void compute(POI2D* poi) { run(poi, 1); }
+		void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+
+	private:
+		void run(POI2D* p, size_t n)
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.useImages(ref_img, tar_img);
+			e.check(ocb_fftcc2d(e.context(), p, n, subset_radius_x, subset_radius_y));
+		}
+	};
+
+	class FFTCC3D : public DVC
+	{
+	public:
+		FFTCC3D(int subset_radius_x, int subset_radius_y, int subset_radius_z, int thread_number)
+		{
+			this->subset_radius_x = subset_radius_x;
+			this->subset_radius_y = subset_radius_y;
+			this->subset_radius_z = subset_radius_z;
+			this->thread_number = thread_number;
+		}
+		~FFTCC3D() {}
+		void prepare() {}
+		void compute(POI3D* poi) { run(poi, 1); }
+		void compute(std::vector<POI3D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+
+	private:
+		void run(POI3D* p, size_t n)
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.useImages(ref_img, tar_img);
+			e.check(ocb_fftcc3d(e.context(), p, n, subset_radius_x, subset_radius_y, subset_radius_z));
+		}
+	};
+
+	// ------------------------------------------------------------------ src/oc_icgn.h
+	namespace b200
+	{
+		template <int ORDER>
+		class ICGN2D : public DIC
+		{
+		protected:
+			float conv_criterion;
+			float stop_condition;
+
+		public:
+			ICGN2D(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
+			{
+				this->subset_radius_x = subset_radius_x;
+				this->subset_radius_y = subset_radius_y;
+				this->conv_criterion = conv_criterion;
+				this->stop_condition = stop_condition;
+				this->thread_number = thread_number;
+				self_adaptive = false;
+			}
+			void setIteration(float conv_criterion, float stop_condition)
+			{
+				this->conv_criterion = conv_criterion;
+				this->stop_condition = stop_condition;
+			}
+			void setIteration(POI2D* poi) // src/oc_icgn.cpp:109-113 / :650-654
+			{
+				conv_criterion = poi->result.convergence;
+				stop_condition = (ORDER == 1) ? (float)(int)poi->result.iteration : poi->result.iteration;
+			}
+			void prepareRef() { prepare(); }
+			void prepareTar() { prepare(); }
+			void prepare()
+			{
+				Engine& e = Engine::get();
+				std::lock_guard<std::mutex> g(e.lock);
+				e.useImages(ref_img, tar_img);
+				e.check(ocb_icgn2d_prepare(e.context()));
+				e.prepared = true;
+			}
+			void compute(POI2D* poi) { run(poi, 1); }
+			void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+
+		private:
+			void run(POI2D* p, size_t n)
+			{
+				if (self_adaptive) throw std::string("opencorr_b200: self-adaptive subsets are not implemented yet (DESIGN.md, next rows)");
+				Engine& e = Engine::get();
+				std::lock_guard<std::mutex> g(e.lock);
+				e.useImages(ref_img, tar_img);
+				if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+				if (ORDER == 1) e.check(ocb_icgn2d1(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
+				else e.check(ocb_icgn2d2(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
+			}
+		};
+	} // namespace b200
+
+	class ICGN2D1 : public b200::ICGN2D<1>
+	{
+	public:
+		ICGN2D1(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
+			: b200::ICGN2D<1>(subset_radius_x, subset_radius_y, conv_criterion, stop_condition, thread_number) {}
+	};
+
+	class ICGN2D2 : public b200::ICGN2D<2>
+	{
+	public:
+		ICGN2D2(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
+			: b200::ICGN2D<2>(subset_radius_x, subset_radius_y, conv_criterion, stop_condition, thread_number) {}
+	};
+
+	class ICGN3D1 : public DVC
+	{
+	private:
+		float conv_criterion;
+		float stop_condition;
+
+	public:
+		ICGN3D1(int subset_radius_x, int subset_radius_y, int subset_radius_z, float conv_criterion, float stop_condition, int thread_number)
+		{
+			this->subset_radius_x = subset_radius_x;
+			this->subset_radius_y = subset_radius_y;
+			this->subset_radius_z = subset_radius_z;
+			this->conv_criterion = conv_criterion;
+			this->stop_condition = stop_condition;
+			this->thread_number = thread_number;
+		}
+		~ICGN3D1() {}
+		void setIteration(float conv_criterion, float stop_condition)
+		{
+			this->conv_criterion = conv_criterion;
+			this->stop_condition = stop_condition;
+		}
+		void setIteration(POI3D* poi) // src/oc_icgn.cpp:1234-1238
+		{
+			conv_criterion = poi->result.convergence;
+			stop_condition = (float)(int)poi->result.iteration;
+		}
+		void prepareRef() { prepare(); }
+		void prepareTar() { prepare(); }
+		void prepare()
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.useImages(ref_img, tar_img);
+			e.check(ocb_icgn3d_prepare(e.context()));
+			e.prepared = true;
+		}
+		void compute(POI3D* poi) { run(poi, 1); }
+		void compute(std::vector<POI3D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+
+	private:
+		void run(POI3D* p, size_t n)
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.useImages(ref_img, tar_img);
+			if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+			e.check(ocb_icgn3d1(e.context(), p, n, subset_radius_x, subset_radius_y, subset_radius_z, conv_criterion, stop_condition));
+		}
+	};
+
+	// ------------------------------------------------------------------ src/oc_io.h (subset used by the two examples)
+	enum OutputVariable
+	{
+		u = 1, v = 2, w = 3, e_xx = 4, e_yy = 5, e_zz = 6, e_xy = 7, e_yz = 8, e_zx = 9, zncc = 10, zncc_r1r2 = 11, zncc_r1t2 = 12,
+		deformation_increment = 13, iteration_step = 14, feature_nearby = 15, u_x = 16, u_y = 17, u_z = 18, v_x = 19, v_y = 20, v_z = 21,
+		w_x = 22, w_y = 23, w_z = 24,
+	};
+
+	class IO2D
+	{
+	private:
+		std::string file_path;
+		std::string delimiter = ",";
+		int width = 0, height = 0;
+
+	public:
+		IO2D() {}
+		~IO2D() {}
+		OutputVariable out_var;
+		std::string getPath() const { return file_path; }
+		std::string getDelimiter() const { return delimiter; }
+		int getWidth() const { return width; }
+		int getHeight() const { return height; }
+		void setPath(std::string file_path) { this->file_path = file_path; }
+		void setDelimiter(std::string delimiter) { this->delimiter = delimiter; }
+		void setWidth(int width) { this->width = width; }
+		void setHeight(int height) { this->height = height; }
+
+		// src/oc_io.cpp:318-373
+		void saveTable2D(std::vector<POI2D>& poi_queue)
+		{
+			std::ofstream file_out(file_path);
+			file_out.setf(std::ios::fixed);
+			file_out << std::setprecision(8);
+			if (file_out.is_open()) {
+				const char* head[] = { "x", "y", "u", "v", "u0", "v0", "ZNCC", "iteration", "convergence", "feature", "exx", "eyy", "exy", "subset_rx", "subset_ry" };
+				for (const char* h : head) file_out << h << delimiter;
+				file_out << std::endl;
+				for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
+					file_out << iter->x << delimiter << iter->y << delimiter;
+					file_out << iter->deformation.u << delimiter << iter->deformation.v << delimiter;
+					for (int i = 0; i < 6; i++) file_out << iter->result.r[i] << delimiter;
+					for (int i = 0; i < 3; i++) file_out << iter->strain.e[i] << delimiter;
+					file_out << iter->subset_radius.x << delimiter << iter->subset_radius.y << delimiter;
+					file_out << std::endl;
+				}
+			}
+			file_out.close();
+		}
+		// src/oc_io.cpp:375-421
+		void saveDeformationTable2D(std::vector<POI2D>& poi_queue)
+		{
+			std::ofstream file_out(file_path);
+			file_out.setf(std::ios::fixed);
+			file_out << std::setprecision(8);
+			if (file_out.is_open()) {
+				const char* head[] = { "x", "y", "u", "ux", "uy", "uxx", "uxy", "uyy", "v", "vx", "vy", "vxx", "vxy", "vyy", "subset_rx", "subset_ry" };
+				for (const char* h : head) file_out << h << delimiter;
+				file_out << std::endl;
+				for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
+					file_out << iter->x << delimiter << iter->y << delimiter;
+					for (int i = 0; i < 12; i++) file_out << iter->deformation.p[i] << delimiter;
+					file_out << iter->subset_radius.x << delimiter << iter->subset_radius.y << delimiter;
+					file_out << std::endl;
+				}
+			}
+			file_out.close();
+		}
+		// src/oc_io.cpp:423-504
+		void saveMap2D(std::vector<POI2D>& poi_queue, OutputVariable variable)
+		{
+			std::vector<float> output_map((size_t)height * width, 0.f);
+			for (size_t i = 0; i < poi_queue.size(); i++) {
+				const POI2D& p = poi_queue[i];
+				float val;
+				switch (variable) {
+				case u: val = p.deformation.u; break;
+				case v: val = p.deformation.v; break;
+				case zncc: val = p.result.zncc; break;
+				case deformation_increment: val = p.result.convergence; break;
+				case iteration_step: val = p.result.iteration; break;
+				case feature_nearby: val = p.result.feature; break;
+				case e_xx: val = p.strain.exx; break;
+				case e_yy: val = p.strain.eyy; break;
+				case e_xy: val = p.strain.exy; break;
+				default: return;
+				}
+				output_map[(size_t)(int)p.y * width + (int)p.x] = val;
+			}
+			std::ofstream file_out(file_path);
+			file_out.setf(std::ios::fixed);
+			file_out << std::setprecision(8);
+			if (file_out.is_open()) {
+				for (int r = 0; r < height; r++) {
+					for (int c = 0; c < width; c++) file_out << output_map[(size_t)r * width + c] << delimiter;
+					file_out << std::endl;
+				}
+			}
+			file_out.close();
+		}
+	};
+
+	class IO3D
+	{
+	private:
+		std::string file_path;
+		std::string delimiter;
+		int dim_x = 0, dim_y = 0, dim_z = 0;
+
+	public:
+		IO3D() {}
+		~IO3D() {}
+		std::string getPath() const { return file_path; }
+		std::string getDelimiter() const { return delimiter; }
+		void setPath(std::string file_path) { this->file_path = file_path; }
+		void setDelimiter(std::string delimiter) { this->delimiter = delimiter; }
+		int getDimX() { return dim_x; }
+		int getDimY() { return dim_y; }
+		int getDimZ() { return dim_z; }
+		void setDimX(int dim_x) { this->dim_x = dim_x; }
+		void setDimY(int dim_y) { this->dim_y = dim_y; }
+		void setDimZ(int dim_z) { this->dim_z = dim_z; }
+
+		// src/oc_io.cpp:1004-1089
+		void saveTable3D(std::vector<POI3D>& poi_queue)
+		{
+			std::ofstream file_out(file_path);
+			file_out.setf(std::ios::fixed);
+			file_out << std::setprecision(8);
+			if (file_out.is_open()) {
+				const char* head[] = { "x", "y", "z", "u", "v", "w", "u0", "v0", "w0", "ZNCC", "iteration", "convergence", "feature",
+					"ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "exx", "eyy", "ezz", "exy", "eyz", "ezx", "subset_rx", "subset_ry", "subset_rz" };
+				for (const char* h : head) file_out << h << delimiter;
+				file_out << std::endl;
+				for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
+					file_out << iter->x << delimiter << iter->y << delimiter << iter->z << delimiter;
+					file_out << iter->deformation.u << delimiter << iter->deformation.v << delimiter << iter->deformation.w << delimiter;
+					for (int i = 0; i < 7; i++) file_out << iter->result.r[i] << delimiter;
+					file_out << iter->deformation.ux << delimiter << iter->deformation.uy << delimiter << iter->deformation.uz << delimiter;
+					file_out << iter->deformation.vx << delimiter << iter->deformation.vy << delimiter << iter->deformation.vz << delimiter;
+					file_out << iter->deformation.wx << delimiter << iter->deformation.wy << delimiter << iter->deformation.wz << delimiter;
+					for (int i = 0; i < 6; i++) file_out << iter->strain.e[i] << delimiter;
+					file_out << iter->subset_radius.x << delimiter << iter->subset_radius.y << delimiter << iter->subset_radius.z << delimiter;
+					file_out << std::endl;
+				}
+			}
+			file_out.close();
+		}
+	};
+
+} // namespace opencorr
+
+#endif // _OPENCORR_B200_SHIM_H_

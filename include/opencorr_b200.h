@@ -61,8 +61,11 @@ ocb_ctx* ocb_create(int device);
 void ocb_destroy(ocb_ctx* ctx);
 /* Last error message of this context (or of the process when ctx == NULL). Never NULL. */
 const char* ocb_last_error(const ocb_ctx* ctx);
-/* Use an external cudaStream_t (e.g. PyTorch's current stream); NULL restores the own stream. */
+/* Enqueue on an external cudaStream_t (e.g. PyTorch's current stream).  The handle is used as given:
+ * NULL is CUDA's legacy default stream, NOT "no stream".  ocb_use_own_stream() goes back to the
+ * context's private non-blocking stream (the state after ocb_create). */
 int ocb_set_stream(ocb_ctx* ctx, void* cuda_stream);
+int ocb_use_own_stream(ocb_ctx* ctx);
 /* Block until everything enqueued on the context's stream has finished. */
 int ocb_sync(ocb_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py "gpu_launches"). */

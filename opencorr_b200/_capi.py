@@ -27,6 +27,7 @@ SIGNATURES = {
     "ocb_destroy": (None, [_vp]),
     "ocb_last_error": (ctypes.c_char_p, [_vp]),
     "ocb_set_stream": (_i, [_vp, _vp]),
+    "ocb_use_own_stream": (_i, [_vp]),
     "ocb_sync": (_i, [_vp]),
     "ocb_launch_count": (ctypes.c_longlong, [_vp]),
     "ocb_set_images_2d": (_i, [_vp, _vp, _vp, _i, _i, _i]),

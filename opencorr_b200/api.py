@@ -106,7 +106,11 @@ class Engine:
         self._ck(self._lib.ocb_set_images_3d_dev(self._ctx, int(d_ref), int(d_tar), dim_x, dim_y, dim_z))
 
     def set_stream(self, cuda_stream):
+        """Enqueue on this cudaStream_t handle (0/None = CUDA's legacy default stream)."""
         self._ck(self._lib.ocb_set_stream(self._ctx, int(cuda_stream) if cuda_stream else None))
+
+    def use_own_stream(self):
+        self._ck(self._lib.ocb_use_own_stream(self._ctx))
 
     def sync(self):
         self._ck(self._lib.ocb_sync(self._ctx))

@@ -173,7 +173,7 @@ ocb_ctx* ocb_create(int device) {
 void ocb_destroy(ocb_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
+	cudaDeviceSynchronize();
 	cudaFree(ctx->own_ref2);
 	cudaFree(ctx->own_tar2);
 	cudaFree(ctx->own_ref3);
@@ -191,7 +191,13 @@ const char* ocb_last_error(const ocb_ctx* ctx) { return ctx ? ctx->last_error.c_
 
 int ocb_set_stream(ocb_ctx* ctx, void* cuda_stream) {
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
-	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+	ctx->stream = (cudaStream_t)cuda_stream;
+	return OCB_OK;
+}
+
+int ocb_use_own_stream(ocb_ctx* ctx) {
+	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	ctx->stream = ctx->own_stream;
 	return OCB_OK;
 }
 

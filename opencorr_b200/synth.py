@@ -2,16 +2,46 @@
 
 The reference ships no generator; bench.py and the tests use this one.  Gaussian-speckle model,
 8-bit quantised then cast to float for 2D (the reference only ever sees 8-bit-valued floats in
-2D, src/oc_image.cpp:39,56): I(x) = clip(255 * sum_k a_k exp(-|x - c_k|^2 / rho^2)), the target is
-rendered analytically from displaced centres c_k' = c_k + u(c_k).
+2D, src/oc_image.cpp:39,56): I(x) = clip(B + (255 - B) * sum_k a_k exp(-|x - c_k|^2 / rho^2)), the
+target is rendered analytically from displaced centres c_k' = c_k + u(c_k).
+
+The background level B = 24 is a deliberate departure from SURVEY.md's formula (B = 0): the
+reference treats ANY interpolated sample < 0 as "outside the image" (src/oc_icgn.cpp:251-255), and
+bicubic/tricubic overshoot next to truly black pixels produces such samples, so a pattern with a
+zero background makes the reference reject every POI with ZNCC = -3.
 """
 import numpy as np
 
 REF_SEED = 20260924
+BACKGROUND = 24.0
 
 
-def _render(shape, centres, amps, rho):
+def _render_torch(shape, centres, amps, rho, device):
+    """Same as _render on a torch device (float64 accumulation); used for the large bench inputs."""
+    import torch
+    nd = len(shape)
+    c = torch.as_tensor(centres, dtype=torch.float64, device=device)
+    a = torch.as_tensor(amps, dtype=torch.float64, device=device)
+    img = torch.zeros(int(np.prod(shape)), dtype=torch.float64, device=device)
+    base = torch.floor(c).to(torch.int64)
+    half = int(np.ceil(3.5 * rho))
+    rng = torch.arange(-half, half + 1, device=device)
+    offs = torch.stack([g.reshape(-1) for g in torch.meshgrid(*([rng] * nd), indexing="ij")], 1)
+    lim = torch.tensor(shape, device=device)
+    strides = torch.tensor([int(np.prod(shape[i + 1:])) for i in range(nd)], dtype=torch.int64, device=device)
+    inv = 1.0 / (rho * rho)
+    for o in offs:
+        p = base + o
+        ok = ((p >= 0) & (p < lim)).all(1)
+        d2 = ((p[ok].to(torch.float64) - c[ok]) ** 2).sum(1)
+        img.index_add_(0, (p[ok] * strides).sum(1), a[ok] * torch.exp(-d2 * inv))
+    return img.reshape(shape).cpu().numpy()
+
+
+def _render(shape, centres, amps, rho, device=None):
     """Sum of isotropic Gaussians, evaluated within +-3.5 rho of each centre (numpy, any dim)."""
+    if device is not None:
+        return _render_torch(shape, centres, amps, rho, device)
     nd = len(shape)
     img = np.zeros(int(np.prod(shape)), np.float64)
     base = np.floor(centres).astype(np.int64)
@@ -45,26 +75,26 @@ def displacement_3d(x, y, z, dim_x, dim_y, dim_z):
     return 1.3 + 1e-3 * xt, -0.7 + 1.2e-3 * yt, 2.4 - 1.5e-3 * zt
 
 
-def speckle_pair_2d(width, height, second_order=False, rho=2.0, seed=REF_SEED, quantise=True):
+def speckle_pair_2d(width, height, second_order=False, rho=2.0, seed=REF_SEED, quantise=True, device=None):
     """(ref, tar) float32 [height, width]."""
     rng = np.random.default_rng(seed)
     n = int(0.5 * width * height / (np.pi * rho * rho))
     cx = rng.uniform(-8, width + 8, n)
     cy = rng.uniform(-8, height + 8, n)
     amp = rng.uniform(0.4, 1.0, n)
-    ref = _render((height, width), np.stack([cy, cx], 1), amp, rho)
+    ref = _render((height, width), np.stack([cy, cx], 1), amp, rho, device)
     u, v = displacement_2d(cx, cy, width, height, second_order)
-    tar = _render((height, width), np.stack([cy + v, cx + u], 1), amp, rho)
+    tar = _render((height, width), np.stack([cy + v, cx + u], 1), amp, rho, device)
     out = []
     for im in (ref, tar):
-        im = np.clip(255.0 * im, 0, 255)
+        im = np.clip(BACKGROUND + (255.0 - BACKGROUND) * im, 0, 255)
         if quantise:
             im = np.round(im)
         out.append(im.astype(np.float32))
     return out[0], out[1]
 
 
-def speckle_pair_3d(dim_x, dim_y, dim_z, rho=2.0, seed=REF_SEED, quantise=True):
+def speckle_pair_3d(dim_x, dim_y, dim_z, rho=2.0, seed=REF_SEED, quantise=True, device=None):
     """(ref, tar) float32 [dim_z, dim_y, dim_x]."""
     rng = np.random.default_rng(seed)
     n = int(0.35 * dim_x * dim_y * dim_z / (4.0 / 3.0 * np.pi * rho ** 3))
@@ -72,12 +102,12 @@ def speckle_pair_3d(dim_x, dim_y, dim_z, rho=2.0, seed=REF_SEED, quantise=True):
     cy = rng.uniform(-8, dim_y + 8, n)
     cz = rng.uniform(-8, dim_z + 8, n)
     amp = rng.uniform(0.4, 1.0, n)
-    ref = _render((dim_z, dim_y, dim_x), np.stack([cz, cy, cx], 1), amp, rho)
+    ref = _render((dim_z, dim_y, dim_x), np.stack([cz, cy, cx], 1), amp, rho, device)
     u, v, w = displacement_3d(cx, cy, cz, dim_x, dim_y, dim_z)
-    tar = _render((dim_z, dim_y, dim_x), np.stack([cz + w, cy + v, cx + u], 1), amp, rho)
+    tar = _render((dim_z, dim_y, dim_x), np.stack([cz + w, cy + v, cx + u], 1), amp, rho, device)
     out = []
     for im in (ref, tar):
-        im = np.clip(255.0 * im, 0, 255)
+        im = np.clip(BACKGROUND + (255.0 - BACKGROUND) * im, 0, 255)
         if quantise:
             im = np.round(im)
         out.append(im.astype(np.float32))

@@ -115,7 +115,7 @@ struct FFT {
 						}
 					}
 					out[q + s * ((long)r * p)] = b[0];
-					for (int j = 1; j < r; j++) out[q + s * ((long)r * p + j)] = b[j] * tw[((long)p * j * tstep) % n];
+					for (int j = 1; j < r; j++) out[q + s * ((long)r * p + j)] = b[j] * tw[(long)p * j * tstep]; // p*j*tstep < n
 				}
 			}
 			ncur = m;
@@ -125,6 +125,18 @@ struct FFT {
 		if (in != x) std::memcpy(x, in, sizeof(cpx) * (size_t)n * (size_t)s0);
 	}
 };
+
+// FFT of every row of a row-major [rows][n] block (the contiguous axis): transpose, run the strided
+// transform (long contiguous inner loops), transpose back.  tmp: rows*n elements.
+template <class T>
+void fft_rows(const FFT<T>& f, std::complex<T>* x, std::complex<T>* tmp, std::complex<T>* scratch, int rows, bool inverse) {
+	const int n = f.n;
+	for (int r = 0; r < rows; r++)
+		for (int c = 0; c < n; c++) tmp[(size_t)c * rows + r] = x[(size_t)r * n + c];
+	f.run(tmp, scratch, rows, inverse);
+	for (int r = 0; r < rows; r++)
+		for (int c = 0; c < n; c++) x[(size_t)r * n + c] = tmp[(size_t)c * rows + r];
+}
 
 // ----------------------------------------------------------------------------------------------
 // Small dense linear algebra standing in for Eigen (see header).
@@ -317,9 +329,16 @@ inline T bicubic_eval(const Ctx2D& c, T x, T y) {
 }
 
 // FFTCC2D::compute(POI2D*), src/oc_fftcc.cpp:177-275.
+// per-thread scratch of the FFT-CC stage (the reference's FFTW instance pool, src/oc_fftcc.cpp:141-163)
 template <class T>
-void fftcc2d_poi(const Ctx2D& c, float* poi, int rx, int ry, const FFT<T>& fx, const FFT<T>& fy,
-	std::complex<T>* buf, std::complex<T>* scratch) {
+struct FftScratch {
+	std::vector<T> a, b;
+	std::vector<std::complex<T>> buf, cc, scratch, tmp;
+	void resize(size_t n) { a.resize(n); b.resize(n); buf.resize(n); cc.resize(n); scratch.resize(n); }
+};
+
+template <class T>
+void fftcc2d_poi(const Ctx2D& c, float* poi, int rx, int ry, const FFT<T>& fx, const FFT<T>& fy, FftScratch<T>& fs) {
 	typedef std::complex<T> cpx;
 	int sw = 2 * rx, sh = 2 * ry, size = sw * sh;
 	float px = poi[P2_X], py = poi[P2_Y];
@@ -328,7 +347,12 @@ void fftcc2d_poi(const Ctx2D& c, float* poi, int rx, int ry, const FFT<T>& fx, c
 	if ((int)px < rx || (int)px >= c.w - rx || (int)py < ry || (int)py >= c.h - ry
 		|| int(px + u0) < rx || int(px + u0) >= c.w - rx || int(py + v0) < ry || int(py + v0) >= c.h - ry)
 		return;
-	std::vector<T> a(size), b(size);
+	fs.resize(size);
+	std::vector<T>& a = fs.a;
+	std::vector<T>& b = fs.b;
+	cpx* buf = fs.buf.data();
+	cpx* scratch = fs.scratch.data();
+	std::vector<cpx>& cc = fs.cc;
 	T ref_mean = 0, tar_mean = 0, ref_norm = 0, tar_norm = 0;
 	for (int r = 0; r < sh; r++) {
 		for (int col = 0; col < sw; col++) {
@@ -352,9 +376,8 @@ void fftcc2d_poi(const Ctx2D& c, float* poi, int rx, int ry, const FFT<T>& fx, c
 	}
 	// Z = FFT2(a + i b); A = (Z(k)+conj Z(-k))/2, B = (Z(k)-conj Z(-k))/(2i); C = conj(A) B  (:233-241)
 	for (int i = 0; i < size; i++) buf[i] = cpx(a[i], b[i]);
-	for (int r = 0; r < sh; r++) fx.run(buf + (size_t)r * sw, scratch, 1, false);
+	fft_rows(fx, buf, cc.data(), scratch, sh, false);
 	fy.run(buf, scratch, sw, false);
-	std::vector<cpx> cc(size);
 	for (int ky = 0; ky < sh; ky++)
 		for (int kx = 0; kx < sw; kx++) {
 			cpx z = buf[ky * sw + kx];
@@ -365,7 +388,7 @@ void fftcc2d_poi(const Ctx2D& c, float* poi, int rx, int ry, const FFT<T>& fx, c
 			// (:239-240) re = ArBr + AiBi ; im = ArBi - AiBr
 			cc[ky * sw + kx] = cpx(A.real() * B.real() + A.imag() * B.imag(), A.real() * B.imag() - A.imag() * B.real());
 		}
-	for (int r = 0; r < sh; r++) fx.run(cc.data() + (size_t)r * sw, scratch, 1, true);
+	fft_rows(fx, cc.data(), buf, scratch, sh, true);
 	fy.run(cc.data(), scratch, sw, true);
 	// argmax, :246-255
 	T max_zncc = (T)-2;
@@ -722,8 +745,7 @@ inline T tricubic_eval(const Ctx3D& c, T x, T y, T z) {
 // FFTCC3D::compute(POI3D*), src/oc_fftcc.cpp:327-427.  No border guard in the reference; the
 // oracle refuses (leaves the POI untouched) instead of reading out of bounds.
 template <class T>
-void fftcc3d_poi(const Ctx3D& c, float* poi, int rx, int ry, int rz, const FFT<T>& fx, const FFT<T>& fy, const FFT<T>& fz,
-	std::vector<std::complex<T>>& buf, std::vector<std::complex<T>>& cc, std::vector<std::complex<T>>& scratch) {
+void fftcc3d_poi(const Ctx3D& c, float* poi, int rx, int ry, int rz, const FFT<T>& fx, const FFT<T>& fy, const FFT<T>& fz, FftScratch<T>& fs) {
 	typedef std::complex<T> cpx;
 	int sx = 2 * rx, sy = 2 * ry, sz = 2 * rz;
 	size_t size = (size_t)sx * sy * sz;
@@ -739,9 +761,13 @@ void fftcc3d_poi(const Ctx3D& c, float* poi, int rx, int ry, int rz, const FFT<T
 			|| px - rx < 0 || py - ry < 0 || pz - rz < 0 || px - rx + u0 < 0 || py - ry + v0 < 0 || pz - rz + w0 < 0)
 			return;
 	}
-	buf.resize(size); cc.resize(size); scratch.resize(size);
+	fs.resize(size);
+	std::vector<T>& a = fs.a;
+	std::vector<T>& b = fs.b;
+	std::vector<cpx>& buf = fs.buf;
+	std::vector<cpx>& cc = fs.cc;
+	std::vector<cpx>& scratch = fs.scratch;
 	T ref_mean = 0, tar_mean = 0, ref_norm = 0, tar_norm = 0;
-	std::vector<T> a(size), b(size);
 	for (int i = 0; i < sz; i++)
 		for (int j = 0; j < sy; j++)
 			for (int k = 0; k < sx; k++) {
@@ -764,9 +790,10 @@ void fftcc3d_poi(const Ctx3D& c, float* poi, int rx, int ry, int rz, const FFT<T
 		tar_norm += b[i] * b[i];
 	}
 	for (size_t i = 0; i < size; i++) buf[i] = cpx(a[i], b[i]);
+	std::vector<cpx>& tmp = fs.tmp;
+	tmp.resize((size_t)sx * sy);
 	auto fft3 = [&](std::vector<cpx>& d, bool inv) {
-		for (int i = 0; i < sz; i++)
-			for (int j = 0; j < sy; j++) fx.run(d.data() + ((size_t)i * sy + j) * sx, scratch.data(), 1, inv);
+		for (int i = 0; i < sz; i++) fft_rows(fx, d.data() + (size_t)i * sy * sx, tmp.data(), scratch.data(), sy, inv);
 		for (int i = 0; i < sz; i++) fy.run(d.data() + (size_t)i * sy * sx, scratch.data(), sx, inv);
 		fz.run(d.data(), scratch.data(), (long)sx * sy, inv);
 	};
@@ -924,9 +951,9 @@ void run_fftcc2d(const Ctx2D& c, float* pois, long n, int rx, int ry) {
 	fy.plan(2 * ry);
 #pragma omp parallel num_threads(c.threads)
 	{
-		std::vector<std::complex<T>> buf((size_t)4 * rx * ry), scratch((size_t)4 * rx * ry);
-#pragma omp for
-		for (long i = 0; i < n; i++) fftcc2d_poi<T>(c, pois + i * P2_N, rx, ry, fx, fy, buf.data(), scratch.data());
+		FftScratch<T> fs;
+#pragma omp for schedule(dynamic, 64)
+		for (long i = 0; i < n; i++) fftcc2d_poi<T>(c, pois + i * P2_N, rx, ry, fx, fy, fs);
 	}
 }
 template <class T, int NP>
@@ -934,7 +961,7 @@ void run_icgn2d(const Ctx2D& c, float* pois, long n, int rx, int ry, float conv,
 #pragma omp parallel num_threads(c.threads)
 	{
 		Scratch2D<T> s;
-#pragma omp for schedule(static)
+#pragma omp for schedule(dynamic, 64)
 		for (long i = 0; i < n; i++) icgn2d_poi<T, NP>(c, pois + i * P2_N, rx, ry, conv, stop, s);
 	}
 }
@@ -944,9 +971,9 @@ void run_fftcc3d(const Ctx3D& c, float* pois, long n, int rx, int ry, int rz) {
 	fx.plan(2 * rx); fy.plan(2 * ry); fz.plan(2 * rz);
 #pragma omp parallel num_threads(c.threads)
 	{
-		std::vector<std::complex<T>> buf, cc, scratch;
-#pragma omp for
-		for (long i = 0; i < n; i++) fftcc3d_poi<T>(c, pois + i * P3_N, rx, ry, rz, fx, fy, fz, buf, cc, scratch);
+		FftScratch<T> fs;
+#pragma omp for schedule(dynamic, 1)
+		for (long i = 0; i < n; i++) fftcc3d_poi<T>(c, pois + i * P3_N, rx, ry, rz, fx, fy, fz, fs);
 	}
 }
 template <class T>

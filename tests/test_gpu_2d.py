@@ -1,0 +1,219 @@
+"""GPU parity, 2D: FFTCC2D, ICGN2D1, ICGN2D2 through the C ABI vs the CPU oracle and vs the
+reference's golden table.  Tolerances are north_star's: 1e-4 px displacement, 1e-5 ZNCC; integer
+outputs (u0, v0, FFT-CC displacement, iteration count, sentinel codes) must be identical, with the
+documented exception of POIs whose ||dp|| lands within float noise of the convergence threshold."""
+import numpy as np
+import pytest
+
+import opencorr_b200 as ob
+from opencorr_b200 import synth
+from oracle.oracle import Oracle2D
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _config_a():
+    cfg = synth.CONFIGS["A"]
+    ref, tar = synth.speckle_pair_2d(*cfg["size"])
+    xy = synth.grid_2d(*cfg["grid"])
+    return ref, tar, xy, cfg["r"]
+
+
+@pytest.fixture(scope="module")
+def cfg_a():
+    return _config_a()
+
+
+@pytest.mark.parametrize("r", [15, 16, 20, 6])
+def test_fftcc2d_matches_oracle(engine, cfg_a, r):
+    ref, tar, xy, _ = cfg_a
+    q_gpu = ob.make_poi2d(xy)
+    q_cpu = q_gpu.copy()
+    f = ob.FFTCC2D(r, r, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q_gpu)
+    Oracle2D(ref, tar).fftcc2d(q_cpu, r, r)
+    assert np.array_equal(q_gpu[:, [2, 8, 14, 15]], q_cpu[:, [2, 8, 14, 15]])  # integer displacements: bit-exact
+    assert np.abs(q_gpu[:, 16] - q_cpu[:, 16]).max() < 1e-5
+    untouched = np.delete(np.arange(25), [2, 8, 14, 15, 16])
+    assert np.array_equal(q_gpu[:, untouched], q_cpu[:, untouched])
+
+
+def test_fftcc2d_nonsquare_window_and_initial_guess(engine, cfg_a):
+    ref, tar, xy, _ = cfg_a
+    q_gpu = ob.make_poi2d(xy)
+    q_gpu[:, 2] = 1.0   # incoming guess shifts the target window (src/oc_fftcc.cpp:187,215)
+    q_gpu[:, 8] = -2.0
+    q_gpu[::3, 2] = 0.6  # fractional guesses exercise the (int) truncation
+    q_cpu = q_gpu.copy()
+    f = ob.FFTCC2D(12, 10, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q_gpu)
+    Oracle2D(ref, tar).fftcc2d(q_cpu, 12, 10)
+    assert np.array_equal(q_gpu[:, [2, 8, 14, 15]], q_cpu[:, [2, 8, 14, 15]])
+    assert np.abs(q_gpu[:, 16] - q_cpu[:, 16]).max() < 1e-5
+
+
+def test_fftcc2d_border_pois_are_left_untouched(engine, cfg_a):
+    ref, tar, _, _ = cfg_a
+    h, w = ref.shape
+    xy = np.array([[5, 100], [100, 5], [w - 6, 100], [100, h - 6], [15, 15], [16, 16], [w - 16, h - 16], [w - 17, h - 17]], np.float32)
+    q_gpu = ob.make_poi2d(xy)
+    q_gpu[:, 16] = 0.123  # marker that must survive on skipped POIs
+    q_cpu = q_gpu.copy()
+    f = ob.FFTCC2D(16, 16, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q_gpu)
+    Oracle2D(ref, tar).fftcc2d(q_cpu, 16, 16)
+    assert np.array_equal(q_gpu[:, [2, 8, 14, 15]], q_cpu[:, [2, 8, 14, 15]])
+    skipped = q_cpu[:, 16] == np.float32(0.123)
+    assert skipped.sum() == 6
+    assert np.array_equal(q_gpu[skipped], q_cpu[skipped])
+    assert np.abs(q_gpu[:, 16] - q_cpu[:, 16]).max() < 1e-5
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_icgn2d1_config_a(engine, cfg_a, exact):
+    ref, tar, xy, r = cfg_a
+    q = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, r, r)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN2D1(r, r, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    o.icgn2d1(q_cpu, r, r, 0.001, 10, exact=exact)
+    stats = util.compare_2d(q_gpu, q_cpu, "icgn2d1 A exact=%d" % exact)
+    assert stats["n_compared"] >= 0.95 * len(q)
+    ok = (q_gpu[:, 16] >= 0) & (q_gpu[:, 17] == q_cpu[:, 17])
+    assert np.abs(q_gpu[ok][:, [3, 4, 9, 10]] - q_cpu[ok][:, [3, 4, 9, 10]]).max() < 2e-5  # ux uy vx vy
+    assert np.abs(q_gpu[ok, 18] - q_cpu[ok, 18]).max() < 1e-4                              # convergence
+    assert np.array_equal(q_gpu[ok][:, 23:25], q_cpu[ok][:, 23:25])
+    # ground truth of the synthetic field, loose sanity bound
+    u_true, v_true = synth.displacement_2d(xy[:, 0], xy[:, 1], ref.shape[1], ref.shape[0])
+    assert np.abs(q_gpu[ok, 2] - u_true[ok]).max() < 0.05 and np.abs(q_gpu[ok, 8] - v_true[ok]).max() < 0.05
+
+
+def test_icgn2d1_golden_table(engine):
+    """FFTCC2D -> ICGN2D1 on the reference's example pair vs its shipped result table."""
+    ref, tar = util.oht_cfrp_pair()
+    g = util.oht_cfrp_golden()
+    tab = g["table"]
+    q = ob.make_poi2d(tab[:, 0:2])
+    f = ob.FFTCC2D(16, 16, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q)
+    icgn = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q)
+    guess_same = (q[:, 14] == tab[:, 4]) & (q[:, 15] == tab[:, 5])
+    assert guess_same.mean() > 0.998
+    ok = guess_same & (tab[:, 7] < 10) & (q[:, 17] == tab[:, 7])
+    assert ok.sum() > 0.93 * len(tab)
+    assert np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max() < 1e-4
+    assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 1e-5
+    # and against the oracle on the very same POIs
+    qc = ob.make_poi2d(tab[:, 0:2])
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(qc, 16, 16)
+    o.icgn2d1(qc, 16, 16, 0.001, 10)
+    conv = (qc[:, 16] >= 0) & (q[:, 16] >= 0)
+    util.compare_2d(q[conv], qc[conv], "oht_cfrp", max_iter_mismatch_frac=0.02)
+
+
+@pytest.mark.parametrize("r", [20, 12])
+def test_icgn2d2_matches_oracle(engine, r):
+    ref, tar = synth.speckle_pair_2d(512, 512, second_order=True)
+    xy = synth.grid_2d(64, 64, 16, 12, 24, 31)
+    q = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, r, r)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN2D2(r, r, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    o.icgn2d2(q_cpu, r, r, 0.001, 10)
+    stats = util.compare_2d(q_gpu, q_cpu, "icgn2d2 r=%d" % r, max_iter_mismatch_frac=0.03)
+    assert stats["n_compared"] >= 0.9 * len(q)
+    ok = (q_gpu[:, 16] >= 0) & (q_gpu[:, 17] == q_cpu[:, 17])
+    assert np.abs(q_gpu[ok][:, 2:14] - q_cpu[ok][:, 2:14]).max() < 1e-4
+
+
+def test_icgn2d_sentinels(engine, cfg_a):
+    """-3 at the border / skip on incoming zncc<0 / -3 when the warped subset leaves the target /
+    -4 when stop is reached (src/oc_icgn.cpp:160-167,251-255,329-332)."""
+    ref, tar, _, r = cfg_a
+    h, w = ref.shape
+    xy = np.array([[10, 200], [200, 10], [w - 11, 200], [200, h - 11],  # 0-3: subset leaves the reference image
+                   [200, 200], [260, 240],                               # 4,5: fine
+                   [r, r], [w - 1 - r, h - 1 - r],                       # 6,7: guard passes, warped samples leave the target -> -3
+                   [300, 300], [320, 300], [340, 300]], np.float32)      # 8: zncc<0 in, 9: guess pushes out, 10: |u|>=w
+    q = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, r, r)
+    q[8, 16] = -2.0
+    q[9, 2] = w - 330.0   # target subset partly outside -> -3 during iteration 1
+    q[10, 2] = float(w)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN2D1(r, r, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    o.icgn2d1(q_cpu, r, r, 0.001, 10)
+    assert list(q_cpu[[0, 1, 2, 3, 6, 7, 8, 9, 10], 16]) == [-3, -3, -3, -3, -3, -3, -2, -3, -3]
+    util.compare_2d(q_gpu, q_cpu, "sentinels", max_iter_mismatch_frac=0.0)
+    rejected = [0, 1, 2, 3, 6, 7, 8, 9, 10]
+    assert np.array_equal(q_gpu[rejected], q_cpu[rejected])  # rejected records: bit-identical (nothing else written)
+    # stop_condition = 1 -> every POI that does not converge in one step gets -4, parameters kept
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn.set_iteration(1e-6, 1)
+    icgn.compute(q_gpu)
+    o.icgn2d1(q_cpu, r, r, 1e-6, 1)
+    assert (q_cpu[[4, 5], 16] == -4).all()
+    assert np.array_equal(q_gpu[:, 16], q_cpu[:, 16])
+    assert np.abs(q_gpu[[4, 5]][:, 2:14] - q_cpu[[4, 5]][:, 2:14]).max() < 1e-4
+
+
+def test_icgn2d_requires_prepare_and_images():
+    eng = ob.Engine(0)
+    q = ob.make_poi2d([[100, 100]])
+    with pytest.raises(ob.OpenCorrB200Error):
+        eng.icgn2d1(q, 16, 16, 0.001, 10)       # images not set
+    ref, tar = synth.speckle_pair_2d(128, 128)
+    eng.set_images_2d(ref, tar)
+    with pytest.raises(ob.OpenCorrB200Error):
+        eng.icgn2d1(q, 16, 16, 0.001, 10)       # prepare() missing
+    eng.icgn2d_prepare()
+    eng.icgn2d1(q[:0], 16, 16, 0.001, 10)      # empty queue is a no-op
+    with pytest.raises(ob.OpenCorrB200Error):
+        eng.icgn2d1(q, 0, 16, 0.001, 10)        # radius < 1
+    eng.close()
+
+
+def test_large_deformation_gradient_falls_back_to_global_reads(engine):
+    """Samples leaving the staged target tile are read from global memory; result must not change."""
+    ref, _ = synth.speckle_pair_2d(384, 384)
+    # target = reference stretched by 12 % about the centre (far beyond the tile slack at r=16)
+    yy, xx = np.mgrid[0:384, 0:384].astype(np.float32)
+    o_ref = Oracle2D(ref, ref)
+    o_ref.prepare()
+    src = np.stack([(192 + (xx - 192) / 1.12).ravel(), (192 + (yy - 192) / 1.12).ravel()], 1)
+    tar = np.clip(o_ref.bicubic(src), 0, 255).reshape(384, 384).astype(np.float32)
+    xy = synth.grid_2d(150, 150, 5, 5, 20, 20)
+    q = ob.make_poi2d(xy)
+    q[:, 2] = (xy[:, 0] - 192) * 0.12
+    q[:, 8] = (xy[:, 1] - 192) * 0.12
+    q[:, 3] = 0.12
+    q[:, 10] = 0.12
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    Oracle2D(ref, tar).icgn2d1(q_cpu, 16, 16, 0.001, 10)
+    assert (q_cpu[:, 16] > 0.9).all()
+    util.compare_2d(q_gpu, q_cpu, "stretch", max_iter_mismatch_frac=0.05)
