@@ -5,33 +5,98 @@
 // ICGN2D2::compute(POI2D*) (src/oc_icgn.cpp:685-898), including what ICGN2D*::prepare() feeds
 // them (Gradient2D4, src/oc_gradient.cpp:37-79; BicubicBspline, src/oc_cubic_bspline.cpp:84-181).
 //
-// Mapping: ONE WARP PER POI, no block-level synchronisation.
-//   setup   : the (2r+1)^2 reference subset is read once; zero-mean values f, gradients gx, gy
-//             (4th-order differences recomputed from the image, nothing precomputed in HBM) go to
-//             the warp's shared-memory slab; the Hessian, sum(sd) and sum(sd*f) are accumulated in
-//             registers and reduced with warp shuffles; the Hessian is Cholesky-factorised in
-//             registers (same arithmetic replicated in every lane).
-//   iterate : a target tile (subset + bicubic support + slack) is staged in shared memory once per
-//             POI; each iteration evaluates the bicubic interpolant from the 4x4 pixel block
-//             with explicit fp32 weights (the reference's 64 B/pixel LUT is never materialised),
-//             and accumulates ONE pass of sums: with d = (t - mean_ref) - f,
-//                 sum d, sum d^2, sum f*d, sum sd_k*d
-//             from which mean/norm of the warped target, ZNSSD and the Gauss-Newton right-hand
-//             side follow algebraically (see DESIGN.md "single-pass IC-GN sums").
+// Mapping: ONE WARP PER POI, persistent warps pulling POIs from an atomic counter, no CTA barrier.
+// Lanes run along x: lane c owns column c of the subset for every row (columns >= 32 are a short
+// tail), so x-dependent factors are per-lane constants and y-dependent ones are warp-uniform.
+//   stage   : the reference tile (subset + 2-pixel gradient halo) is staged in the warp's smem slab.
+//   setup   : one pass computes R' = R - c0 (c0 = centre pixel, a pilot value that keeps every sum
+//             well conditioned), the 4th-order gradients gx, gy (recomputed from the image, nothing
+//             precomputed in HBM) and stores them to smem; the Hessian is accumulated as FACTORED
+//             sums  sum g_a g_b y^Q  (x^P applied once per lane afterwards), so a sample costs 15
+//             (6-parameter) / 30 (12-parameter) flops instead of 21 / 78 FMAs.  Mean and norm of the
+//             reference subset come from the same pass.  Cholesky factorisation in registers.
+//   iterate : the target tile (subset + bicubic support + slack), minus c0, replaces the reference
+//             tile in the slab.  Each iteration evaluates the bicubic interpolant from the 4x4 pixel
+//             block with explicit fp32 weights (the reference's 64 B/pixel LUT is never built) and
+//             accumulates ONE pass of sums with d = t - R:  sum d, sum d^2, sum R'd, sum g_a d y^Q;
+//             mean/norm of the warped target, ZNSSD and the Gauss-Newton right-hand side follow
+//             algebraically (DESIGN.md "single-pass IC-GN sums").
 //   update  : solve with the Cholesky factors, compose W <- W * W(dp)^-1 in registers.
-// Samples whose 4x4 support leaves the staged tile (large deformation gradients) fall back to
-// global-memory reads of the target image, so results never depend on the tile size.
+// Samples whose 4x4 support leaves the staged tile (large deformation gradients) are read from
+// global memory instead, so results never depend on the tile size.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "ocb_kernels.h"
 
 namespace ocb {
 
-constexpr int ICGN2D_TILE_MARGIN = 2; // slack (pixels) around subset+support in the target tile
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, one barrier per warp -----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+		"{\n\t"
+		".reg .pred p;\n\t"
+		"WAIT_LOOP:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra.uni WAIT_DONE;\n\t"
+		"bra.uni WAIT_LOOP;\n\t"
+		"WAIT_DONE:\n\t"
+		"}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 2D tile load: box (set in the tensor map) whose upper-left corner is (x, y); out-of-image = 0
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+		"l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+		: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__host__ __device__ inline int icgn2d_tile_w(int rx) { return 2 * rx + 4 + 2 * ICGN2D_TILE_MARGIN; }
+constexpr int ICGN2D_TILE_MARGIN = 1; // slack (pixels) around subset+support in the target tile
+// TMA tile loads need the innermost coordinate 16-byte aligned (x multiple of 4 floats; measured: an
+// unaligned x raises 'illegal instruction'), so tile origins are rounded down to a multiple of 4 and
+// the boxes are 3 columns wider.
+
+__host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline int floor4(int v) { return v & ~3; } // rounds toward -inf (two's complement)
+__host__ __device__ inline int icgn2d_ref_w(int rx) { return round_up4(2 * rx + 1 + 4 + 3); }
+__host__ __device__ inline int icgn2d_ref_h(int ry) { return 2 * ry + 1 + 4; }
+__host__ __device__ inline int icgn2d_tar_w(int rx) { return round_up4(2 * rx + 1 + 3 + 2 * ICGN2D_TILE_MARGIN + 3); }
+__host__ __device__ inline int icgn2d_tar_h(int ry) { return 2 * ry + 1 + 3 + 2 * ICGN2D_TILE_MARGIN; }
+__host__ __device__ inline int round_up32(int v) { return (v + 31) & ~31; }
+// per-warp slab (floats): [0,32) mbarrier + pad | tile T (TMA destination, 128-B aligned) | R', gx, gy
+__host__ __device__ inline int icgn2d_tile_floats(int rx, int ry) {
+	const int a = icgn2d_ref_w(rx) * icgn2d_ref_h(ry), b = icgn2d_tar_w(rx) * icgn2d_tar_h(ry);
+	return round_up32(a > b ? a : b);
+}
 __host__ __device__ inline int icgn2d_warp_floats(int rx, int ry) {
-	int n = (2 * rx + 1) * (2 * ry + 1);
-	int t = icgn2d_tile_w(rx) * icgn2d_tile_w(ry);
-	return ((3 * n + t) + 3) & ~3;
+	const int n = (2 * rx + 1) * (2 * ry + 1);
+	return 32 + icgn2d_tile_floats(rx, ry) + round_up32(3 * n);
+}
+
+// Shape functions: sd = g_a * phi_i, phi = [1, x, y, x^2/2, xy, y^2/2] (first 3 for NP == 6);
+// phi_i = c_i x^p_i y^q_i  (reference src/oc_icgn.cpp:191-196, :725-745)
+__host__ __device__ constexpr int phi_p(int i) { return i == 1 ? 1 : (i == 3 ? 2 : (i == 4 ? 1 : 0)); }
+__host__ __device__ constexpr int phi_q(int i) { return i == 2 ? 1 : (i == 4 ? 1 : (i == 5 ? 2 : 0)); }
+__host__ __device__ constexpr float phi_c(int i) { return (i == 3 || i == 5) ? 0.5f : 1.f; }
+// index of monomial x^P y^Q among all monomials ordered by total degree then Q
+__host__ __device__ constexpr int mono(int P, int Q) { return (P + Q) * (P + Q + 1) / 2 + Q; }
+__host__ __device__ constexpr int pair_idx(int a, int b) { return a + b; } // (x,x)=0 (x,y)=1 (y,y)=2
+
+__device__ __forceinline__ float ipow(float x, int p) {
+	float r = 1.f;
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+		if (i < p) r *= x;
+	return r;
 }
 
 // W(p) of the second-order shape function (reference src/oc_deformation.cpp:301-350)
@@ -64,13 +129,9 @@ __device__ __forceinline__ void warp2d2_matrix(const float* p, float* W) {
 // rows <- rows * M^-1 for the 2x6 block `rows` (rows 3,4 of the running warp) and the 6x6 warp
 // increment M whose last row is [0 0 0 0 0 1] (given as its first 5 rows, 30 floats).
 // Gaussian elimination without pivoting: M = W(dp) is a perturbation of the identity.
+// X M = R: reduce M = L U (unit lower L), Y U = R by forward substitution over columns, X = Y L^-1.
 __device__ __forceinline__ void right_divide_2x6(float* rows, float* M) {
-	// Solve X M = R  <=>  for each row x of X: x M = r.  Eliminate column by column:
-	// x_j = (r_j - sum_{i<j} x_i M[i][j]) / M[j][j] requires M upper triangular, so first reduce M
-	// to upper-triangular form U = L^-1 M with row operations, accumulating L: X M = R  <=>
-	// (X L) U = R.  Let Y = X L: solve Y U = R by forward substitution over columns, then
-	// X = Y L^-1, applied by undoing the row operations in reverse order.
-	float Lm[5][5]; // multipliers l[i][k], i > k (rows 0..4; row 5 of M is e5 and needs no elimination)
+	float Lm[5][5];
 #pragma unroll
 	for (int k = 0; k < 5; k++) {
 		float inv = 1.0f / M[k * 6 + k];
@@ -85,7 +146,6 @@ __device__ __forceinline__ void right_divide_2x6(float* rows, float* M) {
 #pragma unroll
 	for (int r = 0; r < 2; r++) {
 		float y[6];
-		// Y U = R, U upper triangular 6x6 (row 5 = e5)
 #pragma unroll
 		for (int j = 0; j < 6; j++) {
 			float v = rows[r * 6 + j];
@@ -95,7 +155,6 @@ __device__ __forceinline__ void right_divide_2x6(float* rows, float* M) {
 			}
 			y[j] = (j < 5) ? v / M[j * 6 + j] : v;
 		}
-		// X = Y L^-1 : x_k = y_k - sum_{i>k} x_i l[i][k], from the last column backwards (i < 5 only)
 #pragma unroll
 		for (int k = 4; k >= 0; k--) {
 			float v = y[k];
@@ -108,25 +167,94 @@ __device__ __forceinline__ void right_divide_2x6(float* rows, float* M) {
 	}
 }
 
+// Stage a (rows x cols) window of a row-major image into smem (row pitch `cols`), origin (ox, oy),
+// subtracting `shift`; pixels outside the image read as -shift.  Lanes run along x (coalesced).
+__device__ __forceinline__ void stage_tile(float* dst, const float* __restrict__ img, int w, int h, int ox, int oy, int cols, int rows,
+	float shift, int lane) {
+	for (int col = lane; col < cols; col += 32) {
+		const int gx = ox + col;
+		const bool colok = gx >= 0 && gx < w;
+#pragma unroll 8
+		for (int row = 0; row < rows; row++) {
+			const int gy = oy + row;
+			float v = 0.f;
+			if (colok && gy >= 0 && gy < h) v = __ldg(img + (size_t)gy * w + gx);
+			dst[row * cols + col] = v - shift;
+		}
+	}
+}
+
+// Bicubic B-spline sample of the target, minus c0, at (X, Y), src/oc_cubic_bspline.cpp:134-181.
+// fast: the 4x4 support lies inside the staged tile.  Otherwise read the image (caller guarantees
+// 1 <= X < w-2, 1 <= Y < h-2).
+__device__ __forceinline__ float bicubic_sample(const float* tile, int TW, int tx0, int ty0, const float* __restrict__ tar, int w, float c0,
+	float X, float Y, bool fast) {
+	const float xf = floorf(X), yf = floorf(Y);
+	float wx[4], wy[4];
+	bicubic_weights(X - xf, wx);
+	bicubic_weights(Y - yf, wy);
+	const int ix = (int)xf - 1, iy = (int)yf - 1;
+	float t = 0.f;
+	if (fast) {
+		const float* q = tile + (iy - ty0) * TW + (ix - tx0);
+#pragma unroll
+		for (int nn = 0; nn < 4; nn++) {
+			float row = fmaf(q[nn * TW + 3], wx[3], fmaf(q[nn * TW + 2], wx[2], fmaf(q[nn * TW + 1], wx[1], q[nn * TW] * wx[0])));
+			t = fmaf(row, wy[nn], t);
+		}
+	} else {
+		const float* q = tar + (size_t)iy * w + ix;
+#pragma unroll
+		for (int nn = 0; nn < 4; nn++) {
+			const float* qq = q + (size_t)nn * w;
+			float row = fmaf(__ldg(qq + 3), wx[3], fmaf(__ldg(qq + 2), wx[2], fmaf(__ldg(qq + 1), wx[1], __ldg(qq) * wx[0])));
+			t = fmaf(row, wy[nn], t);
+		}
+	}
+	return t - c0;
+}
+
 template <int NP>
 __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx, int ry,
-	float conv_criterion, float stop_condition, int warps_per_block) {
-	extern __shared__ __align__(16) float smem[];
+	float conv_criterion, float stop_condition, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_ref,
+	const __grid_constant__ CUtensorMap tm_tar, int use_tma) {
+	extern __shared__ __align__(128) float smem[];
 	constexpr int NH = NP * (NP + 1) / 2;
+	constexpr int NPHI = NP / 2;           // 3 or 6 shape monomials per displacement component
+	constexpr int DEG = (NP == 6) ? 1 : 2; // degree of the shape function
+	constexpr int D2 = 2 * DEG;
+	constexpr int NM = (D2 + 1) * (D2 + 2) / 2; // monomials x^P y^Q with P+Q <= 2*DEG: 6 or 15
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int sw = 2 * rx + 1, sh = 2 * ry + 1, N = sw * sh;
-	const int TW = icgn2d_tile_w(rx), TH = icgn2d_tile_w(ry);
-	float* sF = smem + (size_t)warp * icgn2d_warp_floats(rx, ry);
-	float* sGx = sF + N;
+	const int ncol = sw < 32 ? sw : 32;        // columns handled by the row-mapped main loops
+	const int rem = sw - ncol;                  // columns 32.. handled by the tail loops
+	const int ntail = rem * sh;
+	const int RW = icgn2d_ref_w(rx), RH = icgn2d_ref_h(ry);
+	const int TW = icgn2d_tar_w(rx), TH = icgn2d_tar_h(ry);
+	float* slab = smem + (size_t)warp * icgn2d_warp_floats(rx, ry);
+	uint64_t* bar = (uint64_t*)slab;
+	float* T = slab + 32;
+	float* sR = T + icgn2d_tile_floats(rx, ry);
+	float* sGx = sR + N;
 	float* sGy = sGx + N;
-	float* tile = sGy + N;
+	uint32_t bar_phase = 0;
+	if (use_tma) {
+		if (lane == 0) mbar_init(bar, 1);
+		__syncwarp();
+	}
 	const float* __restrict__ ref = img.ref;
 	const float* __restrict__ tar = img.tar;
 	const int w = img.w, h = img.h;
 	const float inv_n = 1.0f / (float)N;
+	const bool lane_on = lane < ncol;
+	const float xl_lane = (float)(lane - rx);
 
-	for (int poi = blockIdx.x * warps_per_block + warp; poi < n_poi; poi += gridDim.x * warps_per_block) {
+	while (true) {
+		int poi = 0;
+		if (lane == 0) poi = atomicAdd(work_counter, 1);
+		poi = __shfl_sync(0xffffffffu, poi, 0);
+		if (poi >= n_poi) break;
 		float* P = pois + (size_t)poi * P2_N;
 		const float rec = lane < P2_N ? P[lane] : 0.f;
 		const float px = __shfl_sync(0xffffffffu, rec, P2_X);
@@ -142,71 +270,193 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		}
 		__syncwarp();
 
-		// ---------------- setup: reference subset, gradients, Hessian ----------------
-		const int x0 = (int)px - rx, y0 = (int)py - ry;
-		float s1 = 0.f;
-		for (int i = lane; i < N; i += 32) {
-			int r = i / sw, c = i - r * sw;
-			float R = __ldg(ref + (size_t)(y0 + r) * w + (x0 + c));
-			sF[i] = R;
-			s1 += R;
+		// ---------------- stage the reference tile ----------------
+		const int x0 = (int)px - rx, y0 = (int)py - ry; // Subset2D::fill upper-left, src/oc_subset.cpp:41-42
+		const int rox = floor4(x0 - 2), ex = (x0 - 2) - rox; // 16-byte aligned tile origin, column offset 0..3
+		if (use_tma) {
+			if (lane == 0) {
+				fence_proxy_async(); // earlier generic-proxy accesses to T are ordered before the async-proxy write
+				mbar_expect_tx(bar, (uint32_t)(RW * RH * sizeof(float)));
+				tma_load_2d(T, &tm_ref, rox, y0 - 2, bar);
+			}
+			mbar_wait(bar, bar_phase);
+			bar_phase ^= 1;
+		} else {
+			stage_tile(T, ref, w, h, rox, y0 - 2, RW, RH, 0.f, lane);
+			__syncwarp();
 		}
-		const float ref_mean = warp_sum(s1) * inv_n; // Subset2D::zeroMeanNorm, src/oc_subset.cpp:46-53
-		float H[NH], S[NP], SF[NP];
+		const float c0 = T[(ry + 2) * RW + rx + 2 + ex]; // pilot value: the centre pixel
+
+		// ---------------- setup: R', gradients, factored Hessian sums ----------------
+		float r1 = 0.f, r2 = 0.f;
+		float accH[3][D2 + 1];   // sum g_a g_b y^Q over this lane's column
+		float accS[2][DEG + 1];  // sum g_a y^Q
+		float accR[2][DEG + 1];  // sum g_a R' y^Q
 #pragma unroll
-		for (int k = 0; k < NH; k++) H[k] = 0.f;
+		for (int a = 0; a < 3; a++)
 #pragma unroll
-		for (int k = 0; k < NP; k++) { S[k] = 0.f; SF[k] = 0.f; }
-		float f2 = 0.f;
-		for (int i = lane; i < N; i += 32) {
-			int r = i / sw, c = i - r * sw;
-			int xg = x0 + c, yg = y0 + r;
-			float f = sF[i] - ref_mean;
-			sF[i] = f;
-			f2 = fmaf(f, f, f2);
-			const float* q = ref + (size_t)yg * w + xg;
-			float gx = 0.f, gy = 0.f; // 2-pixel borders of the gradient maps are zero (src/oc_gradient.cpp:42,46)
-			if (xg >= 2 && xg < w - 2) gx = grad4(__ldg(q - 2), __ldg(q - 1), __ldg(q + 1), __ldg(q + 2));
-			if (yg >= 2 && yg < h - 2) gy = grad4(__ldg(q - 2 * (size_t)w), __ldg(q - (size_t)w), __ldg(q + (size_t)w), __ldg(q + 2 * (size_t)w));
+			for (int q = 0; q <= D2; q++) accH[a][q] = 0.f;
+#pragma unroll
+		for (int a = 0; a < 2; a++)
+#pragma unroll
+			for (int q = 0; q <= DEG; q++) { accS[a][q] = 0.f; accR[a][q] = 0.f; }
+		{
+			const int xg = x0 + lane;
+			const bool gx_ok = lane_on && xg >= 2 && xg < w - 2; // gradient maps are zero on a 2-pixel border (src/oc_gradient.cpp:42,46)
+			for (int r = 0; r < sh; r++) {
+				const int yg = y0 + r;
+				const bool gy_ok = yg >= 2 && yg < h - 2;
+				const float yl = (float)(r - ry);
+				if (lane_on) {
+					const float* q = T + (r + 2) * RW + lane + 2 + ex;
+					const float R = q[0] - c0;
+					float gx = 0.f, gy = 0.f;
+					if (gx_ok) gx = grad4(q[-2], q[-1], q[1], q[2]);
+					if (gy_ok) gy = grad4(q[-2 * RW], q[-RW], q[RW], q[2 * RW]);
+					const int i = r * sw + lane;
+					sR[i] = R;
+					sGx[i] = gx;
+					sGy[i] = gy;
+					r1 += R;
+					r2 = fmaf(R, R, r2);
+					float g[3] = { gx * gx, gx * gy, gy * gy };
+#pragma unroll
+					for (int a = 0; a < 3; a++) {
+						float t = g[a];
+#pragma unroll
+						for (int qq = 0; qq <= D2; qq++) {
+							accH[a][qq] += t;
+							if (qq < D2) t *= yl;
+						}
+					}
+					float g1[2] = { gx, gy };
+#pragma unroll
+					for (int a = 0; a < 2; a++) {
+						float t = g1[a], tr = g1[a] * R;
+#pragma unroll
+						for (int qq = 0; qq <= DEG; qq++) {
+							accS[a][qq] += t;
+							accR[a][qq] += tr;
+							if (qq < DEG) { t *= yl; tr *= yl; }
+						}
+					}
+				}
+			}
+		}
+		// expand with this lane's x powers: M[pair][mono(P,Q)] = x^P * accH[pair][Q]
+		float M[3][NM], Sg[2][NPHI], SRg[2][NPHI];
+		{
+			float xp[D2 + 1];
+			xp[0] = 1.f;
+#pragma unroll
+			for (int p = 1; p <= D2; p++) xp[p] = xp[p - 1] * xl_lane;
+#pragma unroll
+			for (int Pp = 0; Pp <= D2; Pp++)
+#pragma unroll
+				for (int Q = 0; Q <= D2; Q++)
+					if (Pp + Q <= D2) {
+#pragma unroll
+						for (int a = 0; a < 3; a++) M[a][mono(Pp, Q)] = xp[Pp] * accH[a][Q];
+					}
+#pragma unroll
+			for (int i = 0; i < NPHI; i++)
+#pragma unroll
+				for (int a = 0; a < 2; a++) {
+					Sg[a][i] = xp[phi_p(i)] * accS[a][phi_q(i)];
+					SRg[a][i] = xp[phi_p(i)] * accR[a][phi_q(i)];
+				}
+		}
+		// tail columns (>= 32): lanes run over (row, column) pairs, general x and y
+		for (int idx = lane; idx < ntail; idx += 32) {
+			const int r = idx / rem, c = 32 + (idx - r * rem);
+			const int xg = x0 + c, yg = y0 + r;
+			const float xl = (float)(c - rx), yl = (float)(r - ry);
+			const float* q = T + (r + 2) * RW + c + 2 + ex;
+			const float R = q[0] - c0;
+			float gx = 0.f, gy = 0.f;
+			if (xg >= 2 && xg < w - 2) gx = grad4(q[-2], q[-1], q[1], q[2]);
+			if (yg >= 2 && yg < h - 2) gy = grad4(q[-2 * RW], q[-RW], q[RW], q[2 * RW]);
+			const int i = r * sw + c;
+			sR[i] = R;
 			sGx[i] = gx;
 			sGy[i] = gy;
-			float xl = (float)(c - rx), yl = (float)(r - ry);
-			float sd[NP];
-			if constexpr (NP == 6) { // src/oc_icgn.cpp:191-196
-				sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl;
-				sd[3] = gy; sd[4] = gy * xl; sd[5] = gy * yl;
-			} else { // src/oc_icgn.cpp:725-745
-				float xx = xl * xl * 0.5f, xy = xl * yl, yy = yl * yl * 0.5f;
-				sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl; sd[3] = gx * xx; sd[4] = gx * xy; sd[5] = gx * yy;
-				sd[6] = gy; sd[7] = gy * xl; sd[8] = gy * yl; sd[9] = gy * xx; sd[10] = gy * xy; sd[11] = gy * yy;
-			}
+			r1 += R;
+			r2 = fmaf(R, R, r2);
+			float g[3] = { gx * gx, gx * gy, gy * gy };
+			float g1[2] = { gx, gy };
 #pragma unroll
-			for (int a = 0; a < NP; a++) {
-				S[a] += sd[a];
-				SF[a] = fmaf(sd[a], f, SF[a]);
+			for (int Pp = 0; Pp <= D2; Pp++)
 #pragma unroll
-				for (int b = 0; b <= a; b++) H[a * (a + 1) / 2 + b] = fmaf(sd[a], sd[b], H[a * (a + 1) / 2 + b]);
+				for (int Q = 0; Q <= D2; Q++)
+					if (Pp + Q <= D2) {
+						const float mm = ipow(xl, Pp) * ipow(yl, Q);
+#pragma unroll
+						for (int a = 0; a < 3; a++) M[a][mono(Pp, Q)] = fmaf(g[a], mm, M[a][mono(Pp, Q)]);
+					}
+#pragma unroll
+			for (int ii = 0; ii < NPHI; ii++) {
+				const float mm = ipow(xl, phi_p(ii)) * ipow(yl, phi_q(ii));
+#pragma unroll
+				for (int a = 0; a < 2; a++) {
+					Sg[a][ii] = fmaf(g1[a], mm, Sg[a][ii]);
+					SRg[a][ii] = fmaf(g1[a] * R, mm, SRg[a][ii]);
+				}
 			}
 		}
-		f2 = warp_sum(f2);
+		r1 = warp_sum(r1);
+		r2 = warp_sum(r2);
 #pragma unroll
-		for (int k = 0; k < NH; k++) H[k] = warp_sum(H[k]);
+		for (int a = 0; a < 3; a++)
 #pragma unroll
-		for (int k = 0; k < NP; k++) { S[k] = warp_sum(S[k]); SF[k] = warp_sum(SF[k]); }
-		cholesky_packed<NP>(H);
+			for (int m = 0; m < NM; m++) M[a][m] = warp_sum(M[a][m]);
+#pragma unroll
+		for (int a = 0; a < 2; a++)
+#pragma unroll
+			for (int i = 0; i < NPHI; i++) { Sg[a][i] = warp_sum(Sg[a][i]); SRg[a][i] = warp_sum(SRg[a][i]); }
+		// reference subset statistics (Subset2D::zeroMeanNorm, src/oc_subset.cpp:46-53), relative to c0
+		const float rbar = r1 * inv_n;              // mean(R) - c0
+		const float f2 = r2 - r1 * rbar;            // sum f^2, f = R - mean(R)
 		const float ref_norm = sqrtf(f2);
+		// S_k = sum sd_k, SF_k = sum sd_k f = sum sd_k R' - rbar * S_k ; H = sum sd sd^T (src/oc_icgn.cpp:198-205)
+		float H[NH], S[NP], SF[NP];
+#pragma unroll
+		for (int a = 0; a < 2; a++)
+#pragma unroll
+			for (int i = 0; i < NPHI; i++) {
+				const int k = a * NPHI + i;
+				S[k] = phi_c(i) * Sg[a][i];
+				SF[k] = phi_c(i) * (SRg[a][i] - rbar * Sg[a][i]);
+#pragma unroll
+				for (int b = 0; b < 2; b++)
+#pragma unroll
+					for (int j = 0; j < NPHI; j++) {
+						const int l = b * NPHI + j;
+						if (l <= k) H[k * (k + 1) / 2 + l] = phi_c(i) * phi_c(j) * M[pair_idx(a, b)][mono(phi_p(i) + phi_p(j), phi_q(i) + phi_q(j))];
+					}
+			}
+		cholesky_packed<NP>(H);
 
-		// ---------------- target tile ----------------
-		const int tx0 = (int)floorf(px + u_in) - rx - 1 - ICGN2D_TILE_MARGIN;
-		const int ty0 = (int)floorf(py + v_in) - ry - 1 - ICGN2D_TILE_MARGIN;
-		for (int i = lane; i < TW * TH; i += 32) {
-			int ty = i / TW, tx = i - ty * TW;
-			int gxp = tx0 + tx, gyp = ty0 + ty;
-			float val = 0.f;
-			if (gxp >= 0 && gxp < w && gyp >= 0 && gyp < h) val = __ldg(tar + (size_t)gyp * w + gxp);
-			tile[i] = val;
-		}
+		// ---------------- stage the target tile over the reference tile ----------------
 		__syncwarp();
+		const int tx0 = floor4((int)floorf(px + u_in) - rx - 1 - ICGN2D_TILE_MARGIN);
+		const int ty0 = (int)floorf(py + v_in) - ry - 1 - ICGN2D_TILE_MARGIN;
+		if (use_tma) {
+			if (lane == 0) {
+				fence_proxy_async();
+				mbar_expect_tx(bar, (uint32_t)(TW * TH * sizeof(float)));
+				tma_load_2d(T, &tm_tar, tx0, ty0, bar);
+			}
+			mbar_wait(bar, bar_phase);
+			bar_phase ^= 1;
+		} else {
+			stage_tile(T, tar, w, h, tx0, ty0, TW, TH, 0.f, lane);
+			__syncwarp();
+		}
+		// a sample is "fast" when it is valid (src/oc_cubic_bspline.cpp:137-142) AND its support is in the tile
+		const float xlo = fmaxf(1.f, (float)(tx0 + 1)), xhi = fminf((float)(w - 2), (float)(tx0 + TW - 2));
+		const float ylo = fmaxf(1.f, (float)(ty0 + 1)), yhi = fminf((float)(h - 2), (float)(ty0 + TH - 2));
+		const float xmax = (float)(w - 2), ymax = (float)(h - 2);
+		const float neg_limit = -c0 - 1e-3f; // reference rejects interpolated values < 0 (src/oc_icgn.cpp:251-255)
 
 		// ---------------- IC-GN iterations ----------------
 		// running warp: NP==6 -> A = {W00,W01,W02,W10,W11,W12}; NP==12 -> rows 3,4 of the 6x6 warp
@@ -221,79 +471,112 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				A[6] = 0.f; A[7] = 0.f; A[8] = 0.f; A[9] = vx; A[10] = 1.f + vy; A[11] = v_in;
 			}
 		}
-		const float xmax = (float)(w - 2), ymax = (float)(h - 2);
 		int iteration = 0;
 		float dp_norm = 0.f, zncc = 0.f;
 		bool left_image = false;
 		float dp[NP];
 		do {
 			iteration++;
-			float d1 = 0.f, d2 = 0.f, fd = 0.f;
-			float SD[NP];
+			float d1 = 0.f, d2 = 0.f, rd = 0.f;
+			float G[2][DEG + 1]; // sum g_a d y^Q over this lane's column
 #pragma unroll
-			for (int k = 0; k < NP; k++) SD[k] = 0.f;
+			for (int a = 0; a < 2; a++)
+#pragma unroll
+				for (int q = 0; q <= DEG; q++) G[a][q] = 0.f;
 			bool invalid = false;
-			int r = 0, c = lane;
-			while (c >= sw) { c -= sw; r++; }
-			for (int i = lane; i < N; i += 32) {
-				const float xl = (float)(c - rx), yl = (float)(r - ry);
-				float wxp, wyp;
-				if constexpr (NP == 6) { // Deformation2D1::warp, src/oc_deformation.cpp:94-105
-					wxp = fmaf(A[0], xl, fmaf(A[1], yl, A[2]));
-					wyp = fmaf(A[3], xl, fmaf(A[4], yl, A[5]));
-				} else { // Deformation2D2::warp rows 3,4, src/oc_deformation.cpp:268-282
-					const float m0 = xl * xl, m1 = xl * yl, m2 = yl * yl;
-					wxp = fmaf(A[0], m0, fmaf(A[1], m1, fmaf(A[2], m2, fmaf(A[3], xl, fmaf(A[4], yl, A[5])))));
-					wyp = fmaf(A[6], m0, fmaf(A[7], m1, fmaf(A[8], m2, fmaf(A[9], xl, fmaf(A[10], yl, A[11])))));
+			// per-lane x part of the warp (Deformation2D1::warp src/oc_deformation.cpp:94-105,
+			// Deformation2D2::warp rows 3,4 :268-282): X = px + (ax2*y^2 + ax1*y + ax0)
+			float ax0, ax1, ax2, ay0, ay1, ay2;
+			if constexpr (NP == 6) {
+				ax0 = fmaf(A[0], xl_lane, A[2]); ax1 = A[1]; ax2 = 0.f;
+				ay0 = fmaf(A[3], xl_lane, A[5]); ay1 = A[4]; ay2 = 0.f;
+			} else {
+				ax0 = fmaf(A[0] * xl_lane + A[3], xl_lane, A[5]); ax1 = fmaf(A[1], xl_lane, A[4]); ax2 = A[2];
+				ay0 = fmaf(A[6] * xl_lane + A[9], xl_lane, A[11]); ay1 = fmaf(A[7], xl_lane, A[10]); ay2 = A[8];
+			}
+			for (int r = 0; r < sh; r++) {
+				const float yl = (float)(r - ry);
+				float X, Y;
+				if constexpr (NP == 6) {
+					X = px + fmaf(ax1, yl, ax0);
+					Y = py + fmaf(ay1, yl, ay0);
+				} else {
+					X = px + fmaf(fmaf(ax2, yl, ax1), yl, ax0);
+					Y = py + fmaf(fmaf(ay2, yl, ay1), yl, ay0);
 				}
-				const float X = px + wxp, Y = py + wyp;
-				// BicubicBspline::compute validity, src/oc_cubic_bspline.cpp:137-142 (NaN fails the test too)
-				const bool ok = (X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax);
+				const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
+				const bool all_fast = __all_sync(0xffffffffu, fast || !lane_on);
+				if (lane_on) {
+					bool ok = true;
+					if (!all_fast && !fast) ok = (X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax); // NaN fails too
+					if (!ok) {
+						invalid = true;
+					} else {
+						const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, c0, X, Y, all_fast || fast);
+						if (t < neg_limit) invalid = true;
+						const int i = r * sw + lane;
+						const float R = sR[i];
+						const float d = t - R;
+						d1 += d;
+						d2 = fmaf(d, d, d2);
+						rd = fmaf(R, d, rd);
+						float gd[2] = { sGx[i] * d, sGy[i] * d };
+#pragma unroll
+						for (int a = 0; a < 2; a++) {
+							float tt = gd[a];
+#pragma unroll
+							for (int qq = 0; qq <= DEG; qq++) {
+								G[a][qq] += tt;
+								if (qq < DEG) tt *= yl;
+							}
+						}
+					}
+				}
+			}
+			float SD[NP];
+			{
+				float xp[DEG + 1];
+				xp[0] = 1.f;
+#pragma unroll
+				for (int p = 1; p <= DEG; p++) xp[p] = xp[p - 1] * xl_lane;
+#pragma unroll
+				for (int a = 0; a < 2; a++)
+#pragma unroll
+					for (int i = 0; i < NPHI; i++) SD[a * NPHI + i] = phi_c(i) * xp[phi_p(i)] * G[a][phi_q(i)];
+			}
+			for (int idx = lane; idx < ntail; idx += 32) {
+				const int r = idx / rem, c = 32 + (idx - r * rem);
+				const float xl = (float)(c - rx), yl = (float)(r - ry);
+				float X, Y;
+				if constexpr (NP == 6) {
+					X = px + fmaf(A[0], xl, fmaf(A[1], yl, A[2]));
+					Y = py + fmaf(A[3], xl, fmaf(A[4], yl, A[5]));
+				} else {
+					const float m0 = xl * xl, m1 = xl * yl, m2 = yl * yl;
+					X = px + fmaf(A[0], m0, fmaf(A[1], m1, fmaf(A[2], m2, fmaf(A[3], xl, fmaf(A[4], yl, A[5])))));
+					Y = py + fmaf(A[6], m0, fmaf(A[7], m1, fmaf(A[8], m2, fmaf(A[9], xl, fmaf(A[10], yl, A[11])))));
+				}
+				const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
+				const bool ok = fast || ((X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax));
 				if (!ok) {
 					invalid = true;
 				} else {
-					const float xf = floorf(X), yf = floorf(Y);
-					float wx[4], wy[4];
-					bicubic_weights(X - xf, wx);
-					bicubic_weights(Y - yf, wy);
-					const int ix = (int)xf - 1, iy = (int)yf - 1;
-					const int lx = ix - tx0, ly = iy - ty0;
-					float t = 0.f;
-					if (lx >= 0 && ly >= 0 && lx + 3 < TW && ly + 3 < TH) {
-						const float* q = tile + ly * TW + lx;
-#pragma unroll
-						for (int nn = 0; nn < 4; nn++) {
-							float row = fmaf(q[nn * TW + 3], wx[3], fmaf(q[nn * TW + 2], wx[2], fmaf(q[nn * TW + 1], wx[1], q[nn * TW] * wx[0])));
-							t = fmaf(row, wy[nn], t);
-						}
-					} else {
-						const float* q = tar + (size_t)iy * w + ix;
-#pragma unroll
-						for (int nn = 0; nn < 4; nn++) {
-							const float* qq = q + (size_t)nn * w;
-							float row = fmaf(__ldg(qq + 3), wx[3], fmaf(__ldg(qq + 2), wx[2], fmaf(__ldg(qq + 1), wx[1], __ldg(qq) * wx[0])));
-							t = fmaf(row, wy[nn], t);
-						}
-					}
-					const float f = sF[i];
-					const float d = (t - ref_mean) - f;
+					const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, c0, X, Y, fast);
+					if (t < neg_limit) invalid = true;
+					const int i = r * sw + c;
+					const float R = sR[i];
+					const float d = t - R;
 					d1 += d;
 					d2 = fmaf(d, d, d2);
-					fd = fmaf(f, d, fd);
-					const float gxd = sGx[i] * d, gyd = sGy[i] * d;
-					if constexpr (NP == 6) {
-						SD[0] += gxd; SD[1] = fmaf(gxd, xl, SD[1]); SD[2] = fmaf(gxd, yl, SD[2]);
-						SD[3] += gyd; SD[4] = fmaf(gyd, xl, SD[4]); SD[5] = fmaf(gyd, yl, SD[5]);
-					} else {
-						const float xx = xl * xl * 0.5f, xy = xl * yl, yy = yl * yl * 0.5f;
-						SD[0] += gxd; SD[1] = fmaf(gxd, xl, SD[1]); SD[2] = fmaf(gxd, yl, SD[2]);
-						SD[3] = fmaf(gxd, xx, SD[3]); SD[4] = fmaf(gxd, xy, SD[4]); SD[5] = fmaf(gxd, yy, SD[5]);
-						SD[6] += gyd; SD[7] = fmaf(gyd, xl, SD[7]); SD[8] = fmaf(gyd, yl, SD[8]);
-						SD[9] = fmaf(gyd, xx, SD[9]); SD[10] = fmaf(gyd, xy, SD[10]); SD[11] = fmaf(gyd, yy, SD[11]);
+					rd = fmaf(R, d, rd);
+					float gd[2] = { sGx[i] * d, sGy[i] * d };
+#pragma unroll
+					for (int ii = 0; ii < NPHI; ii++) {
+						const float mm = phi_c(ii) * ipow(xl, phi_p(ii)) * ipow(yl, phi_q(ii));
+#pragma unroll
+						for (int a = 0; a < 2; a++) SD[a * NPHI + ii] = fmaf(gd[a], mm, SD[a * NPHI + ii]);
 					}
 				}
-				c += 32;
-				while (c >= sw) { c -= sw; r++; }
 			}
 			if (__any_sync(0xffffffffu, invalid)) { // src/oc_icgn.cpp:251-255
 				left_image = true;
@@ -301,11 +584,12 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			}
 			d1 = warp_sum(d1);
 			d2 = warp_sum(d2);
-			fd = warp_sum(fd);
+			rd = warp_sum(rd);
 #pragma unroll
 			for (int k = 0; k < NP; k++) SD[k] = warp_sum(SD[k]);
-			// warped-target statistics: g = t - mean(t) = f + (d - dbar)
+			// warped-target statistics: g = t - mean(t) = f + (d - dbar); sum f d = sum R'd - rbar * sum d
 			const float dbar = d1 * inv_n;
+			const float fd = rd - rbar * d1;
 			const float g2 = f2 + 2.f * fd + (d2 - d1 * dbar);
 			const float tar_norm = sqrtf(g2);
 			const float factor = ref_norm / tar_norm; // src/oc_icgn.cpp:260
@@ -328,9 +612,9 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				dp_norm = dp[0] * dp[0] + dp[1] * dp[1] * rx2 + dp[2] * dp[2] * ry2
 					+ dp[3] * dp[3] + dp[4] * dp[4] * rx2 + dp[5] * dp[5] * ry2; // src/oc_icgn.cpp:296-306
 			} else {
-				float M[30];
-				warp2d2_matrix(dp, M);
-				right_divide_2x6(A, M); // rows 3,4 of W * W(dp)^-1 (src/oc_icgn.cpp:831)
+				float Mw[30];
+				warp2d2_matrix(dp, Mw);
+				right_divide_2x6(A, Mw); // rows 3,4 of W * W(dp)^-1 (src/oc_icgn.cpp:831)
 				const int rx2 = rx * rx, ry2 = ry * ry;
 				const float rxy2 = (float)(rx2 * ry2);
 				const float rx4 = (float)(int)((float)(rx2 * rx2) * 0.25f); // float->int truncation, src/oc_icgn.cpp:840-841
@@ -382,9 +666,39 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 }
 
 // host-side launch ---------------------------------------------------------------------------
-// Returns 0, or -1 when one warp's slab does not fit in shared memory.
-int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop,
-	int sm_count, size_t smem_optin, cudaStream_t stream, cudaError_t* err) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+	const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+	static EncodeTiledFn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+			fn = (EncodeTiledFn)p;
+	}
+	return fn;
+}
+
+// Tensor map over a row-major f32 image for (box_w x box_h) tile loads; false when TMA cannot be used
+// (row pitch or base not 16-byte aligned, box too large, driver entry point missing).
+static bool make_tile_map(CUtensorMap* map, const float* base, int w, int h, int box_w, int box_h) {
+	EncodeTiledFn fn = get_encode_fn();
+	if (!fn || (w % 4) != 0 || ((uintptr_t)base % 16) != 0 || box_w > 256 || box_h > 256) return false;
+	cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
+	cuuint64_t strides[1] = { (cuuint64_t)w * sizeof(float) };
+	cuuint32_t box[2] = { (cuuint32_t)box_w, (cuuint32_t)box_h };
+	cuuint32_t estr[2] = { 1, 1 };
+	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Returns 0, -1 when one warp's slab does not fit in shared memory, -2 on a CUDA error.
+// d_counter: one int of device memory owned by the context (work queue head).
+int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
+	size_t smem_optin, int* d_counter, cudaStream_t stream, cudaError_t* err) {
 	const size_t per_warp = (size_t)icgn2d_warp_floats(rx, ry) * sizeof(float);
 	int best_wpb = 0, best_warps = 0;
 	for (int wpb = 4; wpb >= 1; wpb >>= 1) {
@@ -397,14 +711,21 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	}
 	if (best_wpb == 0) return -1;
 	const size_t smem = per_warp * best_wpb;
+	CUtensorMap tm_ref, tm_tar;
+	memset(&tm_ref, 0, sizeof(tm_ref));
+	memset(&tm_tar, 0, sizeof(tm_tar));
+	const int use_tma = !getenv("OCB_NO_TMA") && make_tile_map(&tm_ref, img.ref, img.w, img.h, icgn2d_ref_w(rx), icgn2d_ref_h(ry))
+		&& make_tile_map(&tm_tar, img.tar, img.w, img.h, icgn2d_tar_w(rx), icgn2d_tar_h(ry));
 	auto kern = (np == 6) ? icgn2d_kernel<6> : icgn2d_kernel<12>;
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
+	*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
+	if (*err != cudaSuccess) return -2;
 	long long blocks_needed = ((long long)n + best_wpb - 1) / best_wpb;
 	long long resident = (long long)sm_count * (best_warps / best_wpb);
-	int grid = (int)(blocks_needed < resident * 4 ? blocks_needed : resident * 4);
+	int grid = (int)(blocks_needed < resident ? blocks_needed : resident); // persistent: one wave
 	if (grid < 1) grid = 1;
-	kern<<<grid, best_wpb * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, best_wpb);
+	kern<<<grid, best_wpb * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, d_counter, tm_ref, tm_tar, use_tma);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;
 }

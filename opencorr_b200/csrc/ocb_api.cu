@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -63,6 +64,8 @@ struct ocb_ctx {
 	std::map<int, float2*> twiddles;
 	float2* fft_scratch = nullptr;
 	size_t fft_scratch_elems = 0;
+
+	int* d_counter = nullptr; // work-queue heads of the persistent kernels
 
 	// POI staging
 	float* d_poi = nullptr;
@@ -167,6 +170,12 @@ ocb_ctx* ocb_create(int device) {
 	ctx->stream = ctx->own_stream;
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	if ((e = cudaMalloc(&ctx->d_counter, 16 * sizeof(int))) != cudaSuccess) {
+		set_error(nullptr, OCB_ERR_CUDA, "context creation on device %d failed: %s", device, cudaGetErrorString(e));
+		cudaStreamDestroy(ctx->own_stream);
+		delete ctx;
+		return nullptr;
+	}
 	return ctx;
 }
 
@@ -183,6 +192,7 @@ void ocb_destroy(ocb_ctx* ctx) {
 	for (auto& kv : ctx->twiddles) cudaFree(kv.second);
 	cudaFree(ctx->fft_scratch);
 	cudaFree(ctx->d_poi);
+	cudaFree(ctx->d_counter);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -285,6 +295,13 @@ int ocb_fftcc2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry) {
 	if (n == 0) return OCB_OK;
 	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: too many POIs in one call");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	if (rx == 16 && ry == 16 && !getenv("OCB_FFTCC2D_GENERIC")) { // specialised register-FFT kernel for the 32x32 window
+		cudaError_t err32;
+		if (ocb::fftcc2d_w32_launch(ctx->img2, (float*)d_poi2d, n, ctx->sm_count, ctx->stream, &err32))
+			return set_error(ctx, OCB_ERR_CUDA, "fftcc2d launch failed: %s", cudaGetErrorString(err32));
+		ctx->launches++;
+		return OCB_OK;
+	}
 	ocb::FftAxis ax, ay;
 	if (!ocb::fft_plan_axis(2 * rx, &ax) || !ocb::fft_plan_axis(2 * ry, &ay))
 		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc2d: window size %dx%d has a prime factor > 31", 2 * rx, 2 * ry);
@@ -373,7 +390,7 @@ static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int
 	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "icgn2d: too many POIs in one call");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	cudaError_t err = cudaSuccess;
-	int rc = ocb::icgn2d_launch(np, ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+	int rc = ocb::icgn2d_launch(np, ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->d_counter, ctx->stream, &err);
 	if (rc == -1) return set_error(ctx, OCB_ERR_UNSUPPORTED, "icgn2d: subset radius (%d,%d) exceeds the shared-memory design limit", rx, ry);
 	if (rc) return set_error(ctx, OCB_ERR_CUDA, "icgn2d launch failed: %s", cudaGetErrorString(err));
 	ctx->launches++;

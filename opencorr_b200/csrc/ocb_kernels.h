@@ -34,11 +34,13 @@ inline bool fft_plan_axis(int n, FftAxis* ax) {
 
 // icgn2d.cu
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
-	size_t smem_optin, cudaStream_t stream, cudaError_t* err);
+	size_t smem_optin, int* d_counter, cudaStream_t stream, cudaError_t* err);
 // fftcc.cu
 size_t fftcc2d_smem_bytes(int rx, int ry);
 int fftcc2d_launch(const Image2D& img, float* d_pois, size_t n, int rx, int ry, const FftAxis& ax, const FftAxis& ay,
 	const float2* tw_x, const float2* tw_y, int sm_count, cudaStream_t stream, cudaError_t* err);
+// fftcc2d_w32.cu (32x32 window, one warp per POI, register FFT)
+int fftcc2d_w32_launch(const Image2D& img, float* d_pois, size_t n, int sm_count, cudaStream_t stream, cudaError_t* err);
 size_t fftcc3d_smem_bytes(int rx, int ry, int rz);
 int fftcc3d_grid(int rx, int ry, int rz, int sm_count);
 int fftcc3d_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, int rz, const FftAxis& ax, const FftAxis& ay,
