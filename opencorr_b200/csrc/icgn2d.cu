@@ -184,10 +184,10 @@ __device__ __forceinline__ void stage_tile(float* dst, const float* __restrict__
 	}
 }
 
-// Bicubic B-spline sample of the target, minus c0, at (X, Y), src/oc_cubic_bspline.cpp:134-181.
+// Bicubic B-spline sample of the target at (X, Y), src/oc_cubic_bspline.cpp:134-181.
 // fast: the 4x4 support lies inside the staged tile.  Otherwise read the image (caller guarantees
 // 1 <= X < w-2, 1 <= Y < h-2).
-__device__ __forceinline__ float bicubic_sample(const float* tile, int TW, int tx0, int ty0, const float* __restrict__ tar, int w, float c0,
+__device__ __forceinline__ float bicubic_sample(const float* tile, int TW, int tx0, int ty0, const float* __restrict__ tar, int w,
 	float X, float Y, bool fast) {
 	const float xf = floorf(X), yf = floorf(Y);
 	float wx[4], wy[4];
@@ -211,11 +211,13 @@ __device__ __forceinline__ float bicubic_sample(const float* tile, int TW, int t
 			t = fmaf(row, wy[nn], t);
 		}
 	}
-	return t - c0;
+	return t;
 }
 
-template <int NP>
-__global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx, int ry,
+// RC > 0: subset radius known at compile time (rx == ry == RC), so tile pitches and trip counts fold
+// into immediates; RC == 0: any radii at run time.
+template <int NP, int RC>
+__global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
 	float conv_criterion, float stop_condition, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_ref,
 	const __grid_constant__ CUtensorMap tm_tar, int use_tma) {
 	extern __shared__ __align__(128) float smem[];
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 	constexpr int DEG = (NP == 6) ? 1 : 2; // degree of the shape function
 	constexpr int D2 = 2 * DEG;
 	constexpr int NM = (D2 + 1) * (D2 + 2) / 2; // monomials x^P y^Q with P+Q <= 2*DEG: 6 or 15
+	const int rx = RC ? RC : rx_arg, ry = RC ? RC : ry_arg;
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int sw = 2 * rx + 1, sh = 2 * ry + 1, N = sw * sh;
@@ -235,9 +238,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 	float* slab = smem + (size_t)warp * icgn2d_warp_floats(rx, ry);
 	uint64_t* bar = (uint64_t*)slab;
 	float* T = slab + 32;
-	float* sR = T + icgn2d_tile_floats(rx, ry);
-	float* sGx = sR + N;
-	float* sGy = sGx + N;
+	float* sC = T + icgn2d_tile_floats(rx, ry); // per-sample constants, interleaved {R, gx, gy} (12-byte lane stride: conflict-free)
 	uint32_t bar_phase = 0;
 	if (use_tma) {
 		if (lane == 0) mbar_init(bar, 1);
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 	const float inv_n = 1.0f / (float)N;
 	const bool lane_on = lane < ncol;
 	const float xl_lane = (float)(lane - rx);
+	const int lane_c = lane_on ? lane : ncol - 1; // idle lanes (subsets narrower than 32) shadow the last column
 
 	while (true) {
 		int poi = 0;
@@ -313,10 +315,10 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					float gx = 0.f, gy = 0.f;
 					if (gx_ok) gx = grad4(q[-2], q[-1], q[1], q[2]);
 					if (gy_ok) gy = grad4(q[-2 * RW], q[-RW], q[RW], q[2 * RW]);
-					const int i = r * sw + lane;
-					sR[i] = R;
-					sGx[i] = gx;
-					sGy[i] = gy;
+					float* pc = sC + 3 * (r * sw + lane);
+					pc[0] = q[0]; // raw R
+					pc[1] = gx;
+					pc[2] = gy;
 					r1 += R;
 					r2 = fmaf(R, R, r2);
 					float g[3] = { gx * gx, gx * gy, gy * gy };
@@ -376,10 +378,10 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			float gx = 0.f, gy = 0.f;
 			if (xg >= 2 && xg < w - 2) gx = grad4(q[-2], q[-1], q[1], q[2]);
 			if (yg >= 2 && yg < h - 2) gy = grad4(q[-2 * RW], q[-RW], q[RW], q[2 * RW]);
-			const int i = r * sw + c;
-			sR[i] = R;
-			sGx[i] = gx;
-			sGy[i] = gy;
+			float* pc = sC + 3 * (r * sw + c);
+			pc[0] = q[0];
+			pc[1] = gx;
+			pc[2] = gy;
 			r1 += R;
 			r2 = fmaf(R, R, r2);
 			float g[3] = { gx * gx, gx * gy, gy * gy };
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		const float xlo = fmaxf(1.f, (float)(tx0 + 1)), xhi = fminf((float)(w - 2), (float)(tx0 + TW - 2));
 		const float ylo = fmaxf(1.f, (float)(ty0 + 1)), yhi = fminf((float)(h - 2), (float)(ty0 + TH - 2));
 		const float xmax = (float)(w - 2), ymax = (float)(h - 2);
-		const float neg_limit = -c0 - 1e-3f; // reference rejects interpolated values < 0 (src/oc_icgn.cpp:251-255)
+		const float neg_limit = -1e-3f; // reference rejects interpolated values < 0 (src/oc_icgn.cpp:251-255)
 
 		// ---------------- IC-GN iterations ----------------
 		// running warp: NP==6 -> A = {W00,W01,W02,W10,W11,W12}; NP==12 -> rows 3,4 of the 6x6 warp
@@ -494,40 +496,117 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				ax0 = fmaf(A[0] * xl_lane + A[3], xl_lane, A[5]); ax1 = fmaf(A[1], xl_lane, A[4]); ax2 = A[2];
 				ay0 = fmaf(A[6] * xl_lane + A[9], xl_lane, A[11]); ay1 = fmaf(A[7], xl_lane, A[10]); ay2 = A[8];
 			}
-			for (int r = 0; r < sh; r++) {
-				const float yl = (float)(r - ry);
-				float X, Y;
+			// Can every row-mapped sample take the fast path (valid + support inside the tile)?  The
+			// affine part of the warp maps the subset to a parallelogram, so its 4 corners decide;
+			// the second-order part is bounded by qx/qy and shrinks the window.
+			bool iter_fast;
+			{
+				float qx = 0.f, qy = 0.f;
+				const float fx = (float)rx, fy = (float)ry;
+				float a0, a1, a2, b0, b1, b2; // X = px + a0 x + a1 y + a2 (+ quadratic), same for Y
 				if constexpr (NP == 6) {
-					X = px + fmaf(ax1, yl, ax0);
-					Y = py + fmaf(ay1, yl, ay0);
+					a0 = A[0]; a1 = A[1]; a2 = A[2]; b0 = A[3]; b1 = A[4]; b2 = A[5];
 				} else {
-					X = px + fmaf(fmaf(ax2, yl, ax1), yl, ax0);
-					Y = py + fmaf(fmaf(ay2, yl, ay1), yl, ay0);
+					a0 = A[3]; a1 = A[4]; a2 = A[5]; b0 = A[9]; b1 = A[10]; b2 = A[11];
+					qx = fabsf(A[0]) * fx * fx + fabsf(A[1]) * fx * fy + fabsf(A[2]) * fy * fy;
+					qy = fabsf(A[6]) * fx * fx + fabsf(A[7]) * fx * fy + fabsf(A[8]) * fy * fy;
 				}
-				const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
-				const bool all_fast = __all_sync(0xffffffffu, fast || !lane_on);
-				if (lane_on) {
-					bool ok = true;
-					if (!all_fast && !fast) ok = (X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax); // NaN fails too
-					if (!ok) {
-						invalid = true;
+				const float cx = px + a2, cy = py + b2;
+				const float ex_ = fabsf(a0) * fx + fabsf(a1) * fy + qx, ey_ = fabsf(b0) * fx + fabsf(b1) * fy + qy;
+				iter_fast = (cx - ex_ >= xlo) && (cx + ex_ < xhi) && (cy - ey_ >= ylo) && (cy + ey_ < yhi); // false for NaN
+			}
+			if (iter_fast) {
+				// branch-free row loop: no per-sample validity tests (min(t) is tested after the loop)
+				float tmin = 0.f;
+				float yl = (float)(-ry);
+				const float* pc = sC + 3 * lane_c;
+				float xs0, xs1, xs2, ys0, ys1, ys2;
+				{
+					const float xl = (float)(lane_c - rx);
+					if constexpr (NP == 6) {
+						xs0 = px + fmaf(A[0], xl, A[2]); xs1 = A[1]; xs2 = 0.f;
+						ys0 = py + fmaf(A[3], xl, A[5]); ys1 = A[4]; ys2 = 0.f;
 					} else {
-						const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, c0, X, Y, all_fast || fast);
-						if (t < neg_limit) invalid = true;
-						const int i = r * sw + lane;
-						const float R = sR[i];
-						const float d = t - R;
-						d1 += d;
-						d2 = fmaf(d, d, d2);
-						rd = fmaf(R, d, rd);
-						float gd[2] = { sGx[i] * d, sGy[i] * d };
+						xs0 = px + fmaf(A[0] * xl + A[3], xl, A[5]); xs1 = fmaf(A[1], xl, A[4]); xs2 = A[2];
+						ys0 = py + fmaf(A[6] * xl + A[9], xl, A[11]); ys1 = fmaf(A[7], xl, A[10]); ys2 = A[8];
+					}
+				}
+				const float* tbase = T - (ty0 + 1) * TW - (tx0 + 1);
+#pragma unroll 3
+				for (int r = 0; r < sh; r++) {
+					float X, Y;
+					if constexpr (NP == 6) {
+						X = fmaf(xs1, yl, xs0);
+						Y = fmaf(ys1, yl, ys0);
+					} else {
+						X = fmaf(fmaf(xs2, yl, xs1), yl, xs0);
+						Y = fmaf(fmaf(ys2, yl, ys1), yl, ys0);
+					}
+					const float xf = floorf(X), yf = floorf(Y);
+					float wx[4], wy[4];
+					bicubic_weights(X - xf, wx);
+					bicubic_weights(Y - yf, wy);
+					const float* q = tbase + (int)yf * TW + (int)xf;
+					float t = 0.f;
 #pragma unroll
-						for (int a = 0; a < 2; a++) {
-							float tt = gd[a];
+					for (int nn = 0; nn < 4; nn++) {
+						float row = fmaf(q[nn * TW + 3], wx[3], fmaf(q[nn * TW + 2], wx[2], fmaf(q[nn * TW + 1], wx[1], q[nn * TW] * wx[0])));
+						t = fmaf(row, wy[nn], t);
+					}
+					tmin = fminf(tmin, t);
+					const float R = pc[0];
+					const float d = lane_on ? t - R : 0.f;
+					d1 += d;
+					d2 = fmaf(d, d, d2);
+					rd = fmaf(R, d, rd);
+					float gd[2] = { pc[1] * d, pc[2] * d };
 #pragma unroll
-							for (int qq = 0; qq <= DEG; qq++) {
-								G[a][qq] += tt;
-								if (qq < DEG) tt *= yl;
+					for (int a = 0; a < 2; a++) {
+						float tt = gd[a];
+#pragma unroll
+						for (int qq = 0; qq <= DEG; qq++) {
+							G[a][qq] += tt;
+							if (qq < DEG) tt *= yl;
+						}
+					}
+					pc += 3 * sw;
+					yl += 1.f;
+				}
+				if (tmin < neg_limit) invalid = true;
+			} else {
+				for (int r = 0; r < sh; r++) {
+					const float yl = (float)(r - ry);
+					float X, Y;
+					if constexpr (NP == 6) {
+						X = px + fmaf(ax1, yl, ax0);
+						Y = py + fmaf(ay1, yl, ay0);
+					} else {
+						X = px + fmaf(fmaf(ax2, yl, ax1), yl, ax0);
+						Y = py + fmaf(fmaf(ay2, yl, ay1), yl, ay0);
+					}
+					if (lane_on) {
+						const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
+						const bool ok = fast || ((X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax)); // NaN fails
+						if (!ok) {
+							invalid = true;
+						} else {
+							const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast);
+							if (t < neg_limit) invalid = true;
+							const float* pc = sC + 3 * (r * sw + lane);
+							const float R = pc[0];
+							const float d = t - R;
+							d1 += d;
+							d2 = fmaf(d, d, d2);
+							rd = fmaf(R, d, rd);
+							float gd[2] = { pc[1] * d, pc[2] * d };
+#pragma unroll
+							for (int a = 0; a < 2; a++) {
+								float tt = gd[a];
+#pragma unroll
+								for (int qq = 0; qq <= DEG; qq++) {
+									G[a][qq] += tt;
+									if (qq < DEG) tt *= yl;
+								}
 							}
 						}
 					}
@@ -561,15 +640,15 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				if (!ok) {
 					invalid = true;
 				} else {
-					const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, c0, X, Y, fast);
+					const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast);
 					if (t < neg_limit) invalid = true;
-					const int i = r * sw + c;
-					const float R = sR[i];
+					const float* pc = sC + 3 * (r * sw + c);
+					const float R = pc[0];
 					const float d = t - R;
 					d1 += d;
 					d2 = fmaf(d, d, d2);
 					rd = fmaf(R, d, rd);
-					float gd[2] = { sGx[i] * d, sGy[i] * d };
+					float gd[2] = { pc[1] * d, pc[2] * d };
 #pragma unroll
 					for (int ii = 0; ii < NPHI; ii++) {
 						const float mm = phi_c(ii) * ipow(xl, phi_p(ii)) * ipow(yl, phi_q(ii));
@@ -589,7 +668,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			for (int k = 0; k < NP; k++) SD[k] = warp_sum(SD[k]);
 			// warped-target statistics: g = t - mean(t) = f + (d - dbar); sum f d = sum R'd - rbar * sum d
 			const float dbar = d1 * inv_n;
-			const float fd = rd - rbar * d1;
+			const float fd = (rd - c0 * d1) - rbar * d1; // rd holds sum R d with the raw R
 			const float g2 = f2 + 2.f * fd + (d2 - d1 * dbar);
 			const float tar_norm = sqrtf(g2);
 			const float factor = ref_norm / tar_norm; // src/oc_icgn.cpp:260
@@ -716,7 +795,9 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	memset(&tm_tar, 0, sizeof(tm_tar));
 	const int use_tma = !getenv("OCB_NO_TMA") && make_tile_map(&tm_ref, img.ref, img.w, img.h, icgn2d_ref_w(rx), icgn2d_ref_h(ry))
 		&& make_tile_map(&tm_tar, img.tar, img.w, img.h, icgn2d_tar_w(rx), icgn2d_tar_h(ry));
-	auto kern = (np == 6) ? icgn2d_kernel<6> : icgn2d_kernel<12>;
+	void (*kern)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int);
+	if (np == 6) kern = (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16> : icgn2d_kernel<6, 0>;
+	else kern = (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20> : icgn2d_kernel<12, 0>;
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
 	*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
