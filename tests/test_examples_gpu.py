@@ -1,0 +1,64 @@
+"""Acceptance: the reference's own example program, compiled UNCHANGED against the C++ shim
+(examples/Makefile -> examples/bin/test_2d_dic_fftcc_icgn1, built where the reference checkout is
+mounted), runs on the GPU and reproduces the reference's shipped result table."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "examples", "bin")
+
+
+def _read_table(path):
+    with open(path) as f:
+        header = f.readline().strip().strip(",").split(",")
+        rows = [[float(x) for x in line.strip().strip(",").split(",")] for line in f if line.strip()]
+    return header, np.array(rows)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "test_2d_dic_fftcc_icgn1")), reason="example binary not built")
+def test_reference_2d_example_runs_unchanged(tmp_path):
+    data = tmp_path / "d:" / "dic_tests" / "2d_dic"  # the example hard-codes d:/dic_tests/2d_dic/...
+    data.mkdir(parents=True)
+    for name in ("oht_cfrp_0.bmp", "oht_cfrp_4.bmp"):
+        shutil.copyfile(os.path.join(util.GOLDEN, name), data / name)
+    out = subprocess.run([os.path.join(BIN, "test_2d_dic_fftcc_icgn1")], cwd=tmp_path, stdin=subprocess.DEVNULL,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "30000 POIs" in out.stdout
+    header, tab = _read_table(data / "oht_cfrp_4_fftcc_icgn1_r16.csv")
+    assert header[:9] == ["x", "y", "u", "v", "u0", "v0", "ZNCC", "iteration", "convergence"]
+    assert tab.shape[0] == 30000
+    g = util.oht_cfrp_golden()
+    gold, rows = g["table"], g["rows"]
+    mine = tab[rows]
+    assert np.array_equal(mine[:, 0:2], gold[:, 0:2])
+    same_guess = (mine[:, 4] == gold[:, 4]) & (mine[:, 5] == gold[:, 5])
+    assert same_guess.mean() > 0.998
+    ok = same_guess & (gold[:, 7] < 10) & (mine[:, 7] == gold[:, 7])
+    assert ok.sum() > 0.93 * len(gold)
+    assert np.abs(mine[ok][:, 2:4] - gold[ok][:, 2:4]).max() < 1e-4
+    assert np.abs(mine[ok, 6] - gold[ok, 6]).max() < 1e-5
+    # the other files the example writes
+    for suffix in ("_deformation.csv", "_u.csv", "_v.csv", "_time.csv"):
+        assert (data / ("oht_cfrp_4_fftcc_icgn1_r16" + suffix)).exists()
+    _, dtab = _read_table(data / "oht_cfrp_4_fftcc_icgn1_r16_deformation.csv")
+    gd = g["deformation"]
+    assert np.abs(dtab[rows][ok][:, [3, 4, 9, 10]] - gd[ok][:, [3, 4, 6, 7]]).max() < 2e-5  # ux uy vx vy
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "dic_fftcc_icgn1_demo")), reason="demo binary not built")
+def test_shim_demo(tmp_path):
+    out_csv = tmp_path / "out.csv"
+    out = subprocess.run([os.path.join(BIN, "dic_fftcc_icgn1_demo"), os.path.join(util.GOLDEN, "oht_cfrp_0.bmp"),
+                          os.path.join(util.GOLDEN, "oht_cfrp_4.bmp"), str(out_csv), "16", "8"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    _, tab = _read_table(out_csv)
+    assert tab.shape[0] > 1000 and (tab[:, 6] > 0.9).mean() > 0.9
