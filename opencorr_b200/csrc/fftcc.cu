@@ -15,6 +15,10 @@
 
 namespace ocb {
 
+// floor(x / d) for 0 <= x < 2^21 and d >= 1 via one FMUL (inv = 1.0f / d): exact because the
+// distance of (x + 0.5) / d to the nearest integer is >= 0.5 / d, far above the fp32 rounding error.
+__device__ __forceinline__ int fdiv(int x, float inv) { return __float2int_rz(((float)x + 0.5f) * inv); }
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -36,10 +40,11 @@ __device__ void fft_axis(float2** pin, float2** pout, const FftAxis& ax, int s0,
 		const int tstep = n / ncur;
 		const int per_batch = m * s;
 		const int total = batch * per_batch;
+		const float inv_pb = 1.0f / (float)per_batch, inv_s = 1.0f / (float)s;
 		for (int t = threadIdx.x; t < total; t += blockDim.x) {
-			const int bi = t / per_batch;
+			const int bi = fdiv(t, inv_pb);
 			const int rem = t - bi * per_batch;
-			const int p = rem / s;
+			const int p = fdiv(rem, inv_s);
 			const int q = rem - p * s;
 			const float2* src = in + (size_t)bi * bstride + q + s * p;
 			float2* dst = out + (size_t)bi * bstride + q + s * (r * p);
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(128) fftcc2d_kernel(Image2D img, float* __rest
 	for (int i = threadIdx.x; i < sw; i += blockDim.x) twx[i] = fp.tw_x[i];
 	for (int i = threadIdx.x; i < sh; i += blockDim.x) twy[i] = fp.tw_y[i];
 	const int w = img.w, h = img.h;
+	const float inv_sw = 1.0f / (float)sw;
 
 	for (int poi = blockIdx.x; poi < n_poi; poi += gridDim.x) {
 		float* P = pois + (size_t)poi * P2_N;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(128) fftcc2d_kernel(Image2D img, float* __rest
 		// fill both windows (src/oc_fftcc.cpp:204-219): float coordinate arithmetic, then (int) truncation
 		float sa = 0.f, sb = 0.f;
 		for (int i = threadIdx.x; i < M; i += blockDim.x) {
-			const int r = i / sw, c = i - r * sw;
+			const int r = fdiv(i, inv_sw), c = i - r * sw;
 			const float rpx = px + c - rx, rpy = py + r - ry;
 			const float a = __ldg(img.ref + (size_t)(int)rpy * w + (int)rpx);
 			const float tpx = rpx + u0, tpy = rpy + v0;
@@ -204,8 +210,8 @@ __global__ void __launch_bounds__(128) fftcc2d_kernel(Image2D img, float* __rest
 		fft_axis(&in, &out, fp.ax, 1, sh, sw, twx, false);
 		fft_axis(&in, &out, fp.ay, sw, 1, 0, twy, false);
 		for (int i = threadIdx.x; i < M; i += blockDim.x) {
-			const int ky = i / sw, kx = i - ky * sw;
-			const int j = ((sh - ky) % sh) * sw + ((sw - kx) % sw);
+			const int ky = fdiv(i, inv_sw), kx = i - ky * sw;
+			const int j = (ky ? sh - ky : 0) * sw + (kx ? sw - kx : 0);
 			out[i] = cross_spectrum(in[i], in[j]);
 		}
 		__syncthreads();
@@ -255,6 +261,7 @@ __global__ void __launch_bounds__(256) fftcc3d_kernel(Image3D img, float* __rest
 	for (int i = threadIdx.x; i < sz; i += blockDim.x) twz[i] = fp.tw_z[i];
 	float2* S = fp.scratch + (size_t)blockIdx.x * M;
 	const int dx = img.dx, dy = img.dy, dz = img.dz;
+	const float inv_sx = 1.0f / (float)sx, inv_slice = 1.0f / (float)slice, inv_rowp = 1.0f / (float)(sz * sx);
 
 	for (int poi = blockIdx.x; poi < n_poi; poi += gridDim.x) {
 		float* P = pois + (size_t)poi * P3_N;
@@ -276,12 +283,16 @@ __global__ void __launch_bounds__(256) fftcc3d_kernel(Image3D img, float* __rest
 		__syncthreads();
 		// pass 0: means (src/oc_fftcc.cpp:346-367)
 		float sa = 0.f, sb = 0.f;
-		for (size_t i = threadIdx.x; i < M; i += blockDim.x) {
-			const int k = (int)(i % sx), j = (int)((i / sx) % sy), ii = (int)(i / slice);
-			const float rpx = px + k - rx, rpy = py + j - ry, rpz = pz + ii - rz;
-			sa += __ldg(img.ref + ((size_t)(int)rpz * dy + (int)rpy) * dx + (int)rpx);
-			const float tpx = rpx + u0, tpy = rpy + v0, tpz = rpz + w0;
-			sb += __ldg(img.tar + ((size_t)(int)tpz * dy + (int)tpy) * dx + (int)tpx);
+		for (int ii = 0; ii < sz; ii++) {
+			const float rpz = pz + ii - rz;
+			const float tpz = rpz + w0;
+			for (int i = threadIdx.x; i < slice; i += blockDim.x) {
+				const int j = fdiv(i, inv_sx), k = i - j * sx;
+				const float rpx = px + k - rx, rpy = py + j - ry;
+				sa += __ldg(img.ref + ((size_t)(int)rpz * dy + (int)rpy) * dx + (int)rpx);
+				const float tpx = rpx + u0, tpy = rpy + v0;
+				sb += __ldg(img.tar + ((size_t)(int)tpz * dy + (int)tpy) * dx + (int)tpx);
+			}
 		}
 		block_sum2(sa, sb, red);
 		const float ref_mean = sa / (float)M, tar_mean = sb / (float)M;
@@ -291,7 +302,7 @@ __global__ void __launch_bounds__(256) fftcc3d_kernel(Image3D img, float* __rest
 			const float rpz = pz + ii - rz;
 			const float tpz = rpz + w0;
 			for (int i = threadIdx.x; i < slice; i += blockDim.x) {
-				const int j = i / sx, k = i - j * sx;
+				const int j = fdiv(i, inv_sx), k = i - j * sx;
 				const float rpx = px + k - rx, rpy = py + j - ry;
 				float a = __ldg(img.ref + ((size_t)(int)rpz * dy + (int)rpy) * dx + (int)rpx) - ref_mean;
 				const float tpx = rpx + u0, tpy = rpy + v0;
@@ -315,9 +326,9 @@ __global__ void __launch_bounds__(256) fftcc3d_kernel(Image3D img, float* __rest
 			const int kyn = (sy - ky) % sy;
 			const int nrow = (kyn == ky) ? 1 : 2;
 			for (int i = threadIdx.x; i < nrow * sz * sx; i += blockDim.x) {
-				const int rs = i / (sz * sx);
+				const int rs = fdiv(i, inv_rowp);
 				const int rem = i - rs * sz * sx;
-				const int kz = rem / sx, kx = rem - kz * sx;
+				const int kz = fdiv(rem, inv_sx), kx = rem - kz * sx;
 				bufA[i] = __ldcg(S + ((size_t)kz * sy + (rs ? kyn : ky)) * sx + kx);
 			}
 			__syncthreads();
@@ -325,20 +336,20 @@ __global__ void __launch_bounds__(256) fftcc3d_kernel(Image3D img, float* __rest
 			float2* out = bufB;
 			fft_axis(&in, &out, fp.az, sx, nrow, sz * sx, twz, false);
 			for (int i = threadIdx.x; i < nrow * sz * sx; i += blockDim.x) {
-				const int rs = i / (sz * sx);
+				const int rs = fdiv(i, inv_rowp);
 				const int rem = i - rs * sz * sx;
-				const int kz = rem / sx, kx = rem - kz * sx;
+				const int kz = fdiv(rem, inv_sx), kx = rem - kz * sx;
 				const int prs = (nrow == 2) ? 1 - rs : 0;
-				const int j = prs * sz * sx + ((sz - kz) % sz) * sx + ((sx - kx) % sx);
+				const int j = prs * sz * sx + (kz ? sz - kz : 0) * sx + (kx ? sx - kx : 0);
 				out[i] = cross_spectrum(in[i], in[j]);
 			}
 			__syncthreads();
 			{ float2* t = in; in = out; out = t; }
 			fft_axis(&in, &out, fp.az, sx, nrow, sz * sx, twz, true);
 			for (int i = threadIdx.x; i < nrow * sz * sx; i += blockDim.x) {
-				const int rs = i / (sz * sx);
+				const int rs = fdiv(i, inv_rowp);
 				const int rem = i - rs * sz * sx;
-				const int kz = rem / sx, kx = rem - kz * sx;
+				const int kz = fdiv(rem, inv_sx), kx = rem - kz * sx;
 				S[((size_t)kz * sy + (rs ? kyn : ky)) * sx + kx] = in[i];
 			}
 			__syncthreads();

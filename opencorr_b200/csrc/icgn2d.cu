@@ -24,54 +24,23 @@
 //   update  : solve with the Cholesky factors, compose W <- W * W(dp)^-1 in registers.
 // Samples whose 4x4 support leaves the staged tile (large deformation gradients) are read from
 // global memory instead, so results never depend on the tile size.
-#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "ocb_kernels.h"
+#include "ocb_tma.cuh"
 
 namespace ocb {
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives, one barrier per warp -----------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-	asm volatile(
-		"{\n\t"
-		".reg .pred p;\n\t"
-		"WAIT_LOOP:\n\t"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra.uni WAIT_DONE;\n\t"
-		"bra.uni WAIT_LOOP;\n\t"
-		"WAIT_DONE:\n\t"
-		"}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 2D tile load: box (set in the tensor map) whose upper-left corner is (x, y); out-of-image = 0
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-		"l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-		: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int ICGN2D_TILE_MARGIN = 1; // slack (pixels) around subset+support in the target tile
 // TMA tile loads need the innermost coordinate 16-byte aligned (x multiple of 4 floats; measured: an
 // unaligned x raises 'illegal instruction'), so tile origins are rounded down to a multiple of 4 and
 // the boxes are 3 columns wider.
 
-__host__ __device__ inline int round_up4(int v) { return (v + 3) & ~3; }
-__host__ __device__ inline int floor4(int v) { return v & ~3; } // rounds toward -inf (two's complement)
 __host__ __device__ inline int icgn2d_ref_w(int rx) { return round_up4(2 * rx + 1 + 4 + 3); }
 __host__ __device__ inline int icgn2d_ref_h(int ry) { return 2 * ry + 1 + 4; }
 __host__ __device__ inline int icgn2d_tar_w(int rx) { return round_up4(2 * rx + 1 + 3 + 2 * ICGN2D_TILE_MARGIN + 3); }
 __host__ __device__ inline int icgn2d_tar_h(int ry) { return 2 * ry + 1 + 3 + 2 * ICGN2D_TILE_MARGIN; }
-__host__ __device__ inline int round_up32(int v) { return (v + 31) & ~31; }
 // per-warp slab (floats): [0,32) mbarrier + pad | tile T (TMA destination, 128-B aligned) | R', gx, gy
 __host__ __device__ inline int icgn2d_tile_floats(int rx, int ry) {
 	const int a = icgn2d_ref_w(rx) * icgn2d_ref_h(ry), b = icgn2d_tar_w(rx) * icgn2d_tar_h(ry);
@@ -745,35 +714,6 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 }
 
 // host-side launch ---------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-	const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-	static EncodeTiledFn fn = nullptr;
-	static bool tried = false;
-	if (!tried) {
-		tried = true;
-		void* p = nullptr;
-		cudaDriverEntryPointQueryResult qres;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-			fn = (EncodeTiledFn)p;
-	}
-	return fn;
-}
-
-// Tensor map over a row-major f32 image for (box_w x box_h) tile loads; false when TMA cannot be used
-// (row pitch or base not 16-byte aligned, box too large, driver entry point missing).
-static bool make_tile_map(CUtensorMap* map, const float* base, int w, int h, int box_w, int box_h) {
-	EncodeTiledFn fn = get_encode_fn();
-	if (!fn || (w % 4) != 0 || ((uintptr_t)base % 16) != 0 || box_w > 256 || box_h > 256) return false;
-	cuuint64_t dims[2] = { (cuuint64_t)w, (cuuint64_t)h };
-	cuuint64_t strides[1] = { (cuuint64_t)w * sizeof(float) };
-	cuuint32_t box[2] = { (cuuint32_t)box_w, (cuuint32_t)box_h };
-	cuuint32_t estr[2] = { 1, 1 };
-	return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-			   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // Returns 0, -1 when one warp's slab does not fit in shared memory, -2 on a CUDA error.
 // d_counter: one int of device memory owned by the context (work queue head).
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
@@ -793,8 +733,9 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	CUtensorMap tm_ref, tm_tar;
 	memset(&tm_ref, 0, sizeof(tm_ref));
 	memset(&tm_tar, 0, sizeof(tm_tar));
-	const int use_tma = !getenv("OCB_NO_TMA") && make_tile_map(&tm_ref, img.ref, img.w, img.h, icgn2d_ref_w(rx), icgn2d_ref_h(ry))
-		&& make_tile_map(&tm_tar, img.tar, img.w, img.h, icgn2d_tar_w(rx), icgn2d_tar_h(ry));
+	const int dims[2] = { img.w, img.h };
+	const int box_ref[2] = { icgn2d_ref_w(rx), icgn2d_ref_h(ry) }, box_tar[2] = { icgn2d_tar_w(rx), icgn2d_tar_h(ry) };
+	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm_ref, img.ref, 2, dims, box_ref) && tma_make_map(&tm_tar, img.tar, 2, dims, box_tar);
 	void (*kern)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int);
 	if (np == 6) kern = (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16> : icgn2d_kernel<6, 0>;
 	else kern = (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20> : icgn2d_kernel<12, 0>;

@@ -5,11 +5,21 @@
 // (src/oc_gradient.cpp:143-231) and TricubicBspline::prepare/compute
 // (src/oc_cubic_bspline.cpp:214-405).
 //
-// Mapping: ONE CTA (256 threads) PER POI; the (2r+1)^3 samples are strided over the CTA with x
-// fastest, so the reference-volume reads (value + 3 gradient volumes) are coalesced.  Per-iteration
-// single-pass sums as in icgn2d.cu; the 12x12 Cholesky factor and the running 3x4 warp live in
-// shared memory and are updated by one thread between two barriers.
+// Mapping: ONE CTA (256 threads) PER POI, persistent CTAs pulling POIs from an atomic counter; the
+// (2r+1)^3 samples are strided over the CTA with x fastest, so the reference-volume reads (value + 3
+// gradient volumes) are coalesced.  The 64-tap tricubic evaluation reads a B-spline coefficient TILE
+// staged in shared memory by TMA.  A (2r+8)^3 tile does not fit next to a second CTA, so the subset
+// is processed in z-SLABS: per iteration and slab, one 3D TMA box (x origin 16-byte aligned, centred
+// on the CURRENT warp) lands in smem, all samples of the slab are evaluated from it, the next slab
+// replaces it; two CTAs per SM overlap one CTA's load with the other's math.  Samples whose support
+// leaves the tile (large deformation gradients) read the coefficient volume through L1/L2 instead.
+// Per-iteration single-pass sums as in icgn2d.cu; the 12x12 Cholesky factor and the running 3x4
+// warp live in shared memory and are updated by one thread between two barriers.
+#include <stdlib.h>
+#include <string.h>
+
 #include "ocb_kernels.h"
+#include "ocb_tma.cuh"
 
 namespace ocb {
 
@@ -71,8 +81,9 @@ void prefilter3d_launch(const float* in, float* out, int dx, int dy, int dz, int
 // ---- ICGN3D1::compute ---------------------------------------------------------------------------
 constexpr int NP3 = 12;
 constexpr int NH3 = NP3 * (NP3 + 1) / 2; // 78
-constexpr int NSETUP = NH3 + 2 * NP3 + 1; // Hessian + S + SF + f2 = 103
-constexpr int NITER = 3 + NP3;            // d1, d2, fd, SD[12]
+constexpr int NSETUP = NH3 + 2 * NP3 + 2; // Hessian + S + SR + r1 + r2 = 104
+constexpr int NITER = 3 + NP3;            // d1, d2, rd, SD[12]
+constexpr int ICGN3D_TILE_MARGIN = 1;
 
 struct Icgn3dShared {
 	float part[ICGN3D_WARPS][NSETUP]; // per-warp partial sums
@@ -80,29 +91,47 @@ struct Icgn3dShared {
 	float L[NH3];   // packed Cholesky factor (diag = 1/L_ii)
 	float S[NP3], SF[NP3];
 	float A[12];    // running warp rows: [1+ux uy uz u | vx 1+vy vz v | wx wy 1+wz w]
-	float f2, ref_mean;
+	float f2, rbar, c0;
 	float dp_norm, zncc;
 	int keep_going;
+	int poi;
 };
 
-__device__ __forceinline__ float tricubic_sample(const float* __restrict__ coef, int dx, int dy, float X, float Y, float Z) {
-	const float xf = floorf(X), yf = floorf(Y), zf = floorf(Z);
-	float bx[4], by[4], bz[4];
-	bspline_basis(X - xf, bx);
-	bspline_basis(Y - yf, by);
-	bspline_basis(Z - zf, bz);
-	const float* base = coef + ((size_t)((int)zf - 1) * dy + ((int)yf - 1)) * dx + ((int)xf - 1);
+// floor(x / d) for 0 <= x < 2^21, d >= 1 (inv = 1.0f / d); see fftcc.cu
+__device__ __forceinline__ int fdiv3(int x, float inv) { return __float2int_rz(((float)x + 0.5f) * inv); }
+
+// Cubic B-spline basis (src/oc_cubic_bspline.cpp:35-53), 12 operations: b0 = (1-t)^3/6, b3 = t^3/6,
+// b1 = 2/3 - t^2 (1 - t/2), b2 = 1 - b0 - b1 - b3 (partition of unity)
+__device__ __forceinline__ void bspline_basis_fast(float t, float* b) {
+	const float om = 1.f - t, t2 = t * t;
+	b[0] = om * om * om * (1.f / 6.f);
+	b[3] = t2 * t * (1.f / 6.f);
+	b[1] = fmaf(t2, fmaf(0.5f, t, -1.f), 2.f / 3.f);
+	b[2] = ((1.f - b[0]) - b[1]) - b[3];
+}
+
+// 64-tap evaluation (src/oc_cubic_bspline.cpp:390-401) from a dense array with pitches (py_, pz_) floats
+template <bool GLOBAL>
+__device__ __forceinline__ float tricubic_taps(const float* __restrict__ base, int py_, int pz_, const float* bx, const float* by, const float* bz) {
 	float value = 0.f;
 #pragma unroll
 	for (int i = 0; i < 4; i++) {
 		float sy_acc = 0.f;
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-			const float* row = base + ((size_t)i * dy + j) * dx;
-			float sx_acc = __ldg(row) * bx[0];
-			sx_acc = fmaf(__ldg(row + 1), bx[1], sx_acc);
-			sx_acc = fmaf(__ldg(row + 2), bx[2], sx_acc);
-			sx_acc = fmaf(__ldg(row + 3), bx[3], sx_acc);
+			const float* row = base + i * pz_ + j * py_;
+			float sx_acc;
+			if (GLOBAL) {
+				sx_acc = __ldg(row) * bx[0];
+				sx_acc = fmaf(__ldg(row + 1), bx[1], sx_acc);
+				sx_acc = fmaf(__ldg(row + 2), bx[2], sx_acc);
+				sx_acc = fmaf(__ldg(row + 3), bx[3], sx_acc);
+			} else {
+				sx_acc = row[0] * bx[0];
+				sx_acc = fmaf(row[1], bx[1], sx_acc);
+				sx_acc = fmaf(row[2], bx[2], sx_acc);
+				sx_acc = fmaf(row[3], bx[3], sx_acc);
+			}
 			sy_acc = fmaf(sx_acc, by[j], sy_acc);
 		}
 		value = fmaf(sy_acc, bz[i], value);
@@ -110,21 +139,41 @@ __device__ __forceinline__ float tricubic_sample(const float* __restrict__ coef,
 	return value;
 }
 
-__global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, float* __restrict__ pois, int n_poi, int rx, int ry, int rz,
-	float conv_criterion, float stop_condition) {
+__host__ __device__ inline int icgn3d_tile_x(int rx) { return round_up4(2 * rx + 1 + 3 + 2 * ICGN3D_TILE_MARGIN + 3); }
+__host__ __device__ inline int icgn3d_tile_y(int ry) { return 2 * ry + 1 + 3 + 2 * ICGN3D_TILE_MARGIN; }
+__host__ __device__ inline int icgn3d_tile_z(int slab_k) { return slab_k + 3 + 2 * ICGN3D_TILE_MARGIN; }
+
+// RC > 0: radius known at compile time (rx == ry == rz == RC): tile pitches become immediates.
+template <int RC>
+__global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg, int rz_arg,
+	float conv_criterion, float stop_condition, int slab_k, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_coef, int use_tma) {
+	extern __shared__ __align__(128) float dsmem[];
 	__shared__ Icgn3dShared sh;
+	uint64_t* bar = (uint64_t*)dsmem;
+	float* T = dsmem + 32;
+	const int rx = RC ? RC : rx_arg, ry = RC ? RC : ry_arg, rz = RC ? RC : rz_arg;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int sx = 2 * rx + 1, sy = 2 * ry + 1, sz = 2 * rz + 1;
 	const int slice = sx * sy, N = slice * sz;
 	const int dx = img.dx, dy = img.dy, dz = img.dz;
-	const float inv_n = 1.0f / (float)N;
+	const int TX = icgn3d_tile_x(rx), TY = icgn3d_tile_y(ry), TZ = icgn3d_tile_z(slab_k);
+	const int TXY = TX * TY;
+	const float inv_n = 1.0f / (float)N, inv_slice = 1.0f / (float)slice, inv_sx = 1.0f / (float)sx;
+	const float* __restrict__ coef = img.coef;
+	uint32_t bar_phase = 0;
+	if (tid == 0 && use_tma) mbar_init(bar, 1);
+	__syncthreads();
 
-	for (int poi = blockIdx.x; poi < n_poi; poi += gridDim.x) {
+	while (true) {
+		if (tid == 0) sh.poi = atomicAdd(work_counter, 1);
+		__syncthreads();
+		const int poi = sh.poi;
+		if (poi >= n_poi) break;
 		float* P = pois + (size_t)poi * P3_N;
 		const float px = P[P3_X], py = P[P3_Y], pz = P[P3_Z];
 		const float u_in = P[P3_DEF + 0], v_in = P[P3_DEF + 4], w_in = P[P3_DEF + 8];
 		const float zncc_in = P[P3_ZNCC];
-		__syncthreads(); // everyone has read the record before thread 0 may overwrite it
+		__syncthreads(); // everyone has read the record (and sh.poi) before thread 0 may overwrite them
 		// guard, src/oc_icgn.cpp:1279-1286
 		if ((px - rx) < 0 || (py - ry) < 0 || (pz - rz) < 0 || (px + rx) > (dx - 1) || (py + ry) > (dy - 1) || (pz + rz) > (dz - 1)
 			|| fabsf(u_in) >= dx || fabsf(v_in) >= dy || fabsf(w_in) >= dz || zncc_in < 0
@@ -133,35 +182,18 @@ __global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, fl
 			continue;
 		}
 		const int x0 = (int)px - rx, y0 = (int)py - ry, z0 = (int)pz - rz;
-		const float* refb = img.ref + ((size_t)z0 * dy + y0) * dx + x0;
 		const size_t goff = ((size_t)z0 * dy + y0) * dx + x0;
+		const float c0 = __ldg(img.ref + ((size_t)(int)pz * dy + (int)py) * dx + (int)px); // pilot value: centre voxel
 
-		// ---- reference subset mean (Subset3D::zeroMeanNorm, src/oc_subset.cpp:104-117)
-		float s1 = 0.f;
-		for (int i = tid; i < N; i += ICGN3D_THREADS) {
-			const int ii = i / slice, rem = i - ii * slice, j = rem / sx, k = rem - j * sx;
-			s1 += __ldg(refb + ((size_t)ii * dy + j) * dx + k);
-		}
-		s1 = warp_sum(s1);
-		if (lane == 0) sh.part[warp][0] = s1;
-		__syncthreads();
-		if (tid == 0) {
-			float t = 0.f;
-			for (int i = 0; i < ICGN3D_WARPS; i++) t += sh.part[i][0];
-			sh.ref_mean = t * inv_n;
-		}
-		__syncthreads();
-		const float ref_mean = sh.ref_mean;
-
-		// ---- steepest-descent images + Hessian (src/oc_icgn.cpp:1298-1337)
+		// ---- reference subset statistics + steepest-descent images + Hessian (src/oc_icgn.cpp:1291-1337)
 		{
 			float acc[NSETUP];
 #pragma unroll
 			for (int k = 0; k < NSETUP; k++) acc[k] = 0.f;
 			for (int i = tid; i < N; i += ICGN3D_THREADS) {
-				const int ii = i / slice, rem = i - ii * slice, j = rem / sx, k = rem - j * sx;
+				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
 				const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
-				const float f = __ldg(img.ref + o) - ref_mean;
+				const float R = __ldg(img.ref + o) - c0;
 				const float gx = __ldg(img.gx + o), gy = __ldg(img.gy + o), gz = __ldg(img.gz + o);
 				const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
 				float sd[NP3];
@@ -171,11 +203,12 @@ __global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, fl
 #pragma unroll
 				for (int a = 0; a < NP3; a++) {
 					acc[NH3 + a] += sd[a];
-					acc[NH3 + NP3 + a] = fmaf(sd[a], f, acc[NH3 + NP3 + a]);
+					acc[NH3 + NP3 + a] = fmaf(sd[a], R, acc[NH3 + NP3 + a]);
 #pragma unroll
 					for (int b = 0; b <= a; b++) acc[a * (a + 1) / 2 + b] = fmaf(sd[a], sd[b], acc[a * (a + 1) / 2 + b]);
 				}
-				acc[NSETUP - 1] = fmaf(f, f, acc[NSETUP - 1]);
+				acc[NSETUP - 2] += R;
+				acc[NSETUP - 1] = fmaf(R, R, acc[NSETUP - 1]);
 			}
 #pragma unroll
 			for (int k = 0; k < NSETUP; k++) {
@@ -197,8 +230,15 @@ __global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, fl
 			cholesky_packed<NP3>(Hh);
 #pragma unroll
 			for (int k = 0; k < NH3; k++) sh.L[k] = Hh[k];
-			for (int k = 0; k < NP3; k++) { sh.S[k] = sh.tot[NH3 + k]; sh.SF[k] = sh.tot[NH3 + NP3 + k]; }
-			sh.f2 = sh.tot[NSETUP - 1];
+			const float r1 = sh.tot[NSETUP - 2], r2 = sh.tot[NSETUP - 1];
+			const float rbar = r1 * inv_n; // mean(R) - c0  (Subset3D::zeroMeanNorm, src/oc_subset.cpp:104-132)
+			sh.rbar = rbar;
+			sh.f2 = r2 - r1 * rbar;
+			sh.c0 = c0;
+			for (int k = 0; k < NP3; k++) {
+				sh.S[k] = sh.tot[NH3 + k];
+				sh.SF[k] = sh.tot[NH3 + NP3 + k] - rbar * sh.tot[NH3 + k]; // sum sd_k f = sum sd_k R' - rbar sum sd_k
+			}
 			// initial warp (Deformation3D1::setWarp, src/oc_deformation.cpp:495-516)
 			sh.A[0] = 1.f + P[P3_DEF + 1]; sh.A[1] = P[P3_DEF + 2]; sh.A[2] = P[P3_DEF + 3]; sh.A[3] = u_in;
 			sh.A[4] = P[P3_DEF + 5]; sh.A[5] = 1.f + P[P3_DEF + 6]; sh.A[6] = P[P3_DEF + 7]; sh.A[7] = v_in;
@@ -219,31 +259,80 @@ __global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, fl
 #pragma unroll
 			for (int k = 0; k < NITER; k++) acc[k] = 0.f;
 			int invalid = 0;
-			for (int i = tid; i < N; i += ICGN3D_THREADS) {
-				const int ii = i / slice, rem = i - ii * slice, j = rem / sx, k = rem - j * sx;
-				const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
-				// Deformation3D1::warp, src/oc_deformation.cpp:518-530; centre + warped (:1376)
-				const float X = px + fmaf(A[0], xl, fmaf(A[1], yl, fmaf(A[2], zl, A[3])));
-				const float Y = py + fmaf(A[4], xl, fmaf(A[5], yl, fmaf(A[6], zl, A[7])));
-				const float Z = pz + fmaf(A[8], xl, fmaf(A[9], yl, fmaf(A[10], zl, A[11])));
-				// TricubicBspline::compute validity, src/oc_cubic_bspline.cpp:356-361
-				const bool ok = (X >= 1.f) && (Y >= 1.f) && (Z >= 1.f) && (X < xmax) && (Y < ymax) && (Z < zmax);
-				if (!ok) {
-					invalid = 1;
-					continue;
+			float tmin = 0.f;
+			// tile origin in x, y follows the CURRENT translation; x is 16-byte aligned for TMA
+			const int tx0 = floor4((int)floorf(px + A[3]) - rx - 1 - ICGN3D_TILE_MARGIN);
+			const int ty0 = (int)floorf(py + A[7]) - ry - 1 - ICGN3D_TILE_MARGIN;
+			const float xlo = fmaxf(1.f, (float)(tx0 + 1)), xhi = fminf(xmax, (float)(tx0 + TX - 2));
+			const float ylo = fmaxf(1.f, (float)(ty0 + 1)), yhi = fminf(ymax, (float)(ty0 + TY - 2));
+			for (int zs = 0; zs < sz; zs += slab_k) {
+				const int nz = (sz - zs) < slab_k ? (sz - zs) : slab_k;
+				// slab centre line in z: Z = pz + w + (1 + wz) zl (+ shear); origin from its first layer
+				const float zl0 = (float)(zs - rz);
+				const float zc_lo = pz + A[11] + fminf(A[10] * zl0, A[10] * (zl0 + (float)(nz - 1)));
+				const int tz0 = (int)floorf(zc_lo) - 1 - ICGN3D_TILE_MARGIN;
+				const float zlo = fmaxf(1.f, (float)(tz0 + 1)), zhi = fminf(zmax, (float)(tz0 + TZ - 2));
+				__syncthreads(); // previous slab's readers are done with T
+				if (use_tma) {
+					if (tid == 0) {
+						fence_proxy_async();
+						mbar_expect_tx(bar, (uint32_t)(TXY * TZ * sizeof(float)));
+						tma_load_3d(T, &tm_coef, tx0, ty0, tz0, bar);
+					}
+					mbar_wait(bar, bar_phase);
+					bar_phase ^= 1;
+				} else {
+					const float inv_txy = 1.0f / (float)TXY, inv_tx = 1.0f / (float)TX;
+					for (int i = tid; i < TXY * TZ; i += ICGN3D_THREADS) {
+						const int tz = fdiv3(i, inv_txy), rem = i - tz * TXY, ty = fdiv3(rem, inv_tx), tx = rem - ty * TX;
+						const int gx_ = tx0 + tx, gy_ = ty0 + ty, gz_ = tz0 + tz;
+						float v = 0.f;
+						if (gx_ >= 0 && gx_ < dx && gy_ >= 0 && gy_ < dy && gz_ >= 0 && gz_ < dz) v = __ldg(coef + ((size_t)gz_ * dy + gy_) * dx + gx_);
+						T[i] = v;
+					}
+					__syncthreads();
 				}
-				const float t = tricubic_sample(img.coef, dx, dy, X, Y, Z);
-				const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
-				const float f = __ldg(img.ref + o) - ref_mean;
-				const float d = (t - ref_mean) - f;
-				acc[0] += d;
-				acc[1] = fmaf(d, d, acc[1]);
-				acc[2] = fmaf(f, d, acc[2]);
-				const float gxd = __ldg(img.gx + o) * d, gyd = __ldg(img.gy + o) * d, gzd = __ldg(img.gz + o) * d;
-				acc[3] += gxd; acc[4] = fmaf(gxd, xl, acc[4]); acc[5] = fmaf(gxd, yl, acc[5]); acc[6] = fmaf(gxd, zl, acc[6]);
-				acc[7] += gyd; acc[8] = fmaf(gyd, xl, acc[8]); acc[9] = fmaf(gyd, yl, acc[9]); acc[10] = fmaf(gyd, zl, acc[10]);
-				acc[11] += gzd; acc[12] = fmaf(gzd, xl, acc[12]); acc[13] = fmaf(gzd, yl, acc[13]); acc[14] = fmaf(gzd, zl, acc[14]);
+				const float* tbase = T - ((tz0 + 1) * TXY + (ty0 + 1) * TX + (tx0 + 1));
+				const int ns = nz * slice;
+				for (int i = tid; i < ns; i += ICGN3D_THREADS) {
+					const int il = fdiv3(i, inv_slice), rem = i - il * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
+					const int ii = zs + il;
+					const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
+					// Deformation3D1::warp, src/oc_deformation.cpp:518-530; centre + warped (:1376)
+					const float X = px + fmaf(A[0], xl, fmaf(A[1], yl, fmaf(A[2], zl, A[3])));
+					const float Y = py + fmaf(A[4], xl, fmaf(A[5], yl, fmaf(A[6], zl, A[7])));
+					const float Z = pz + fmaf(A[8], xl, fmaf(A[9], yl, fmaf(A[10], zl, A[11])));
+					const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi) && (Z >= zlo) && (Z < zhi);
+					if (!fast) {
+						// TricubicBspline::compute validity, src/oc_cubic_bspline.cpp:356-361 (NaN fails too)
+						const bool ok = (X >= 1.f) && (Y >= 1.f) && (Z >= 1.f) && (X < xmax) && (Y < ymax) && (Z < zmax);
+						if (!ok) {
+							invalid = 1;
+							continue;
+						}
+					}
+					const float xf = floorf(X), yf = floorf(Y), zf = floorf(Z);
+					float bx[4], by[4], bz[4];
+					bspline_basis_fast(X - xf, bx);
+					bspline_basis_fast(Y - yf, by);
+					bspline_basis_fast(Z - zf, bz);
+					float t;
+					if (fast) t = tricubic_taps<false>(tbase + ((int)zf * TXY + (int)yf * TX + (int)xf), TX, TXY, bx, by, bz);
+					else t = tricubic_taps<true>(coef + ((size_t)((int)zf - 1) * dy + ((int)yf - 1)) * dx + ((int)xf - 1), dx, dx * dy, bx, by, bz);
+					tmin = fminf(tmin, t);
+					const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
+					const float R = __ldg(img.ref + o);
+					const float d = t - R;
+					acc[0] += d;
+					acc[1] = fmaf(d, d, acc[1]);
+					acc[2] = fmaf(R, d, acc[2]);
+					const float gxd = __ldg(img.gx + o) * d, gyd = __ldg(img.gy + o) * d, gzd = __ldg(img.gz + o) * d;
+					acc[3] += gxd; acc[4] = fmaf(gxd, xl, acc[4]); acc[5] = fmaf(gxd, yl, acc[5]); acc[6] = fmaf(gxd, zl, acc[6]);
+					acc[7] += gyd; acc[8] = fmaf(gyd, xl, acc[8]); acc[9] = fmaf(gyd, yl, acc[9]); acc[10] = fmaf(gyd, zl, acc[10]);
+					acc[11] += gzd; acc[12] = fmaf(gzd, xl, acc[12]); acc[13] = fmaf(gzd, yl, acc[13]); acc[14] = fmaf(gzd, zl, acc[14]);
+				}
 			}
+			if (tmin < -1e-3f) invalid = 1; // the reference rejects interpolated values < 0 (src/oc_icgn.cpp:1378-1381)
 #pragma unroll
 			for (int k = 0; k < NITER; k++) {
 				float v = warp_sum(acc[k]);
@@ -261,8 +350,9 @@ __global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, fl
 					for (int i = 0; i < ICGN3D_WARPS; i++) t += sh.part[i][k];
 					tot[k] = t;
 				}
-				const float f2 = sh.f2;
-				const float d1 = tot[0], d2 = tot[1], fd = tot[2];
+				const float f2 = sh.f2, rbar = sh.rbar;
+				const float d1 = tot[0], d2 = tot[1];
+				const float fd = (tot[2] - sh.c0 * d1) - rbar * d1; // sum f d, from sum R d with the raw R
 				const float dbar = d1 * inv_n;
 				const float g2 = f2 + 2.f * fd + (d2 - d1 * dbar);
 				const float ref_norm = sqrtf(f2), tar_norm = sqrtf(g2);
@@ -331,12 +421,41 @@ __global__ void __launch_bounds__(ICGN3D_THREADS) icgn3d1_kernel(Image3D img, fl
 	}
 }
 
-int icgn3d1_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, int rz, float conv, float stop, int sm_count,
-	cudaStream_t stream, cudaError_t* err) {
-	long long grid = (long long)sm_count * 4;
+// Returns 0, -1 when even a one-layer slab does not fit in shared memory, -2 on a CUDA error.
+int icgn3d1_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, int rz, float conv, float stop, int sm_count, size_t smem_optin,
+	int* d_counter, cudaStream_t stream, cudaError_t* err) {
+	const int sz = 2 * rz + 1;
+	const size_t layer = (size_t)icgn3d_tile_x(rx) * icgn3d_tile_y(ry) * sizeof(float);
+	const size_t fixed = 128 + sizeof(Icgn3dShared) + 1024; // barrier pad + static smem + per-CTA reservation
+	const int halo = 3 + 2 * ICGN3D_TILE_MARGIN;
+	// prefer two CTAs per SM (one loads while the other computes) when that leaves slabs of >= 6 layers
+	int ctas = 2;
+	long long k = (long long)(((228 * 1024) / 2 - fixed) / layer) - halo;
+	if (k < 6 && k < sz) {
+		ctas = 1;
+		size_t budget = smem_optin < (size_t)(227 * 1024) ? smem_optin : (size_t)(227 * 1024);
+		k = (long long)((budget - 128 - sizeof(Icgn3dShared)) / layer) - halo;
+	}
+	if (k < 1) return -1;
+	if (k > sz) k = sz;
+	const int nslab = (int)((sz + k - 1) / k);
+	const int slab_k = (sz + nslab - 1) / nslab; // even out the slabs
+	const size_t smem = 128 + layer * icgn3d_tile_z(slab_k);
+	CUtensorMap tm;
+	memset(&tm, 0, sizeof(tm));
+	const int dims[3] = { img.dx, img.dy, img.dz };
+	const int box[3] = { icgn3d_tile_x(rx), icgn3d_tile_y(ry), icgn3d_tile_z(slab_k) };
+	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm, img.coef, 3, dims, box);
+	void (*kern)(Image3D, float*, int, int, int, int, float, float, int, int*, const CUtensorMap, int);
+	kern = (rx == 16 && ry == 16 && rz == 16) ? icgn3d1_kernel<16> : icgn3d1_kernel<0>;
+	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (*err != cudaSuccess) return -2;
+	*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
+	if (*err != cudaSuccess) return -2;
+	long long grid = (long long)sm_count * ctas;
 	if (grid > (long long)n) grid = (long long)n;
 	if (grid < 1) grid = 1;
-	icgn3d1_kernel<<<(int)grid, ICGN3D_THREADS, 0, stream>>>(img, d_pois, (int)n, rx, ry, rz, conv, stop);
+	kern<<<(int)grid, ICGN3D_THREADS, smem, stream>>>(img, d_pois, (int)n, rx, ry, rz, conv, stop, slab_k, d_counter, tm, use_tma);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;
 }
