@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img,
 	const int dx = img.dx, dy = img.dy, dz = img.dz;
 	const int TX = icgn3d_tile_x(rx), TY = icgn3d_tile_y(ry), TZ = icgn3d_tile_z(slab_k);
 	const int TXY = TX * TY;
-	const float inv_n = 1.0f / (float)N, inv_slice = 1.0f / (float)slice, inv_sx = 1.0f / (float)sx;
+	const float inv_n = 1.0f / (float)N, inv_slice = 1.0f / (float)slice, inv_sx = 1.0f / (float)sx, inv_sy = 1.0f / (float)sy;
+	const int ncol = sx < 32 ? sx : 32, rem = sx - ncol;
+	const float inv_rem = rem > 0 ? 1.0f / (float)rem : 1.f;
 	const float* __restrict__ coef = img.coef;
 	uint32_t bar_phase = 0;
 	if (tid == 0 && use_tma) mbar_init(bar, 1);
@@ -293,10 +295,8 @@ __global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img,
 					__syncthreads();
 				}
 				const float* tbase = T - ((tz0 + 1) * TXY + (ty0 + 1) * TX + (tx0 + 1));
-				const int ns = nz * slice;
-				for (int i = tid; i < ns; i += ICGN3D_THREADS) {
-					const int il = fdiv3(i, inv_slice), rem = i - il * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
-					const int ii = zs + il;
+				// One sample: warp, 64-tap B-spline evaluation, single-pass sums.
+				auto sample = [&](int ii, int j, int k) {
 					const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
 					// Deformation3D1::warp, src/oc_deformation.cpp:518-530; centre + warped (:1376)
 					const float X = px + fmaf(A[0], xl, fmaf(A[1], yl, fmaf(A[2], zl, A[3])));
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img,
 						const bool ok = (X >= 1.f) && (Y >= 1.f) && (Z >= 1.f) && (X < xmax) && (Y < ymax) && (Z < zmax);
 						if (!ok) {
 							invalid = 1;
-							continue;
+							return;
 						}
 					}
 					const float xf = floorf(X), yf = floorf(Y), zf = floorf(Z);
@@ -330,6 +330,19 @@ __global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img,
 					acc[3] += gxd; acc[4] = fmaf(gxd, xl, acc[4]); acc[5] = fmaf(gxd, yl, acc[5]); acc[6] = fmaf(gxd, zl, acc[6]);
 					acc[7] += gyd; acc[8] = fmaf(gyd, xl, acc[8]); acc[9] = fmaf(gyd, yl, acc[9]); acc[10] = fmaf(gyd, zl, acc[10]);
 					acc[11] += gzd; acc[12] = fmaf(gzd, xl, acc[12]); acc[13] = fmaf(gzd, yl, acc[13]); acc[14] = fmaf(gzd, zl, acc[14]);
+				};
+				// Lanes run along x within ONE row (y, z) per warp: consecutive tile addresses, no bank
+				// conflicts (a linear index over 33-wide rows straddles two rows and conflicts 2-way);
+				// columns >= 32 form a short tail with lanes over rows.
+				const int nrows = nz * sy;
+				for (int row = warp; row < nrows; row += ICGN3D_WARPS) {
+					const int il = fdiv3(row, inv_sy), j = row - il * sy;
+					if (lane < ncol) sample(zs + il, j, lane);
+				}
+				for (int i = tid; i < nrows * rem; i += ICGN3D_THREADS) {
+					const int row = fdiv3(i, inv_rem), k = 32 + (i - row * rem);
+					const int il = fdiv3(row, inv_sy), j = row - il * sy;
+					sample(zs + il, j, k);
 				}
 			}
 			if (tmin < -1e-3f) invalid = 1; // the reference rejects interpolated values < 0 (src/oc_icgn.cpp:1378-1381)
