@@ -27,8 +27,8 @@ constexpr int ICGN3D_THREADS = 256;
 constexpr int ICGN3D_WARPS = ICGN3D_THREADS / 32;
 
 // ---- ICGN3D1::prepareRef: Gradient3D4::getGradientX/Y/Z, src/oc_gradient.cpp:143-231 ----------
-__global__ void gradient3d_kernel(const float* __restrict__ f, float* __restrict__ gx, float* __restrict__ gy, float* __restrict__ gz,
-	int dx, int dy, int dz) {
+// Output is packed {ref, gx, gy, gz} per voxel so that IC-GN fetches a sample's constants with one 16-byte load.
+__global__ void gradient3d_kernel(const float* __restrict__ f, float4* __restrict__ rg, int dx, int dy, int dz) {
 	const size_t total = (size_t)dx * dy * dz;
 	const size_t sy = (size_t)dx, sz = (size_t)dx * dy;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -37,9 +37,7 @@ __global__ void gradient3d_kernel(const float* __restrict__ f, float* __restrict
 		if (k >= 2 && k < dx - 2) vx = grad4(f[i - 2], f[i - 1], f[i + 1], f[i + 2]);
 		if (j >= 2 && j < dy - 2) vy = grad4(f[i - 2 * sy], f[i - sy], f[i + sy], f[i + 2 * sy]);
 		if (ii >= 2 && ii < dz - 2) vz = grad4(f[i - 2 * sz], f[i - sz], f[i + sz], f[i + 2 * sz]);
-		gx[i] = vx;
-		gy[i] = vy;
-		gz[i] = vz;
+		rg[i] = make_float4(f[i], vx, vy, vz);
 	}
 }
 
@@ -71,8 +69,8 @@ __global__ void prefilter3d_kernel(const float* __restrict__ in, float* __restri
 	}
 }
 
-void gradient3d_launch(const float* ref, float* gx, float* gy, float* gz, int dx, int dy, int dz, int sm_count, cudaStream_t s) {
-	gradient3d_kernel<<<sm_count * 8, 256, 0, s>>>(ref, gx, gy, gz, dx, dy, dz);
+void gradient3d_launch(const float* ref, float4* rg, int dx, int dy, int dz, int sm_count, cudaStream_t s) {
+	gradient3d_kernel<<<sm_count * 8, 256, 0, s>>>(ref, rg, dx, dy, dz);
 }
 void prefilter3d_launch(const float* in, float* out, int dx, int dy, int dz, int axis, int sm_count, cudaStream_t s) {
 	prefilter3d_kernel<<<sm_count * 8, 256, 0, s>>>(in, out, dx, dy, dz, axis);
@@ -195,8 +193,9 @@ __global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img,
 			for (int i = tid; i < N; i += ICGN3D_THREADS) {
 				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
 				const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
-				const float R = __ldg(img.ref + o) - c0;
-				const float gx = __ldg(img.gx + o), gy = __ldg(img.gy + o), gz = __ldg(img.gz + o);
+				const float4 c4 = __ldg(img.rg + o);
+				const float R = c4.x - c0;
+				const float gx = c4.y, gy = c4.z, gz = c4.w;
 				const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
 				float sd[NP3];
 				sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl; sd[3] = gx * zl;
@@ -297,6 +296,7 @@ __global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img,
 				const float* tbase = T - ((tz0 + 1) * TXY + (ty0 + 1) * TX + (tx0 + 1));
 				// One sample: warp, 64-tap B-spline evaluation, single-pass sums.
 				auto sample = [&](int ii, int j, int k) {
+					const float4 c4 = __ldg(img.rg + (goff + ((size_t)ii * dy + j) * dx + k)); // issued first: its latency hides under the taps
 					const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
 					// Deformation3D1::warp, src/oc_deformation.cpp:518-530; centre + warped (:1376)
 					const float X = px + fmaf(A[0], xl, fmaf(A[1], yl, fmaf(A[2], zl, A[3])));
@@ -320,13 +320,12 @@ __global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img,
 					if (fast) t = tricubic_taps<false>(tbase + ((int)zf * TXY + (int)yf * TX + (int)xf), TX, TXY, bx, by, bz);
 					else t = tricubic_taps<true>(coef + ((size_t)((int)zf - 1) * dy + ((int)yf - 1)) * dx + ((int)xf - 1), dx, dx * dy, bx, by, bz);
 					tmin = fminf(tmin, t);
-					const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
-					const float R = __ldg(img.ref + o);
+					const float R = c4.x;
 					const float d = t - R;
 					acc[0] += d;
 					acc[1] = fmaf(d, d, acc[1]);
 					acc[2] = fmaf(R, d, acc[2]);
-					const float gxd = __ldg(img.gx + o) * d, gyd = __ldg(img.gy + o) * d, gzd = __ldg(img.gz + o) * d;
+					const float gxd = c4.y * d, gyd = c4.z * d, gzd = c4.w * d;
 					acc[3] += gxd; acc[4] = fmaf(gxd, xl, acc[4]); acc[5] = fmaf(gxd, yl, acc[5]); acc[6] = fmaf(gxd, zl, acc[6]);
 					acc[7] += gyd; acc[8] = fmaf(gyd, xl, acc[8]); acc[9] = fmaf(gyd, yl, acc[9]); acc[10] = fmaf(gyd, zl, acc[10]);
 					acc[11] += gzd; acc[12] = fmaf(gzd, xl, acc[12]); acc[13] = fmaf(gzd, yl, acc[13]); acc[14] = fmaf(gzd, zl, acc[14]);

@@ -54,10 +54,11 @@ struct ocb_ctx {
 	float* own_ref3 = nullptr;
 	float* own_tar3 = nullptr;
 	size_t own3_elems = 0;
-	float* tab3[4] = { nullptr, nullptr, nullptr, nullptr }; // gx gy gz coef
+	float4* rg3 = nullptr;   // packed {ref, gx, gy, gz}
+	float* coef3 = nullptr;  // tricubic B-spline coefficients
 	float* tmp3 = nullptr;
 	size_t tab3_elems = 0;
-	ocb::Image3D img3{ nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0 };
+	ocb::Image3D img3{ nullptr, nullptr, nullptr, nullptr, 0, 0, 0 };
 	bool prepared3 = false;
 
 	// FFT
@@ -187,7 +188,8 @@ void ocb_destroy(ocb_ctx* ctx) {
 	cudaFree(ctx->own_tar2);
 	cudaFree(ctx->own_ref3);
 	cudaFree(ctx->own_tar3);
-	for (int i = 0; i < 4; i++) cudaFree(ctx->tab3[i]);
+	cudaFree(ctx->rg3);
+	cudaFree(ctx->coef3);
 	cudaFree(ctx->tmp3);
 	for (auto& kv : ctx->twiddles) cudaFree(kv.second);
 	cudaFree(ctx->fft_scratch);
@@ -264,7 +266,7 @@ int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int widt
 int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int dim_x, int dim_y, int dim_z) {
 	if (!ctx || !d_ref || !d_tar || dim_x < 15 || dim_y < 15 || dim_z < 15) // TricubicBspline needs >= 15 (src/oc_cubic_bspline.cpp:201)
 		return set_error(ctx, OCB_ERR_ARG, "set_images_3d: bad arguments (each dimension must be >= 15)");
-	ctx->img3 = ocb::Image3D{ d_ref, d_tar, nullptr, nullptr, nullptr, nullptr, dim_x, dim_y, dim_z };
+	ctx->img3 = ocb::Image3D{ d_ref, d_tar, nullptr, nullptr, dim_x, dim_y, dim_z };
 	ctx->prepared3 = false;
 	return OCB_OK;
 }
@@ -420,25 +422,26 @@ int ocb_icgn3d_prepare(ocb_ctx* ctx) {
 	const int dx = ctx->img3.dx, dy = ctx->img3.dy, dz = ctx->img3.dz;
 	const size_t elems = (size_t)dx * dy * dz;
 	if (elems > ctx->tab3_elems) {
-		for (int i = 0; i < 4; i++) { cudaFree(ctx->tab3[i]); ctx->tab3[i] = nullptr; }
+		cudaFree(ctx->rg3);
+		cudaFree(ctx->coef3);
 		cudaFree(ctx->tmp3);
-		ctx->tmp3 = nullptr;
+		ctx->rg3 = nullptr;
+		ctx->coef3 = ctx->tmp3 = nullptr;
 		ctx->tab3_elems = 0;
-		for (int i = 0; i < 4; i++) OCB_CUDA(ctx, cudaMalloc(&ctx->tab3[i], elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->rg3, elems * sizeof(float4)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->coef3, elems * sizeof(float)));
 		OCB_CUDA(ctx, cudaMalloc(&ctx->tmp3, elems * sizeof(float)));
 		ctx->tab3_elems = elems;
 	}
-	ocb::gradient3d_launch(ctx->img3.ref, ctx->tab3[0], ctx->tab3[1], ctx->tab3[2], dx, dy, dz, ctx->sm_count, ctx->stream);
+	ocb::gradient3d_launch(ctx->img3.ref, ctx->rg3, dx, dy, dz, ctx->sm_count, ctx->stream);
 	// TricubicBspline::prepare: x -> coefficient, y -> conv_buffer, z -> coefficient
-	ocb::prefilter3d_launch(ctx->img3.tar, ctx->tab3[3], dx, dy, dz, 0, ctx->sm_count, ctx->stream);
-	ocb::prefilter3d_launch(ctx->tab3[3], ctx->tmp3, dx, dy, dz, 1, ctx->sm_count, ctx->stream);
-	ocb::prefilter3d_launch(ctx->tmp3, ctx->tab3[3], dx, dy, dz, 2, ctx->sm_count, ctx->stream);
+	ocb::prefilter3d_launch(ctx->img3.tar, ctx->coef3, dx, dy, dz, 0, ctx->sm_count, ctx->stream);
+	ocb::prefilter3d_launch(ctx->coef3, ctx->tmp3, dx, dy, dz, 1, ctx->sm_count, ctx->stream);
+	ocb::prefilter3d_launch(ctx->tmp3, ctx->coef3, dx, dy, dz, 2, ctx->sm_count, ctx->stream);
 	ctx->launches += 4;
 	OCB_CUDA(ctx, cudaGetLastError());
-	ctx->img3.gx = ctx->tab3[0];
-	ctx->img3.gy = ctx->tab3[1];
-	ctx->img3.gz = ctx->tab3[2];
-	ctx->img3.coef = ctx->tab3[3];
+	ctx->img3.rg = ctx->rg3;
+	ctx->img3.coef = ctx->coef3;
 	ctx->prepared3 = true;
 	return OCB_OK;
 }
@@ -475,10 +478,13 @@ int ocb_get_tables_3d(ocb_ctx* ctx, float* gx, float* gy, float* gz, float* coef
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
 	if (!ctx->prepared3) return set_error(ctx, OCB_ERR_STATE, "get_tables_3d: prepare() has not been called");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
-	const size_t bytes = (size_t)ctx->img3.dx * ctx->img3.dy * ctx->img3.dz * sizeof(float);
-	float* dst[4] = { gx, gy, gz, coefficient };
-	for (int i = 0; i < 4; i++)
-		if (dst[i]) OCB_CUDA(ctx, cudaMemcpyAsync(dst[i], ctx->tab3[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	const size_t elems = (size_t)ctx->img3.dx * ctx->img3.dy * ctx->img3.dz;
+	float* dst[3] = { gx, gy, gz };
+	for (int i = 0; i < 3; i++) // de-interleave component i+1 of the packed {ref, gx, gy, gz} volume (inspection path, not hot)
+		if (dst[i])
+			OCB_CUDA(ctx, cudaMemcpy2DAsync(dst[i], sizeof(float), (const float*)ctx->rg3 + (i + 1), sizeof(float4), sizeof(float), elems,
+				cudaMemcpyDeviceToHost, ctx->stream));
+	if (coefficient) OCB_CUDA(ctx, cudaMemcpyAsync(coefficient, ctx->coef3, elems * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return OCB_OK;
 }

@@ -26,9 +26,7 @@ struct Image2D {
 struct Image3D {
 	const float* ref;
 	const float* tar;
-	const float* gx; // Gradient3D4 of ref (built by prepare)
-	const float* gy;
-	const float* gz;
+	const float4* rg;  // per voxel {ref, gx, gy, gz}: Gradient3D4 of ref packed with ref (built by prepare)
 	const float* coef; // tricubic B-spline coefficients of tar (built by prepare)
 	int dx, dy, dz;
 };

@@ -47,7 +47,7 @@ int fftcc3d_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, 
 	const FftAxis& az, const float2* tw_x, const float2* tw_y, const float2* tw_z, float2* scratch, int grid, cudaStream_t stream,
 	cudaError_t* err);
 // icgn3d.cu
-void gradient3d_launch(const float* ref, float* gx, float* gy, float* gz, int dx, int dy, int dz, int sm_count, cudaStream_t s);
+void gradient3d_launch(const float* ref, float4* rg, int dx, int dy, int dz, int sm_count, cudaStream_t s);
 void prefilter3d_launch(const float* in, float* out, int dx, int dy, int dz, int axis, int sm_count, cudaStream_t s);
 int icgn3d1_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, int rz, float conv, float stop, int sm_count, size_t smem_optin,
 	int* d_counter, cudaStream_t stream, cudaError_t* err);

@@ -217,3 +217,90 @@ def test_large_deformation_gradient_falls_back_to_global_reads(engine):
     Oracle2D(ref, tar).icgn2d1(q_cpu, 16, 16, 0.001, 10)
     assert (q_cpu[:, 16] > 0.9).all()
     util.compare_2d(q_gpu, q_cpu, "stretch", max_iter_mismatch_frac=0.05)
+
+
+@pytest.mark.parametrize("width", [330, 331, 333])
+def test_icgn2d1_image_width_not_multiple_of_four(engine, width):
+    """TMA tile loads need a 16-byte aligned row pitch; other widths take the staged-load path.
+    Both must give the same answer as the oracle (the reference's example pair is 280 px wide)."""
+    ref, tar = synth.speckle_pair_2d(width, 300)
+    xy = synth.grid_2d(40, 40, 10, 8, 25, 27)
+    q = ob.make_poi2d(xy)
+    f = ob.FFTCC2D(16, 16, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    o = Oracle2D(ref, tar)
+    qo = ob.make_poi2d(xy)
+    o.fftcc2d(qo, 16, 16)
+    assert np.array_equal(q[:, [2, 8]], qo[:, [2, 8]])
+    icgn = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    o.icgn2d1(q_cpu, 16, 16, 0.001, 10)
+    stats = util.compare_2d(q_gpu, q_cpu, "width %d" % width, max_iter_mismatch_frac=0.03)
+    assert stats["n_compared"] >= 0.9 * len(q)
+
+
+@pytest.mark.parametrize("rx,ry", [(16, 10), (9, 21), (33, 33), (4, 4)])
+def test_icgn2d1_other_radii(engine, rx, ry):
+    """Non-square subsets, a subset wider than 64 px (tail columns, two lane passes) and a tiny one."""
+    ref, tar = synth.speckle_pair_2d(400, 360)
+    xy = synth.grid_2d(100, 90, 6, 5, 33, 37)
+    q = ob.make_poi2d(xy)
+    u, v = synth.displacement_2d(xy[:, 0], xy[:, 1], 400, 360)
+    q[:, 2], q[:, 8] = np.round(u), np.round(v)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN2D1(rx, ry, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    Oracle2D(ref, tar).icgn2d1(q_cpu, rx, ry, 0.001, 10)
+    stats = util.compare_2d(q_gpu, q_cpu, "r=(%d,%d)" % (rx, ry), max_iter_mismatch_frac=0.1)
+    assert stats["n_compared"] >= 0.8 * len(q)
+
+
+def test_borrowed_device_images_and_device_queue(engine):
+    """The *_dev entry points: images and the POI queue stay on the device (torch is only the allocator)."""
+    torch = pytest.importorskip("torch")
+    ref, tar = synth.speckle_pair_2d(320, 256)
+    xy = synth.grid_2d(40, 40, 12, 9, 20, 19)
+    d_ref, d_tar = torch.from_numpy(ref).cuda(), torch.from_numpy(tar).cuda()
+    eng = ob.Engine(0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.set_images_2d_dev(d_ref.data_ptr(), d_tar.data_ptr(), 320, 256)
+    d_q = torch.from_numpy(ob.make_poi2d(xy)).cuda()
+    eng.fftcc2d_dev(d_q.data_ptr(), len(xy), 16, 16)
+    eng.icgn2d_prepare()
+    eng.icgn2d1_dev(d_q.data_ptr(), len(xy), 16, 16, 0.001, 10)
+    torch.cuda.synchronize()
+    q_gpu = d_q.cpu().numpy()
+    q_cpu = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q_cpu, 16, 16)
+    o.icgn2d1(q_cpu, 16, 16, 0.001, 10)
+    util.compare_2d(q_gpu, q_cpu, "device-resident", max_iter_mismatch_frac=0.03)
+    assert eng.launch_count() == 2
+    eng.close()
+
+
+def test_negative_interpolated_sample_is_rejected(engine):
+    """The reference rejects a POI when ANY interpolated sample is < 0 (src/oc_icgn.cpp:251-255); bicubic
+    overshoot next to black pixels produces such samples.  A black-background pattern must give -3 on
+    both sides for the same POIs."""
+    ref, tar = synth.speckle_pair_2d(256, 256)
+    ref = np.clip(ref - 24.0, 0, 255).astype(np.float32) * 1.1
+    tar = np.clip(tar - 24.0, 0, 255).astype(np.float32) * 1.1
+    xy = synth.grid_2d(50, 50, 6, 6, 30, 30)
+    q = ob.make_poi2d(xy)
+    q[:, 2], q[:, 8] = 2.0, -2.0
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    Oracle2D(ref, tar).icgn2d1(q_cpu, 16, 16, 0.001, 10)
+    assert (q_cpu[:, 16] == -3).sum() > 0
+    # borderline samples (|t| < 1e-3) may be classified differently; require agreement on >= 90 %
+    assert ((q_gpu[:, 16] == -3) == (q_cpu[:, 16] == -3)).mean() >= 0.9

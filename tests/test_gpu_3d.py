@@ -133,3 +133,36 @@ def test_dvc_golden_tables(engine):
     assert same.mean() > 0.85
     assert np.abs(q10[same][:, [3, 7, 11]] - gpu[sel][same][:, 3:6]).max() < 1e-4
     assert np.abs(q10[same, 18] - gpu[sel][same, 9]).max() < 1e-5
+
+
+def test_icgn3d1_volume_width_not_multiple_of_four(engine):
+    """dim_x % 4 != 0 disables the TMA slab loads; the staged path must agree with the oracle too."""
+    ref, tar = synth.speckle_pair_3d(70, 64, 66)
+    xyz = synth.grid_3d(24, 22, 24, 3, 3, 2, 8, 9, 9)
+    q = ob.make_poi3d(xyz)
+    o = Oracle3D(ref, tar)
+    o.fftcc3d(q, 8, 8, 8)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN3D1(8, 8, 8, 0.001, 20, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    o.icgn3d1(q_cpu, 8, 8, 8, 0.001, 20)
+    util.compare_3d(q_gpu, q_cpu, "dx=70", max_iter_mismatch_frac=0.1)
+
+
+def test_icgn3d1_nonuniform_radii_and_large_gradient(engine, vol):
+    """Non-cubic subvolume; a 6 % stretch guess drives samples out of the slab tile (global fallback)."""
+    ref, tar, _ = vol
+    xyz = np.array([[36, 32, 40], [33, 30, 37], [38, 34, 42]], np.float32)
+    q = ob.make_poi3d(xyz)
+    u, v, w = synth.displacement_3d(xyz[:, 0], xyz[:, 1], xyz[:, 2], 72, 64, 80)
+    q[:, 3], q[:, 7], q[:, 11] = u, v, w
+    q[2, 4] = 0.06  # ux guess far from the truth: first iterations sample outside the tile
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN3D1(10, 7, 9, 0.001, 20, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu)
+    Oracle3D(ref, tar).icgn3d1(q_cpu, 10, 7, 9, 0.001, 20)
+    util.compare_3d(q_gpu, q_cpu, "radii (10,7,9)", max_iter_mismatch_frac=0.34)
