@@ -102,27 +102,34 @@ def run_reference(args):
     n_sample = min(cfg["n_poi"], args.cpu_sample if args.cpu_sample > 0 else (cfg["n_poi"] if cfg["kind"] == "2d" else 400))
     sel = np.linspace(0, cfg["n_poi"] - 1, n_sample).astype(np.int64)
     times = []
+    scale = cfg["n_poi"] / float(n_sample)
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         if cfg["kind"] == "2d":
             q = make_poi2d(pts[sel])
             o = Oracle2D(ref, tar, threads)
             o.fftcc2d(q, r, r)
+            t1 = time.perf_counter()
             o.prepare()
+            t2 = time.perf_counter()
             (o.icgn2d1 if cfg["order"] == 1 else o.icgn2d2)(q, r, r, cfg["conv"], cfg["stop"])
         else:
             q = make_poi3d(pts[sel])
             o = Oracle3D(ref, tar, threads)
             o.fftcc3d(q, r, r, r)
+            t1 = time.perf_counter()
             o.prepare()
+            t2 = time.perf_counter()
             o.icgn3d1(q, r, r, r, cfg["conv"], cfg["stop"])
-        dt = time.perf_counter() - t0
+        t3 = time.perf_counter()
+        # whole-workload time: prepare() once + per-POI stages scaled from the sample to all POIs
+        dt = (t2 - t1) + scale * ((t1 - t0) + (t3 - t2))
         if step >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    value = n_sample / (ms * 1e-3)
-    sample = "%d of %d POIs of the workload per step (evenly spaced), prepare() included, best-of-none mean of %d steps" % (
-        n_sample, cfg["n_poi"], len(times))
+    value = cfg["n_poi"] / (ms * 1e-3)
+    sample = "%d of %d POIs of the workload per step (evenly spaced); prepare() once + per-POI stages x %.1f; mean of %d steps" % (
+        n_sample, cfg["n_poi"], scale, len(times))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -420,8 +427,12 @@ def run_ours(args):
             t2 = time.perf_counter()
             o.icgn3d1(qc, r, r, r, cfg["conv"], cfg["stop"])
         t3 = time.perf_counter()
-        cpu = {"value": n_sample / (t3 - t0), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d of %d POIs, one pass; fftcc %.3fs + prepare %.3fs + icgn %.3fs" % (n_sample, n, t1 - t0, t2 - t1, t3 - t2),
+        # prepare() is paid once per image pair; the per-POI stages scale with the POI count, so the
+        # whole-workload time is prepare + (fftcc + icgn) * n / n_sample
+        scale = n / float(n_sample)
+        cpu = {"value": n / ((t2 - t1) + scale * ((t1 - t0) + (t3 - t2))), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d of %d POIs, one pass; fftcc %.3fs + prepare %.3fs + icgn %.3fs; value = whole workload extrapolated "
+                         "(prepare once, per-POI stages x %.1f)" % (n_sample, n, t1 - t0, t2 - t1, t3 - t2, scale),
                "value_compute_only": n_sample / ((t1 - t0) + (t3 - t2))}
         # parity of the benchmarked run against the oracle on the sample (reported, not asserted)
         same = (res[sel, ic] == qc[:, ic]) & (res[sel, zc] >= 0) & (qc[:, zc] >= 0)

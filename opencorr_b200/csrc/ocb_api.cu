@@ -338,6 +338,24 @@ int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int r
 	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "fftcc3d: too many POIs in one call");
 	if ((size_t)8 * rx * ry * rz > 0x7fffffffull) return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc3d: window too large");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	if (rx == 16 && ry == 16 && rz == 16 && !getenv("OCB_FFTCC3D_GENERIC")) { // specialised register-FFT kernel for the 32^3 window
+		int grid32 = ocb::fftcc3d_w32_grid(ctx->sm_count);
+		if ((size_t)grid32 > n) grid32 = (int)n;
+		const size_t need32 = (size_t)grid32 * 32768;
+		if (need32 > ctx->fft_scratch_elems) {
+			OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			cudaFree(ctx->fft_scratch);
+			ctx->fft_scratch = nullptr;
+			ctx->fft_scratch_elems = 0;
+			OCB_CUDA(ctx, cudaMalloc(&ctx->fft_scratch, need32 * sizeof(float2)));
+			ctx->fft_scratch_elems = need32;
+		}
+		cudaError_t err32;
+		if (ocb::fftcc3d_w32_launch(ctx->img3, (float*)d_poi3d, n, ctx->fft_scratch, grid32, ctx->stream, &err32))
+			return set_error(ctx, OCB_ERR_CUDA, "fftcc3d launch failed: %s", cudaGetErrorString(err32));
+		ctx->launches++;
+		return OCB_OK;
+	}
 	ocb::FftAxis ax, ay, az;
 	if (!ocb::fft_plan_axis(2 * rx, &ax) || !ocb::fft_plan_axis(2 * ry, &ay) || !ocb::fft_plan_axis(2 * rz, &az))
 		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc3d: window size has a prime factor > 31");

@@ -166,3 +166,31 @@ def test_icgn3d1_nonuniform_radii_and_large_gradient(engine, vol):
     icgn.compute(q_gpu)
     Oracle3D(ref, tar).icgn3d1(q_cpu, 10, 7, 9, 0.001, 20)
     util.compare_3d(q_gpu, q_cpu, "radii (10,7,9)", max_iter_mismatch_frac=0.34)
+
+
+def test_fftcc3d_w32_specialised_kernel(engine):
+    """radius 16 takes the register-FFT 32^3 kernel; it must agree with the oracle and with the generic
+    kernel (selected with OCB_FFTCC3D_GENERIC)."""
+    import os
+    ref, tar = synth.speckle_pair_3d(80, 76, 72)
+    xyz = synth.grid_3d(30, 28, 27, 4, 3, 3, 6, 8, 7)
+    q_gpu = ob.make_poi3d(xyz)
+    q_gpu[::4, 3] = 1.0   # incoming guesses shift the target window
+    q_gpu[::5, 11] = -1.0
+    q_cpu, q_gen = q_gpu.copy(), q_gpu.copy()
+    f = ob.FFTCC3D(16, 16, 16, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q_gpu)
+    os.environ["OCB_FFTCC3D_GENERIC"] = "1"
+    try:
+        f.compute(q_gen)
+    finally:
+        del os.environ["OCB_FFTCC3D_GENERIC"]
+    o = Oracle3D(ref, tar)
+    q_exact = q_cpu.copy()
+    o.fftcc3d(q_cpu, 16, 16, 16)
+    o.fftcc3d(q_exact, 16, 16, 16, exact=True)
+    for q in (q_gpu, q_gen):
+        assert np.array_equal(q[:, [3, 7, 11, 15, 16, 17]], q_cpu[:, [3, 7, 11, 15, 16, 17]])
+        assert np.abs(q[:, 18] - q_exact[:, 18]).max() < 1e-5
+    assert (q_cpu[:, 18] > 0.3).all()
