@@ -492,12 +492,15 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				float xs0, xs1, xs2, ys0, ys1, ys2;
 				{
 					const float xl = (float)(lane_c - rx);
+					// the warped offset is formed first and the POI centre added last, with ONE rounding at
+					// the large magnitude, like the reference's `center + warped` (src/oc_icgn.cpp:238-239):
+					// at x ~ 4096 a float ulp is 4.9e-4 px, so the association order is visible in the result
 					if constexpr (NP == 6) {
-						xs0 = px + fmaf(A[0], xl, A[2]); xs1 = A[1]; xs2 = 0.f;
-						ys0 = py + fmaf(A[3], xl, A[5]); ys1 = A[4]; ys2 = 0.f;
+						xs0 = fmaf(A[0], xl, A[2]); xs1 = A[1]; xs2 = 0.f;
+						ys0 = fmaf(A[3], xl, A[5]); ys1 = A[4]; ys2 = 0.f;
 					} else {
-						xs0 = px + fmaf(A[0] * xl + A[3], xl, A[5]); xs1 = fmaf(A[1], xl, A[4]); xs2 = A[2];
-						ys0 = py + fmaf(A[6] * xl + A[9], xl, A[11]); ys1 = fmaf(A[7], xl, A[10]); ys2 = A[8];
+						xs0 = fmaf(A[0] * xl + A[3], xl, A[5]); xs1 = fmaf(A[1], xl, A[4]); xs2 = A[2];
+						ys0 = fmaf(A[6] * xl + A[9], xl, A[11]); ys1 = fmaf(A[7], xl, A[10]); ys2 = A[8];
 					}
 				}
 				const float* tbase = T - (ty0 + 1) * TW - (tx0 + 1);
@@ -505,11 +508,11 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				for (int r = 0; r < sh; r++) {
 					float X, Y;
 					if constexpr (NP == 6) {
-						X = fmaf(xs1, yl, xs0);
-						Y = fmaf(ys1, yl, ys0);
+						X = px + fmaf(xs1, yl, xs0);
+						Y = py + fmaf(ys1, yl, ys0);
 					} else {
-						X = fmaf(fmaf(xs2, yl, xs1), yl, xs0);
-						Y = fmaf(fmaf(ys2, yl, ys1), yl, ys0);
+						X = px + fmaf(fmaf(xs2, yl, xs1), yl, xs0);
+						Y = py + fmaf(fmaf(ys2, yl, ys1), yl, ys0);
 					}
 					const float xf = floorf(X), yf = floorf(Y);
 					float wx[4], wy[4];
