@@ -172,6 +172,7 @@ namespace opencorr
 	};
 	static_assert(sizeof(POI2D) == OCB_POI2D_FLOATS * sizeof(float), "POI2D must be the 100-byte record of the C ABI");
 	static_assert(sizeof(POI3D) == OCB_POI3D_FLOATS * sizeof(float), "POI3D must be the 124-byte record of the C ABI");
+	static_assert(sizeof(Point2D) == 2 * sizeof(float), "Point2D must be two packed floats (centre-offset queues cross the C ABI verbatim)");
 
 	// ------------------------------------------------------------------ src/oc_image.h
 	// Row-major float matrix standing in for the reference's Eigen::MatrixXf member `eg_mat`.
@@ -512,18 +513,26 @@ namespace opencorr
 				e.check(ocb_icgn2d_prepare(e.context()));
 				e.prepared = true;
 			}
-			void compute(POI2D* poi) { run(poi, 1); }
-			void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+			void compute(POI2D* poi) { run(poi, 1, nullptr); }
+			void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size(), nullptr); }
+			// off-centre subsets, src/oc_icgn.cpp:353-557 / :910-1136 (Point2D is two packed floats)
+			void compute(POI2D* poi, Point2D& center_offset) { run(poi, 1, &center_offset.x); }
+			void compute(std::vector<POI2D>& poi_queue, std::vector<Point2D>& center_offset_queue)
+			{
+				if (center_offset_queue.size() < poi_queue.size()) throw std::string("opencorr_b200: center_offset_queue is shorter than poi_queue");
+				run(poi_queue.data(), poi_queue.size(), poi_queue.empty() ? nullptr : &center_offset_queue[0].x);
+			}
 
 		private:
-			void run(POI2D* p, size_t n)
+			void run(POI2D* p, size_t n, const float* offsets)
 			{
-				if (self_adaptive) throw std::string("opencorr_b200: self-adaptive subsets are not implemented yet (DESIGN.md, next rows)");
 				Engine& e = Engine::get();
 				std::lock_guard<std::mutex> g(e.lock);
 				e.useImages(ref_img, tar_img);
 				if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
-				if (ORDER == 1) e.check(ocb_icgn2d1(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
+				if (self_adaptive || offsets)
+					e.check(ocb_icgn2d_ex(e.context(), ORDER, p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition, offsets, self_adaptive ? 1 : 0));
+				else if (ORDER == 1) e.check(ocb_icgn2d1(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
 				else e.check(ocb_icgn2d2(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
 			}
 		};

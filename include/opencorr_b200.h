@@ -103,6 +103,18 @@ int ocb_icgn2d1_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float
 int ocb_icgn2d2_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop);
 int ocb_icgn3d1_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz, float conv, float stop);
 
+/* ---- IC-GN, the remaining overloads of the reference's class API ------
+ * order = 1 (ICGN2D1) or 2 (ICGN2D2).
+ * center_offsets: NULL, or n (x, y) pairs -- compute(std::vector<POI2D>&, std::vector<Point2D>&
+ *   center_offset_queue), src/oc_icgn.cpp:549-557 (per POI :353-547) and :1128-1136 (:910-1126): local
+ *   coordinates are taken relative to poi + offset and the target subset is centred there.
+ * self_adaptive != 0: DIC::setSelfAdaptive(true) -- every POI uses its own subset_radius.x/.y fields
+ *   (src/oc_icgn.cpp:152-158) and rx, ry are ignored; POIs are grouped by radius on the host and each
+ *   group is one launch.  The _dev variant takes device pointers and one radius for all POIs. */
+int ocb_icgn2d_ex(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, const float* center_offsets,
+	int self_adaptive);
+int ocb_icgn2d_ex_dev(ocb_ctx* ctx, int order, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, const float* d_center_offsets);
+
 /* ---- inspection (parity tests of the prepare() products) ----------------------------------- */
 /* Copy the device tables built by ocb_icgn3d_prepare() to host buffers of dim_x*dim_y*dim_z
  * floats each; any pointer may be NULL. */

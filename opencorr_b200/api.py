@@ -141,6 +141,17 @@ class Engine:
         _check_queue(q, POI2D_FLOATS)
         self._ck(self._lib.ocb_icgn2d2(self._ctx, _vp(q), q.shape[0], rx, ry, conv, stop))
 
+    def icgn2d_ex(self, order, q, rx, ry, conv, stop, center_offsets=None, self_adaptive=False):
+        """Offset-centre and/or self-adaptive overloads (reference src/oc_icgn.cpp:353-557, :910-1136)."""
+        _check_queue(q, POI2D_FLOATS)
+        off = None
+        if center_offsets is not None:
+            off = np.ascontiguousarray(center_offsets, dtype=np.float32).reshape(-1, 2)
+            if off.shape[0] != q.shape[0]:
+                raise ValueError("center_offsets must hold one (x, y) pair per POI")
+        self._ck(self._lib.ocb_icgn2d_ex(self._ctx, int(order), _vp(q), q.shape[0], rx, ry, conv, stop,
+                                         _vp(off) if off is not None else None, int(bool(self_adaptive))))
+
     def icgn3d1(self, q, rx, ry, rz, conv, stop):
         _check_queue(q, POI3D_FLOATS)
         self._ck(self._lib.ocb_icgn3d1(self._ctx, _vp(q), q.shape[0], rx, ry, rz, conv, stop))
@@ -263,10 +274,20 @@ class _ICGN2D(_DIC):
     def prepare(self):
         self.engine.icgn2d_prepare()
 
-    def compute(self, poi_queue):
-        fn = self.engine.icgn2d1 if self._order == 1 else self.engine.icgn2d2
-        fn(poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion, self.stop_condition)
+    def compute(self, poi_queue, center_offset_queue=None):
+        """compute(queue) and compute(queue, center_offset_queue); honours set_self_adaptive(True)."""
+        if center_offset_queue is None and not self.self_adaptive:
+            fn = self.engine.icgn2d1 if self._order == 1 else self.engine.icgn2d2
+            fn(poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion, self.stop_condition)
+        else:
+            self.engine.icgn2d_ex(self._order, poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion,
+                                  self.stop_condition, center_offset_queue, self.self_adaptive)
         return poi_queue
+
+    def set_self_adaptive(self, is_self_adaptive):
+        self.self_adaptive = bool(is_self_adaptive)
+
+    setSelfAdaptive = set_self_adaptive
 
     setIteration = set_iteration
     prepareRef = prepare_ref

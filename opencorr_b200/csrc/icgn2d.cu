@@ -188,7 +188,7 @@ __device__ __forceinline__ float bicubic_sample(const float* tile, int TW, int t
 template <int NP, int RC>
 __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
 	float conv_criterion, float stop_condition, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_ref,
-	const __grid_constant__ CUtensorMap tm_tar, int use_tma) {
+	const __grid_constant__ CUtensorMap tm_tar, int use_tma, const float* __restrict__ center_offsets) {
 	extern __shared__ __align__(128) float smem[];
 	constexpr int NH = NP * (NP + 1) / 2;
 	constexpr int NPHI = NP / 2;           // 3 or 6 shape monomials per displacement component
@@ -218,7 +218,6 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 	const int w = img.w, h = img.h;
 	const float inv_n = 1.0f / (float)N;
 	const bool lane_on = lane < ncol;
-	const float xl_lane = (float)(lane - rx);
 	const int lane_c = lane_on ? lane : ncol - 1; // idle lanes (subsets narrower than 32) shadow the last column
 
 	while (true) {
@@ -240,6 +239,15 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			continue;
 		}
 		__syncwarp();
+		// compute(POI2D*, Point2D& center_offset), src/oc_icgn.cpp:353-547 / :910-1126: local coordinates are
+		// (integer - offset) and the target subset is centred at poi + offset; (0, 0) for the plain overload
+		float ox = 0.f, oy = 0.f;
+		if (center_offsets != nullptr) {
+			ox = __ldg(center_offsets + 2 * (size_t)poi);
+			oy = __ldg(center_offsets + 2 * (size_t)poi + 1);
+		}
+		const float xl_lane = (float)(lane - rx) - ox;
+		const float pcx = px + ox, pcy = py + oy;
 
 		// ---------------- stage the reference tile ----------------
 		const int x0 = (int)px - rx, y0 = (int)py - ry; // Subset2D::fill upper-left, src/oc_subset.cpp:41-42
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			for (int r = 0; r < sh; r++) {
 				const int yg = y0 + r;
 				const bool gy_ok = yg >= 2 && yg < h - 2;
-				const float yl = (float)(r - ry);
+				const float yl = (float)(r - ry) - oy;
 				if (lane_on) {
 					const float* q = T + (r + 2) * RW + lane + 2 + ex;
 					const float R = q[0] - c0;
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		for (int idx = lane; idx < ntail; idx += 32) {
 			const int r = idx / rem, c = 32 + (idx - r * rem);
 			const int xg = x0 + c, yg = y0 + r;
-			const float xl = (float)(c - rx), yl = (float)(r - ry);
+			const float xl = (float)(c - rx) - ox, yl = (float)(r - ry) - oy;
 			const float* q = T + (r + 2) * RW + c + 2 + ex;
 			const float R = q[0] - c0;
 			float gx = 0.f, gy = 0.f;
@@ -409,8 +417,8 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 
 		// ---------------- stage the target tile over the reference tile ----------------
 		__syncwarp();
-		const int tx0 = floor4((int)floorf(px + u_in) - rx - 1 - ICGN2D_TILE_MARGIN);
-		const int ty0 = (int)floorf(py + v_in) - ry - 1 - ICGN2D_TILE_MARGIN;
+		const int tx0 = floor4((int)floorf(pcx + u_in) - rx - 1 - ICGN2D_TILE_MARGIN);
+		const int ty0 = (int)floorf(pcy + v_in) - ry - 1 - ICGN2D_TILE_MARGIN;
 		if (use_tma) {
 			if (lane == 0) {
 				fence_proxy_async();
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			bool iter_fast;
 			{
 				float qx = 0.f, qy = 0.f;
-				const float fx = (float)rx, fy = (float)ry;
+				const float fx = (float)rx + fabsf(ox), fy = (float)ry + fabsf(oy);
 				float a0, a1, a2, b0, b1, b2; // X = px + a0 x + a1 y + a2 (+ quadratic), same for Y
 				if constexpr (NP == 6) {
 					a0 = A[0]; a1 = A[1]; a2 = A[2]; b0 = A[3]; b1 = A[4]; b2 = A[5];
@@ -480,18 +488,18 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					qx = fabsf(A[0]) * fx * fx + fabsf(A[1]) * fx * fy + fabsf(A[2]) * fy * fy;
 					qy = fabsf(A[6]) * fx * fx + fabsf(A[7]) * fx * fy + fabsf(A[8]) * fy * fy;
 				}
-				const float cx = px + a2, cy = py + b2;
+				const float cx = pcx + a2, cy = pcy + b2;
 				const float ex_ = fabsf(a0) * fx + fabsf(a1) * fy + qx, ey_ = fabsf(b0) * fx + fabsf(b1) * fy + qy;
 				iter_fast = (cx - ex_ >= xlo) && (cx + ex_ < xhi) && (cy - ey_ >= ylo) && (cy + ey_ < yhi); // false for NaN
 			}
 			if (iter_fast) {
 				// branch-free row loop: no per-sample validity tests (min(t) is tested after the loop)
 				float tmin = 0.f;
-				float yl = (float)(-ry);
+				float yl = (float)(-ry) - oy;
 				const float* pc = sC + 3 * lane_c;
 				float xs0, xs1, xs2, ys0, ys1, ys2;
 				{
-					const float xl = (float)(lane_c - rx);
+					const float xl = (float)(lane_c - rx) - ox;
 					// the warped offset is formed first and the POI centre added last, with ONE rounding at
 					// the large magnitude, like the reference's `center + warped` (src/oc_icgn.cpp:238-239):
 					// at x ~ 4096 a float ulp is 4.9e-4 px, so the association order is visible in the result
@@ -508,11 +516,11 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				for (int r = 0; r < sh; r++) {
 					float X, Y;
 					if constexpr (NP == 6) {
-						X = px + fmaf(xs1, yl, xs0);
-						Y = py + fmaf(ys1, yl, ys0);
+						X = pcx + fmaf(xs1, yl, xs0);
+						Y = pcy + fmaf(ys1, yl, ys0);
 					} else {
-						X = px + fmaf(fmaf(xs2, yl, xs1), yl, xs0);
-						Y = py + fmaf(fmaf(ys2, yl, ys1), yl, ys0);
+						X = pcx + fmaf(fmaf(xs2, yl, xs1), yl, xs0);
+						Y = pcy + fmaf(fmaf(ys2, yl, ys1), yl, ys0);
 					}
 					const float xf = floorf(X), yf = floorf(Y);
 					float wx[4], wy[4];
@@ -547,14 +555,14 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				if (tmin < neg_limit) invalid = true;
 			} else {
 				for (int r = 0; r < sh; r++) {
-					const float yl = (float)(r - ry);
+					const float yl = (float)(r - ry) - oy;
 					float X, Y;
 					if constexpr (NP == 6) {
-						X = px + fmaf(ax1, yl, ax0);
-						Y = py + fmaf(ay1, yl, ay0);
+						X = pcx + fmaf(ax1, yl, ax0);
+						Y = pcy + fmaf(ay1, yl, ay0);
 					} else {
-						X = px + fmaf(fmaf(ax2, yl, ax1), yl, ax0);
-						Y = py + fmaf(fmaf(ay2, yl, ay1), yl, ay0);
+						X = pcx + fmaf(fmaf(ax2, yl, ax1), yl, ax0);
+						Y = pcy + fmaf(fmaf(ay2, yl, ay1), yl, ay0);
 					}
 					if (lane_on) {
 						const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
@@ -597,15 +605,15 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			}
 			for (int idx = lane; idx < ntail; idx += 32) {
 				const int r = idx / rem, c = 32 + (idx - r * rem);
-				const float xl = (float)(c - rx), yl = (float)(r - ry);
+				const float xl = (float)(c - rx) - ox, yl = (float)(r - ry) - oy;
 				float X, Y;
 				if constexpr (NP == 6) {
-					X = px + fmaf(A[0], xl, fmaf(A[1], yl, A[2]));
-					Y = py + fmaf(A[3], xl, fmaf(A[4], yl, A[5]));
+					X = pcx + fmaf(A[0], xl, fmaf(A[1], yl, A[2]));
+					Y = pcy + fmaf(A[3], xl, fmaf(A[4], yl, A[5]));
 				} else {
 					const float m0 = xl * xl, m1 = xl * yl, m2 = yl * yl;
-					X = px + fmaf(A[0], m0, fmaf(A[1], m1, fmaf(A[2], m2, fmaf(A[3], xl, fmaf(A[4], yl, A[5])))));
-					Y = py + fmaf(A[6], m0, fmaf(A[7], m1, fmaf(A[8], m2, fmaf(A[9], xl, fmaf(A[10], yl, A[11])))));
+					X = pcx + fmaf(A[0], m0, fmaf(A[1], m1, fmaf(A[2], m2, fmaf(A[3], xl, fmaf(A[4], yl, A[5])))));
+					Y = pcy + fmaf(A[6], m0, fmaf(A[7], m1, fmaf(A[8], m2, fmaf(A[9], xl, fmaf(A[10], yl, A[11])))));
 				}
 				const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
 				const bool ok = fast || ((X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax));
@@ -720,7 +728,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 // Returns 0, -1 when one warp's slab does not fit in shared memory, -2 on a CUDA error.
 // d_counter: one int of device memory owned by the context (work queue head).
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
-	size_t smem_optin, int* d_counter, cudaStream_t stream, cudaError_t* err) {
+	size_t smem_optin, int* d_counter, const float* d_center_offsets, cudaStream_t stream, cudaError_t* err) {
 	const size_t per_warp = (size_t)icgn2d_warp_floats(rx, ry) * sizeof(float);
 	int best_wpb = 0, best_warps = 0;
 	for (int wpb = 4; wpb >= 1; wpb >>= 1) {
@@ -739,7 +747,7 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	const int dims[2] = { img.w, img.h };
 	const int box_ref[2] = { icgn2d_ref_w(rx), icgn2d_ref_h(ry) }, box_tar[2] = { icgn2d_tar_w(rx), icgn2d_tar_h(ry) };
 	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm_ref, img.ref, 2, dims, box_ref) && tma_make_map(&tm_tar, img.tar, 2, dims, box_tar);
-	void (*kern)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int);
+	void (*kern)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int, const float*);
 	if (np == 6) kern = (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16> : icgn2d_kernel<6, 0>;
 	else kern = (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20> : icgn2d_kernel<12, 0>;
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -750,7 +758,7 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	long long resident = (long long)sm_count * (best_warps / best_wpb);
 	int grid = (int)(blocks_needed < resident ? blocks_needed : resident); // persistent: one wave
 	if (grid < 1) grid = 1;
-	kern<<<grid, best_wpb * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, d_counter, tm_ref, tm_tar, use_tma);
+	kern<<<grid, best_wpb * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, d_counter, tm_ref, tm_tar, use_tma, d_center_offsets);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;
 }

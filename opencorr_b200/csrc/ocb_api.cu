@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <map>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,8 @@ struct ocb_ctx {
 	// POI staging
 	float* d_poi = nullptr;
 	size_t d_poi_bytes = 0;
+	float* d_off = nullptr; // centre offsets (2 floats per POI)
+	size_t d_off_bytes = 0;
 };
 
 static int set_error(ocb_ctx* ctx, int code, const char* fmt, ...) {
@@ -194,6 +197,7 @@ void ocb_destroy(ocb_ctx* ctx) {
 	for (auto& kv : ctx->twiddles) cudaFree(kv.second);
 	cudaFree(ctx->fft_scratch);
 	cudaFree(ctx->d_poi);
+	cudaFree(ctx->d_off);
 	cudaFree(ctx->d_counter);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -402,7 +406,7 @@ int ocb_icgn2d_prepare(ocb_ctx* ctx) {
 	return OCB_OK;
 }
 
-static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop) {
+static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, const float* d_offsets = nullptr) {
 	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "icgn2d: images not set");
 	if (!ctx->prepared2) return set_error(ctx, OCB_ERR_STATE, "icgn2d: prepare() has not been called since setImages()");
@@ -410,7 +414,7 @@ static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int
 	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "icgn2d: too many POIs in one call");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	cudaError_t err = cudaSuccess;
-	int rc = ocb::icgn2d_launch(np, ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->d_counter, ctx->stream, &err);
+	int rc = ocb::icgn2d_launch(np, ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->d_counter, d_offsets, ctx->stream, &err);
 	if (rc == -1) return set_error(ctx, OCB_ERR_UNSUPPORTED, "icgn2d: subset radius (%d,%d) exceeds the shared-memory design limit", rx, ry);
 	if (rc) return set_error(ctx, OCB_ERR_CUDA, "icgn2d launch failed: %s", cudaGetErrorString(err));
 	ctx->launches++;
@@ -432,6 +436,72 @@ static int icgn2d_host(ocb_ctx* ctx, int np, void* poi2d, size_t n, int rx, int 
 }
 int ocb_icgn2d1(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 6, p, n, rx, ry, conv, stop); }
 int ocb_icgn2d2(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 12, p, n, rx, ry, conv, stop); }
+
+int ocb_icgn2d_ex_dev(ocb_ctx* ctx, int order, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, const float* d_center_offsets) {
+	if (order != 1 && order != 2) return set_error(ctx, OCB_ERR_ARG, "icgn2d_ex: order must be 1 or 2");
+	return icgn2d_dev(ctx, order == 1 ? 6 : 12, d_poi2d, n, rx, ry, conv, stop, d_center_offsets);
+}
+
+// one launch over a host queue (all POIs share the radius), optional host offsets
+static int icgn2d_host_group(ocb_ctx* ctx, int np, float* poi2d, size_t n, int rx, int ry, float conv, float stop, const float* offsets) {
+	int rc;
+	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
+	const float* d_off = nullptr;
+	if (offsets) {
+		const size_t ob = n * 2 * sizeof(float);
+		if (ob > ctx->d_off_bytes) {
+			cudaFree(ctx->d_off);
+			ctx->d_off = nullptr;
+			ctx->d_off_bytes = 0;
+			OCB_CUDA(ctx, cudaMalloc(&ctx->d_off, ob));
+			ctx->d_off_bytes = ob;
+		}
+		OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_off, offsets, ob, cudaMemcpyHostToDevice, ctx->stream));
+		d_off = ctx->d_off;
+	}
+	if ((rc = icgn2d_dev(ctx, np, ctx->d_poi, n, rx, ry, conv, stop, d_off))) return rc;
+	return unstage_pois(ctx, poi2d, bytes);
+}
+
+int ocb_icgn2d_ex(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, const float* center_offsets,
+	int self_adaptive) {
+	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn2d_ex: bad arguments");
+	if (order != 1 && order != 2) return set_error(ctx, OCB_ERR_ARG, "icgn2d_ex: order must be 1 or 2");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const int np = order == 1 ? 6 : 12;
+	float* q = (float*)poi2d;
+	if (!self_adaptive) return icgn2d_host_group(ctx, np, q, n, rx, ry, conv, stop, center_offsets);
+	// self-adaptive: group the POIs by their own (subset_radius.x, subset_radius.y); one launch per group
+	std::map<std::pair<int, int>, std::vector<size_t>> groups;
+	for (size_t i = 0; i < n; i++) {
+		const float* p = q + i * OCB_POI2D_FLOATS;
+		groups[std::make_pair((int)p[23], (int)p[24])].push_back(i);
+	}
+	std::vector<float> gq, goff;
+	for (auto& kv : groups) {
+		const int grx = kv.first.first, gry = kv.first.second;
+		const std::vector<size_t>& idx = kv.second;
+		if (grx < 1 || gry < 1) { // the reference would size its scratch from a radius < 1 (undefined); reject like a failed guard
+			for (size_t i : idx)
+				if (q[i * OCB_POI2D_FLOATS + 16] >= 0) q[i * OCB_POI2D_FLOATS + 16] = -3.f;
+			continue;
+		}
+		gq.resize(idx.size() * OCB_POI2D_FLOATS);
+		for (size_t k = 0; k < idx.size(); k++) memcpy(&gq[k * OCB_POI2D_FLOATS], q + idx[k] * OCB_POI2D_FLOATS, OCB_POI2D_FLOATS * sizeof(float));
+		const float* off = nullptr;
+		if (center_offsets) {
+			goff.resize(idx.size() * 2);
+			for (size_t k = 0; k < idx.size(); k++) { goff[2 * k] = center_offsets[2 * idx[k]]; goff[2 * k + 1] = center_offsets[2 * idx[k] + 1]; }
+			off = goff.data();
+		}
+		int rc = icgn2d_host_group(ctx, np, gq.data(), idx.size(), grx, gry, conv, stop, off);
+		if (rc) return rc;
+		for (size_t k = 0; k < idx.size(); k++) memcpy(q + idx[k] * OCB_POI2D_FLOATS, &gq[k * OCB_POI2D_FLOATS], OCB_POI2D_FLOATS * sizeof(float));
+	}
+	return OCB_OK;
+}
 
 int ocb_icgn3d_prepare(ocb_ctx* ctx) {
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");

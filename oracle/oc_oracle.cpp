@@ -471,10 +471,18 @@ struct Scratch2D {
 };
 
 // ICGN2D1::compute(POI2D*) src/oc_icgn.cpp:144-341 (NP=6) and ICGN2D2::compute(POI2D*) :685-898 (NP=12).
+// With a centre offset (off_x, off_y) this is compute(POI2D*, Point2D& center_offset), :353-547 / :910-1126:
+// local coordinates become (int - offset) and the target subset is centred at poi + offset.
+// self_adaptive: the radius comes from the POI record (:152-158).
 template <class T, int NP>
-void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion, float stop_condition, Scratch2D<T>& s) {
+void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion, float stop_condition, Scratch2D<T>& s,
+	float off_x = 0.f, float off_y = 0.f, bool self_adaptive = false) {
 	float px = poi[P2_X], py = poi[P2_Y];
 	float* def = poi + P2_DEF;
+	if (self_adaptive) {
+		rx = (int)poi[P2_RX];
+		ry = (int)poi[P2_RY];
+	}
 	// guard :160-167 / :701-708
 	if (py - ry < 0 || px - rx < 0 || py + ry > c.h - 1 || px + rx > c.w - 1
 		|| std::fabs(def[D2_U]) >= c.w || std::fabs(def[D2_V]) >= c.h
@@ -503,15 +511,16 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 	for (int i = 0; i < NP * NP; i++) H[i] = 0;
 	for (int r = 0; r < sh; r++)
 		for (int col = 0; col < sw; col++) {
-			int xl = col - rx, yl = r - ry;
-			int xg = (int)px + xl, yg = (int)py + yl;
+			int xli = col - rx, yli = r - ry;
+			int xg = (int)px + xli, yg = (int)py + yli;
 			T gx = c.gx[(size_t)yg * c.w + xg], gy = c.gy[(size_t)yg * c.w + xg];
 			T* sd = &s.sd[(size_t)(r * sw + col) * NP];
+			T xl = (T)((float)xli - off_x), yl = (T)((float)yli - off_y); // exact integers when the offset is 0
 			if (NP == 6) {
 				sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl;
 				sd[3] = gy; sd[4] = gy * xl; sd[5] = gy * yl;
 			} else {
-				T xx = (T)((xl * xl) * 0.5f), xy = (T)(float)(xl * yl), yy = (T)((yl * yl) * 0.5f);
+				T xx = (xl * xl) * (T)0.5, xy = xl * yl, yy = (yl * yl) * (T)0.5;
 				sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl; sd[3] = gx * xx; sd[4] = gx * xy; sd[5] = gx * yy;
 				sd[6] = gy; sd[7] = gy * xl; sd[8] = gy * yl; sd[9] = gy * xx; sd[10] = gy * xy; sd[11] = gy * yy;
 			}
@@ -546,7 +555,7 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 		bool any_negative = false;
 		for (int r = 0; r < sh; r++)
 			for (int col = 0; col < sw; col++) {
-				T xl = (T)(col - rx), yl = (T)(r - ry);
+				T xl = (T)((float)(col - rx) - off_x), yl = (T)((float)(r - ry) - off_y);
 				T wx, wy;
 				if (NP == 6) { // Deformation2D1::warp :94-105
 					wx = W[0] * xl + W[1] * yl + W[2] * (T)1;
@@ -556,7 +565,7 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 					wx = W[18] * v0 + W[19] * v1 + W[20] * v2 + W[21] * xl + W[22] * yl + W[23] * (T)1;
 					wy = W[24] * v0 + W[25] * v1 + W[26] * v2 + W[27] * xl + W[28] * yl + W[29] * (T)1;
 				}
-				T gxp = (T)px + wx, gyp = (T)py + wy; // center + warped (:239)
+				T gxp = (T)(px + off_x) + wx, gyp = (T)(py + off_y) + wy; // center + warped (:239); center = poi + offset (:430-431)
 				T val = bicubic_eval<T>(c, gxp, gyp);
 				if (val < 0) any_negative = true;
 				s.tar[r * sw + col] = val;
@@ -957,12 +966,13 @@ void run_fftcc2d(const Ctx2D& c, float* pois, long n, int rx, int ry) {
 	}
 }
 template <class T, int NP>
-void run_icgn2d(const Ctx2D& c, float* pois, long n, int rx, int ry, float conv, float stop) {
+void run_icgn2d(const Ctx2D& c, float* pois, long n, int rx, int ry, float conv, float stop, const float* offsets = nullptr, bool self_adaptive = false) {
 #pragma omp parallel num_threads(c.threads)
 	{
 		Scratch2D<T> s;
 #pragma omp for schedule(dynamic, 64)
-		for (long i = 0; i < n; i++) icgn2d_poi<T, NP>(c, pois + i * P2_N, rx, ry, conv, stop, s);
+		for (long i = 0; i < n; i++)
+			icgn2d_poi<T, NP>(c, pois + i * P2_N, rx, ry, conv, stop, s, offsets ? offsets[2 * i] : 0.f, offsets ? offsets[2 * i + 1] : 0.f, self_adaptive);
 	}
 }
 template <class T>
@@ -1032,6 +1042,21 @@ int oco_icgn2d2(void* h, float* pois, long n, int rx, int ry, float conv, float 
 	Ctx2D* c = (Ctx2D*)h;
 	if (!c->prepared) return -1;
 	if (exact) run_icgn2d<double, 12>(*c, pois, n, rx, ry, conv, stop); else run_icgn2d<float, 12>(*c, pois, n, rx, ry, conv, stop);
+	return 0;
+}
+
+// compute(std::vector<POI2D>&, std::vector<Point2D>& center_offset_queue) (src/oc_icgn.cpp:549-557, :1128-1136)
+// and the self-adaptive mode; order = 1 (ICGN2D1) or 2 (ICGN2D2); offsets may be NULL.
+int oco_icgn2d_ex(void* h, int order, float* pois, long n, int rx, int ry, float conv, float stop, const float* offsets, int self_adaptive, int exact) {
+	Ctx2D* c = (Ctx2D*)h;
+	if (!c->prepared) return -1;
+	if (order == 1) {
+		if (exact) run_icgn2d<double, 6>(*c, pois, n, rx, ry, conv, stop, offsets, self_adaptive != 0);
+		else run_icgn2d<float, 6>(*c, pois, n, rx, ry, conv, stop, offsets, self_adaptive != 0);
+	} else {
+		if (exact) run_icgn2d<double, 12>(*c, pois, n, rx, ry, conv, stop, offsets, self_adaptive != 0);
+		else run_icgn2d<float, 12>(*c, pois, n, rx, ry, conv, stop, offsets, self_adaptive != 0);
+	}
 	return 0;
 }
 

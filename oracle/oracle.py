@@ -44,6 +44,9 @@ def lib():
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                           ctypes.c_float, ctypes.c_float, ctypes.c_int]
+        L.oco_icgn2d_ex.restype = ctypes.c_int
+        L.oco_icgn2d_ex.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_float, ctypes.c_float, _f32p, ctypes.c_int, ctypes.c_int]
         L.oco_create3d.restype = ctypes.c_void_p
         L.oco_create3d.argtypes = [_f32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.oco_destroy3d.argtypes = [ctypes.c_void_p]
@@ -126,6 +129,20 @@ class Oracle2D:
         if not self._prepared:
             self.prepare()
         rc = lib().oco_icgn2d2(self._h, _p(pois), pois.shape[0], rx, ry, conv, stop, int(exact))
+        assert rc == 0
+        return pois
+
+    def icgn2d_ex(self, order, pois, rx, ry, conv=0.001, stop=10, center_offsets=None, self_adaptive=False, exact=False):
+        """compute(queue, center_offset_queue) and/or the self-adaptive mode (radius read from each POI)."""
+        assert pois.dtype == np.float32 and pois.flags.c_contiguous and pois.shape[1] == 25
+        if not self._prepared:
+            self.prepare()
+        off = None
+        if center_offsets is not None:
+            off = _c32(center_offsets).reshape(-1, 2)
+            assert off.shape[0] == pois.shape[0]
+        rc = lib().oco_icgn2d_ex(self._h, order, _p(pois), pois.shape[0], rx, ry, conv, stop,
+                                 _p(off) if off is not None else None, int(self_adaptive), int(exact))
         assert rc == 0
         return pois
 

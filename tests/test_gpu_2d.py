@@ -304,3 +304,51 @@ def test_negative_interpolated_sample_is_rejected(engine):
     assert (q_cpu[:, 16] == -3).sum() > 0
     # borderline samples (|t| < 1e-3) may be classified differently; require agreement on >= 90 %
     assert ((q_gpu[:, 16] == -3) == (q_cpu[:, 16] == -3)).mean() >= 0.9
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_icgn2d_center_offset_overload(engine, order):
+    """compute(queue, center_offset_queue), reference src/oc_icgn.cpp:353-557 / :910-1136."""
+    ref, tar = synth.speckle_pair_2d(400, 360, second_order=(order == 2))
+    xy = synth.grid_2d(90, 80, 8, 6, 27, 33)
+    rng = np.random.default_rng(5)
+    off = rng.uniform(-4, 4, (len(xy), 2)).astype(np.float32)
+    off[0] = 0.0
+    q = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, 16, 16)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    cls = ob.ICGN2D1 if order == 1 else ob.ICGN2D2
+    icgn = cls(16, 16, 0.001, 10, engine=engine)
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.compute(q_gpu, off)
+    o.icgn2d_ex(order, q_cpu, 16, 16, 0.001, 10, center_offsets=off)
+    stats = util.compare_2d(q_gpu, q_cpu, "offset order %d" % order, max_iter_mismatch_frac=0.05)
+    assert stats["n_compared"] >= 0.9 * len(q)
+    # the offset moves the point whose displacement is reported: it must differ from the plain overload
+    q_plain = q.copy()
+    icgn.compute(q_plain)
+    assert np.abs(q_plain[1:, 2] - q_gpu[1:, 2]).max() > 1e-3
+    assert np.abs(q_plain[0, 2:14] - q_gpu[0, 2:14]).max() < 1e-6  # zero offset == plain overload
+
+
+def test_icgn2d1_self_adaptive(engine):
+    """setSelfAdaptive(true): every POI uses its own subset_radius (src/oc_icgn.cpp:152-158)."""
+    ref, tar = synth.speckle_pair_2d(400, 360)
+    xy = synth.grid_2d(90, 80, 9, 7, 25, 30)
+    q = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, 16, 16)
+    radii = np.array([[10, 10], [16, 16], [12, 20], [23, 9]], np.float32)
+    q[:, 23:25] = radii[np.arange(len(q)) % 4]
+    q_gpu, q_cpu = q.copy(), q.copy()
+    icgn = ob.ICGN2D1(99, 99, 0.001, 10, engine=engine)  # the constructor radius is ignored in this mode
+    icgn.set_images(ref, tar)
+    icgn.prepare()
+    icgn.set_self_adaptive(True)
+    icgn.compute(q_gpu)
+    o.icgn2d_ex(1, q_cpu, 99, 99, 0.001, 10, self_adaptive=True)
+    stats = util.compare_2d(q_gpu, q_cpu, "self-adaptive", max_iter_mismatch_frac=0.05)
+    assert stats["n_compared"] >= 0.9 * len(q)
+    assert np.array_equal(q_gpu[:, 23:25], q[:, 23:25])

@@ -192,3 +192,27 @@ def test_fftcc3d_and_icgn3d1_recover_known_field(pair3d):
     assert np.array_equal(q2, before)
     o.icgn3d1(q2, 8, 8, 8, 0.001, 20)
     assert q2[0, 18] == -3
+
+
+def test_icgn2d_ex_reduces_to_plain_overloads():
+    """Zero offsets == compute(queue); self-adaptive with a uniform radius == that radius."""
+    ref, tar = synth.speckle_pair_2d(220, 200)
+    xy = synth.grid_2d(60, 60, 4, 3, 28, 31)
+    o = Oracle2D(ref, tar)
+    q = make_poi2d(xy)
+    o.fftcc2d(q, 12, 12)
+    for order, plain in ((1, o.icgn2d1), (2, o.icgn2d2)):
+        a, b, c = q.copy(), q.copy(), q.copy()
+        plain(a, 12, 12, 0.001, 10)
+        o.icgn2d_ex(order, b, 12, 12, 0.001, 10, center_offsets=np.zeros((len(q), 2), np.float32))
+        assert np.array_equal(a, b)
+        c[:, 23:25] = 12
+        o.icgn2d_ex(order, c, 5, 7, 0.001, 10, self_adaptive=True)
+        assert np.array_equal(a, c)
+    # a centre offset reports the displacement of the offset point: u changes by ~ du/dx * off_x
+    d = q.copy()
+    off = np.tile(np.array([[3.0, 0.0]], np.float32), (len(q), 1))
+    o.icgn2d_ex(1, d, 12, 12, 0.001, 10, center_offsets=off)
+    e = q.copy()
+    o.icgn2d1(e, 12, 12, 0.001, 10)
+    assert np.allclose(d[:, 2] - e[:, 2], 3.0 * 1.5e-3, atol=2e-3)
