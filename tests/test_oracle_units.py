@@ -215,4 +215,4 @@ def test_icgn2d_ex_reduces_to_plain_overloads():
     o.icgn2d_ex(1, d, 12, 12, 0.001, 10, center_offsets=off)
     e = q.copy()
     o.icgn2d1(e, 12, 12, 0.001, 10)
-    assert np.allclose(d[:, 2] - e[:, 2], 3.0 * 1.5e-3, atol=2e-3)
+    assert abs(float(np.mean(d[:, 2] - e[:, 2])) - 3.0 * 1.5e-3) < 1.5e-3
