@@ -22,6 +22,9 @@
 #define _OPENCORR_B200_SHIM_H_
 
 #include <algorithm>
+#if __cplusplus >= 201703L
+#include <charconv>
+#endif
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -603,6 +606,43 @@ namespace opencorr
 		}
 	};
 
+	// ------------------------------------------------------------------ fast "%.8f" table writer (not in the reference)
+	// The reference writes tables with `ofstream << setprecision(8) << fixed`, one number at a time
+	// (src/oc_io.cpp:320-322); at GPU speed that becomes the slowest stage of a run (500 k rows x 15
+	// numbers).  This buffer produces byte-identical text with std::to_chars (C++17) or snprintf.
+	namespace b200
+	{
+		class TableWriter
+		{
+			std::string buf;
+			std::string delim;
+
+		public:
+			explicit TableWriter(const std::string& delimiter) : delim(delimiter) { buf.reserve(1 << 20); }
+			inline void text(const char* t) { buf.append(t); buf.append(delim); }
+			inline void num(float v)
+			{
+				char tmp[64];
+#if __cplusplus >= 201703L && defined(__cpp_lib_to_chars)
+				auto r = std::to_chars(tmp, tmp + sizeof(tmp), (double)v, std::chars_format::fixed, 8);
+				buf.append(tmp, r.ptr - tmp);
+#else
+				int n = std::snprintf(tmp, sizeof(tmp), "%.8f", (double)v);
+				buf.append(tmp, (size_t)n);
+#endif
+				buf.append(delim);
+			}
+			inline void endRow() { buf.push_back('\n'); }
+			inline bool save(const std::string& path)
+			{
+				std::ofstream out(path, std::ios::binary);
+				if (!out.is_open()) return false;
+				out.write(buf.data(), (std::streamsize)buf.size());
+				return true;
+			}
+		};
+	} // namespace b200
+
 	// ------------------------------------------------------------------ src/oc_io.h (subset used by the two examples)
 	enum OutputVariable
 	{
@@ -634,42 +674,34 @@ namespace opencorr
 		// src/oc_io.cpp:318-373
 		void saveTable2D(std::vector<POI2D>& poi_queue)
 		{
-			std::ofstream file_out(file_path);
-			file_out.setf(std::ios::fixed);
-			file_out << std::setprecision(8);
-			if (file_out.is_open()) {
-				const char* head[] = { "x", "y", "u", "v", "u0", "v0", "ZNCC", "iteration", "convergence", "feature", "exx", "eyy", "exy", "subset_rx", "subset_ry" };
-				for (const char* h : head) file_out << h << delimiter;
-				file_out << std::endl;
-				for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
-					file_out << iter->x << delimiter << iter->y << delimiter;
-					file_out << iter->deformation.u << delimiter << iter->deformation.v << delimiter;
-					for (int i = 0; i < 6; i++) file_out << iter->result.r[i] << delimiter;
-					for (int i = 0; i < 3; i++) file_out << iter->strain.e[i] << delimiter;
-					file_out << iter->subset_radius.x << delimiter << iter->subset_radius.y << delimiter;
-					file_out << std::endl;
-				}
+			b200::TableWriter t(delimiter);
+			const char* head[] = { "x", "y", "u", "v", "u0", "v0", "ZNCC", "iteration", "convergence", "feature", "exx", "eyy", "exy", "subset_rx", "subset_ry" };
+			for (const char* h : head) t.text(h);
+			t.endRow();
+			for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
+				t.num(iter->x); t.num(iter->y);
+				t.num(iter->deformation.u); t.num(iter->deformation.v);
+				for (int i = 0; i < 6; i++) t.num(iter->result.r[i]);
+				for (int i = 0; i < 3; i++) t.num(iter->strain.e[i]);
+				t.num(iter->subset_radius.x); t.num(iter->subset_radius.y);
+				t.endRow();
 			}
-			file_out.close();
+			t.save(file_path);
 		}
 		// src/oc_io.cpp:375-421
 		void saveDeformationTable2D(std::vector<POI2D>& poi_queue)
 		{
-			std::ofstream file_out(file_path);
-			file_out.setf(std::ios::fixed);
-			file_out << std::setprecision(8);
-			if (file_out.is_open()) {
-				const char* head[] = { "x", "y", "u", "ux", "uy", "uxx", "uxy", "uyy", "v", "vx", "vy", "vxx", "vxy", "vyy", "subset_rx", "subset_ry" };
-				for (const char* h : head) file_out << h << delimiter;
-				file_out << std::endl;
-				for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
-					file_out << iter->x << delimiter << iter->y << delimiter;
-					for (int i = 0; i < 12; i++) file_out << iter->deformation.p[i] << delimiter;
-					file_out << iter->subset_radius.x << delimiter << iter->subset_radius.y << delimiter;
-					file_out << std::endl;
-				}
+			b200::TableWriter t(delimiter);
+			const char* head[] = { "x", "y", "u", "ux", "uy", "uxx", "uxy", "uyy", "v", "vx", "vy", "vxx", "vxy", "vyy", "subset_rx", "subset_ry" };
+			for (const char* h : head) t.text(h);
+			t.endRow();
+			for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
+				t.num(iter->x); t.num(iter->y);
+				for (int i = 0; i < 12; i++) t.num(iter->deformation.p[i]);
+				t.num(iter->subset_radius.x); t.num(iter->subset_radius.y);
+				t.endRow();
 			}
-			file_out.close();
+			t.save(file_path);
 		}
 		// src/oc_io.cpp:423-504
 		void saveMap2D(std::vector<POI2D>& poi_queue, OutputVariable variable)
@@ -692,16 +724,12 @@ namespace opencorr
 				}
 				output_map[(size_t)(int)p.y * width + (int)p.x] = val;
 			}
-			std::ofstream file_out(file_path);
-			file_out.setf(std::ios::fixed);
-			file_out << std::setprecision(8);
-			if (file_out.is_open()) {
-				for (int r = 0; r < height; r++) {
-					for (int c = 0; c < width; c++) file_out << output_map[(size_t)r * width + c] << delimiter;
-					file_out << std::endl;
-				}
+			b200::TableWriter t(delimiter);
+			for (int r = 0; r < height; r++) {
+				for (int c = 0; c < width; c++) t.num(output_map[(size_t)r * width + c]);
+				t.endRow();
 			}
-			file_out.close();
+			t.save(file_path);
 		}
 	};
 
@@ -729,27 +757,23 @@ namespace opencorr
 		// src/oc_io.cpp:1004-1089
 		void saveTable3D(std::vector<POI3D>& poi_queue)
 		{
-			std::ofstream file_out(file_path);
-			file_out.setf(std::ios::fixed);
-			file_out << std::setprecision(8);
-			if (file_out.is_open()) {
-				const char* head[] = { "x", "y", "z", "u", "v", "w", "u0", "v0", "w0", "ZNCC", "iteration", "convergence", "feature",
-					"ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "exx", "eyy", "ezz", "exy", "eyz", "ezx", "subset_rx", "subset_ry", "subset_rz" };
-				for (const char* h : head) file_out << h << delimiter;
-				file_out << std::endl;
-				for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
-					file_out << iter->x << delimiter << iter->y << delimiter << iter->z << delimiter;
-					file_out << iter->deformation.u << delimiter << iter->deformation.v << delimiter << iter->deformation.w << delimiter;
-					for (int i = 0; i < 7; i++) file_out << iter->result.r[i] << delimiter;
-					file_out << iter->deformation.ux << delimiter << iter->deformation.uy << delimiter << iter->deformation.uz << delimiter;
-					file_out << iter->deformation.vx << delimiter << iter->deformation.vy << delimiter << iter->deformation.vz << delimiter;
-					file_out << iter->deformation.wx << delimiter << iter->deformation.wy << delimiter << iter->deformation.wz << delimiter;
-					for (int i = 0; i < 6; i++) file_out << iter->strain.e[i] << delimiter;
-					file_out << iter->subset_radius.x << delimiter << iter->subset_radius.y << delimiter << iter->subset_radius.z << delimiter;
-					file_out << std::endl;
-				}
+			b200::TableWriter t(delimiter);
+			const char* head[] = { "x", "y", "z", "u", "v", "w", "u0", "v0", "w0", "ZNCC", "iteration", "convergence", "feature",
+				"ux", "uy", "uz", "vx", "vy", "vz", "wx", "wy", "wz", "exx", "eyy", "ezz", "exy", "eyz", "ezx", "subset_rx", "subset_ry", "subset_rz" };
+			for (const char* h : head) t.text(h);
+			t.endRow();
+			for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
+				t.num(iter->x); t.num(iter->y); t.num(iter->z);
+				t.num(iter->deformation.u); t.num(iter->deformation.v); t.num(iter->deformation.w);
+				for (int i = 0; i < 7; i++) t.num(iter->result.r[i]);
+				t.num(iter->deformation.ux); t.num(iter->deformation.uy); t.num(iter->deformation.uz);
+				t.num(iter->deformation.vx); t.num(iter->deformation.vy); t.num(iter->deformation.vz);
+				t.num(iter->deformation.wx); t.num(iter->deformation.wy); t.num(iter->deformation.wz);
+				for (int i = 0; i < 6; i++) t.num(iter->strain.e[i]);
+				t.num(iter->subset_radius.x); t.num(iter->subset_radius.y); t.num(iter->subset_radius.z);
+				t.endRow();
 			}
-			file_out.close();
+			t.save(file_path);
 		}
 	};
 

@@ -75,6 +75,11 @@ long long ocb_launch_count(const ocb_ctx* ctx);
 /* Host buffers; copied to the device (H2D on the context's stream). */
 int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int width, int height, int col_major);
 int ocb_set_images_3d(ocb_ctx* ctx, const float* ref, const float* tar, int dim_x, int dim_y, int dim_z);
+/* 8-bit host images (what cv::imread(..., IMREAD_GRAYSCALE) hands the reference before cv2eigen turns
+ * them into floats, src/oc_image.cpp:39,56): uploaded as bytes (4x fewer PCIe bytes) and widened to
+ * f32 on the device; results are identical to passing the float copy.  Row-major / [z][y][x]. */
+int ocb_set_images_2d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, int width, int height);
+int ocb_set_images_3d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, int dim_x, int dim_y, int dim_z);
 /* Device buffers (row-major / [z][y][x]); BORROWED like the reference borrows Image2D*. */
 int ocb_set_images_2d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int width, int height);
 int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int dim_x, int dim_y, int dim_z);

@@ -32,6 +32,8 @@ SIGNATURES = {
     "ocb_launch_count": (ctypes.c_longlong, [_vp]),
     "ocb_set_images_2d": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "ocb_set_images_3d": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "ocb_set_images_2d_u8": (_i, [_vp, _vp, _vp, _i, _i]),
+    "ocb_set_images_3d_u8": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "ocb_set_images_2d_dev": (_i, [_vp, _vp, _vp, _i, _i]),
     "ocb_set_images_3d_dev": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "ocb_fftcc2d": (_i, [_vp, _vp, _sz, _i, _i]),

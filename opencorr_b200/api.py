@@ -82,21 +82,33 @@ class Engine:
 
     # images ------------------------------------------------------------------------------------
     def set_images_2d(self, ref, tar):
-        ref = np.ascontiguousarray(ref, dtype=np.float32)
-        tar = np.ascontiguousarray(tar, dtype=np.float32)
+        """float32 images, or uint8 images (as read from an 8-bit file): the latter are uploaded as
+        bytes and widened on the device -- same results, a quarter of the PCIe traffic."""
+        ref, tar = np.asarray(ref), np.asarray(tar)
         if ref.ndim != 2 or ref.shape != tar.shape:
             raise ValueError("ref/tar must be 2-D arrays of equal shape")
         h, w = ref.shape
-        self._ck(self._lib.ocb_set_images_2d(self._ctx, _vp(ref), _vp(tar), w, h, 0))
+        if ref.dtype == np.uint8 and tar.dtype == np.uint8:
+            ref, tar = np.ascontiguousarray(ref), np.ascontiguousarray(tar)
+            self._ck(self._lib.ocb_set_images_2d_u8(self._ctx, _vp(ref), _vp(tar), w, h))
+        else:
+            ref = np.ascontiguousarray(ref, dtype=np.float32)
+            tar = np.ascontiguousarray(tar, dtype=np.float32)
+            self._ck(self._lib.ocb_set_images_2d(self._ctx, _vp(ref), _vp(tar), w, h, 0))
         self._ck(self._lib.ocb_sync(self._ctx))
 
     def set_images_3d(self, ref, tar):
-        ref = np.ascontiguousarray(ref, dtype=np.float32)
-        tar = np.ascontiguousarray(tar, dtype=np.float32)
+        ref, tar = np.asarray(ref), np.asarray(tar)
         if ref.ndim != 3 or ref.shape != tar.shape:
             raise ValueError("ref/tar must be 3-D arrays [z, y, x] of equal shape")
         dz, dy, dx = ref.shape
-        self._ck(self._lib.ocb_set_images_3d(self._ctx, _vp(ref), _vp(tar), dx, dy, dz))
+        if ref.dtype == np.uint8 and tar.dtype == np.uint8:
+            ref, tar = np.ascontiguousarray(ref), np.ascontiguousarray(tar)
+            self._ck(self._lib.ocb_set_images_3d_u8(self._ctx, _vp(ref), _vp(tar), dx, dy, dz))
+        else:
+            ref = np.ascontiguousarray(ref, dtype=np.float32)
+            tar = np.ascontiguousarray(tar, dtype=np.float32)
+            self._ck(self._lib.ocb_set_images_3d(self._ctx, _vp(ref), _vp(tar), dx, dy, dz))
         self._ck(self._lib.ocb_sync(self._ctx))
 
     def set_images_2d_dev(self, d_ref, d_tar, width, height):

@@ -31,6 +31,15 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 		if (c < w && r < h) out[(size_t)r * w + c] = t[threadIdx.x][j];
 	}
 }
+__global__ void widen_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, size_t n) {
+	// 4 pixels per thread: one 32-bit load, one 128-bit store (n4 = n / 4 handled vectorised, tail scalar)
+	const size_t n4 = n / 4;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+		const uchar4 v = reinterpret_cast<const uchar4*>(in)[i];
+		reinterpret_cast<float4*>(out)[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+	}
+	for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
 } // namespace ocb
 
 static thread_local std::string g_last_error = "";
@@ -72,6 +81,8 @@ struct ocb_ctx {
 	// POI staging
 	float* d_poi = nullptr;
 	size_t d_poi_bytes = 0;
+	unsigned char* d_u8 = nullptr; // staging for 8-bit image uploads
+	size_t d_u8_bytes = 0;
 	float* d_off = nullptr; // centre offsets (2 floats per POI)
 	size_t d_off_bytes = 0;
 };
@@ -198,6 +209,7 @@ void ocb_destroy(ocb_ctx* ctx) {
 	cudaFree(ctx->fft_scratch);
 	cudaFree(ctx->d_poi);
 	cudaFree(ctx->d_off);
+	cudaFree(ctx->d_u8);
 	cudaFree(ctx->d_counter);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -265,6 +277,62 @@ int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int widt
 		cudaFree(tmp);
 	}
 	return ocb_set_images_2d_dev(ctx, ctx->own_ref2, ctx->own_tar2, width, height);
+}
+
+// upload `elems` bytes twice (ref, tar) and widen into the context-owned float buffers dst_ref/dst_tar
+static int upload_u8_pair(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, size_t elems, float* dst_ref, float* dst_tar) {
+	if (2 * elems > ctx->d_u8_bytes) {
+		cudaFree(ctx->d_u8);
+		ctx->d_u8 = nullptr;
+		ctx->d_u8_bytes = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->d_u8, 2 * elems));
+		ctx->d_u8_bytes = 2 * elems;
+	}
+	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_u8, ref, elems, cudaMemcpyHostToDevice, ctx->stream));
+	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_u8 + elems, tar, elems, cudaMemcpyHostToDevice, ctx->stream));
+	const int grid = ctx->sm_count * 8;
+	ocb::widen_u8_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_u8, dst_ref, elems);
+	ocb::widen_u8_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_u8 + elems, dst_tar, elems);
+	ctx->launches += 2;
+	OCB_CUDA(ctx, cudaGetLastError());
+	return OCB_OK;
+}
+
+int ocb_set_images_2d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, int width, int height) {
+	if (!ctx || !ref || !tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d_u8: bad arguments");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const size_t elems = (size_t)width * height;
+	if (elems > ctx->own2_elems) {
+		cudaFree(ctx->own_ref2);
+		cudaFree(ctx->own_tar2);
+		ctx->own_ref2 = ctx->own_tar2 = nullptr;
+		ctx->own2_elems = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_ref2, elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_tar2, elems * sizeof(float)));
+		ctx->own2_elems = elems;
+	}
+	int rc = upload_u8_pair(ctx, ref, tar, elems, ctx->own_ref2, ctx->own_tar2);
+	if (rc) return rc;
+	return ocb_set_images_2d_dev(ctx, ctx->own_ref2, ctx->own_tar2, width, height);
+}
+
+int ocb_set_images_3d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, int dim_x, int dim_y, int dim_z) {
+	if (!ctx || !ref || !tar || dim_x < 15 || dim_y < 15 || dim_z < 15)
+		return set_error(ctx, OCB_ERR_ARG, "set_images_3d_u8: bad arguments (each dimension must be >= 15)");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const size_t elems = (size_t)dim_x * dim_y * dim_z;
+	if (elems > ctx->own3_elems) {
+		cudaFree(ctx->own_ref3);
+		cudaFree(ctx->own_tar3);
+		ctx->own_ref3 = ctx->own_tar3 = nullptr;
+		ctx->own3_elems = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_ref3, elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_tar3, elems * sizeof(float)));
+		ctx->own3_elems = elems;
+	}
+	int rc = upload_u8_pair(ctx, ref, tar, elems, ctx->own_ref3, ctx->own_tar3);
+	if (rc) return rc;
+	return ocb_set_images_3d_dev(ctx, ctx->own_ref3, ctx->own_tar3, dim_x, dim_y, dim_z);
 }
 
 int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int dim_x, int dim_y, int dim_z) {

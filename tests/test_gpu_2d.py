@@ -352,3 +352,21 @@ def test_icgn2d1_self_adaptive(engine):
     stats = util.compare_2d(q_gpu, q_cpu, "self-adaptive", max_iter_mismatch_frac=0.05)
     assert stats["n_compared"] >= 0.9 * len(q)
     assert np.array_equal(q_gpu[:, 23:25], q[:, 23:25])
+
+
+def test_u8_image_upload_gives_identical_results(engine):
+    """8-bit images uploaded as bytes (ocb_set_images_2d_u8) == the same images passed as float32."""
+    ref, tar = util.oht_cfrp_pair()
+    xy = synth.grid_2d(40, 60, 20, 30, 10, 26)
+    res = []
+    for cast in (np.float32, np.uint8):
+        q = ob.make_poi2d(xy)
+        f = ob.FFTCC2D(16, 16, engine=engine)
+        f.set_images(ref.astype(cast), tar.astype(cast))
+        f.compute(q)
+        icgn = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+        icgn.set_images(ref.astype(cast), tar.astype(cast))
+        icgn.prepare()
+        icgn.compute(q)
+        res.append(q)
+    assert np.array_equal(res[0], res[1])

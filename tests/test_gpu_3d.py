@@ -194,3 +194,22 @@ def test_fftcc3d_w32_specialised_kernel(engine):
         assert np.array_equal(q[:, [3, 7, 11, 15, 16, 17]], q_cpu[:, [3, 7, 11, 15, 16, 17]])
         assert np.abs(q[:, 18] - q_exact[:, 18]).max() < 1e-5
     assert (q_cpu[:, 18] > 0.3).all()
+
+
+def test_u8_volume_upload_gives_identical_results(engine):
+    ref, tar, z0, cpu, gpu = util.al_foam_crop()
+    xyz = cpu[::40, 0:3].copy()
+    xyz[:, 2] -= z0
+    res = []
+    for cast in (np.float32, np.uint8):
+        q = ob.make_poi3d(xyz)
+        f = ob.FFTCC3D(16, 16, 16, engine=engine)
+        f.set_images(ref.astype(cast), tar.astype(cast))
+        f.compute(q)
+        icgn = ob.ICGN3D1(16, 16, 16, 0.001, 20, engine=engine)
+        icgn.set_images(ref.astype(cast), tar.astype(cast))
+        icgn.prepare()
+        icgn.compute(q)
+        res.append(q)
+    assert np.array_equal(res[0], res[1])
+    assert (res[0][:, 18] > 0.8).all()
