@@ -555,6 +555,91 @@ namespace opencorr
 			: b200::ICGN2D<2>(subset_radius_x, subset_radius_y, conv_criterion, stop_condition, thread_number) {}
 	};
 
+	// ------------------------------------------------------------------ src/oc_iclm.h
+	struct DampingParameter
+	{
+		float lambda = 100.f;
+		float alpha = 0.1f;
+		float beta = 10.f;
+	};
+
+	namespace b200
+	{
+		template <int ORDER>
+		class ICLM2D : public DIC
+		{
+		protected:
+			float conv_criterion;
+			float stop_condition;
+			DampingParameter damping;
+
+		public:
+			ICLM2D(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
+			{
+				this->subset_radius_x = subset_radius_x;
+				this->subset_radius_y = subset_radius_y;
+				this->conv_criterion = conv_criterion;
+				this->stop_condition = stop_condition;
+				this->thread_number = thread_number;
+				self_adaptive = false;
+			}
+			void setIteration(float conv_criterion, float stop_condition)
+			{
+				this->conv_criterion = conv_criterion;
+				this->stop_condition = stop_condition;
+			}
+			void setIteration(POI2D* poi)
+			{
+				conv_criterion = poi->result.convergence;
+				stop_condition = (float)(int)poi->result.iteration;
+			}
+			void setDamping(float lambda, float alpha, float beta) // src/oc_iclm.cpp:114-119
+			{
+				damping.lambda = lambda;
+				damping.alpha = alpha;
+				damping.beta = beta;
+			}
+			void prepareRef() { prepare(); }
+			void prepareTar() { prepare(); }
+			void prepare()
+			{
+				Engine& e = Engine::get();
+				std::lock_guard<std::mutex> g(e.lock);
+				e.useImages(ref_img, tar_img);
+				e.check(ocb_icgn2d_prepare(e.context()));
+				e.prepared = true;
+			}
+			void compute(POI2D* poi) { run(poi, 1); }
+			void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+
+		private:
+			void run(POI2D* p, size_t n)
+			{
+				if (self_adaptive) throw std::string("opencorr_b200: self-adaptive subsets are implemented for ICGN2D1/ICGN2D2 only");
+				Engine& e = Engine::get();
+				std::lock_guard<std::mutex> g(e.lock);
+				e.useImages(ref_img, tar_img);
+				if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+				e.check(ocb_iclm2d(e.context(), ORDER, p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition, damping.lambda, damping.alpha,
+					damping.beta));
+			}
+		};
+	} // namespace b200
+
+	class ICLM2D1 : public b200::ICLM2D<1>
+	{
+	public:
+		ICLM2D1(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
+			: b200::ICLM2D<1>(subset_radius_x, subset_radius_y, conv_criterion, stop_condition, thread_number) {}
+	};
+
+	class ICLM2D2 : public b200::ICLM2D<2>
+	{
+	public:
+		ICLM2D2(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
+			: b200::ICLM2D<2>(subset_radius_x, subset_radius_y, conv_criterion, stop_condition, thread_number) {}
+	};
+
 	class ICGN3D1 : public DVC
 	{
 	private:

@@ -50,6 +50,8 @@ SIGNATURES = {
     "ocb_icgn3d1_dev": (_i, [_vp, _vp, _sz, _i, _i, _i, _f, _f]),
     "ocb_icgn2d_ex": (_i, [_vp, _i, _vp, _sz, _i, _i, _f, _f, _vp, _i]),
     "ocb_icgn2d_ex_dev": (_i, [_vp, _i, _vp, _sz, _i, _i, _f, _f, _vp]),
+    "ocb_iclm2d": (_i, [_vp, _i, _vp, _sz, _i, _i, _f, _f, _f, _f, _f]),
+    "ocb_iclm2d_dev": (_i, [_vp, _i, _vp, _sz, _i, _i, _f, _f, _f, _f, _f]),
     "ocb_get_tables_3d": (_i, [_vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -164,6 +164,12 @@ class Engine:
         self._ck(self._lib.ocb_icgn2d_ex(self._ctx, int(order), _vp(q), q.shape[0], rx, ry, conv, stop,
                                          _vp(off) if off is not None else None, int(bool(self_adaptive))))
 
+    def iclm2d(self, order, q, rx, ry, conv, stop, damping=(100.0, 0.1, 10.0)):
+        """ICLM2D1 / ICLM2D2 (reference src/oc_iclm.cpp); damping = (lambda, alpha, beta)."""
+        _check_queue(q, POI2D_FLOATS)
+        self._ck(self._lib.ocb_iclm2d(self._ctx, int(order), _vp(q), q.shape[0], rx, ry, conv, stop,
+                                      float(damping[0]), float(damping[1]), float(damping[2])))
+
     def icgn3d1(self, q, rx, ry, rz, conv, stop):
         _check_queue(q, POI3D_FLOATS)
         self._ck(self._lib.ocb_icgn3d1(self._ctx, _vp(q), q.shape[0], rx, ry, rz, conv, stop))
@@ -311,6 +317,32 @@ class ICGN2D1(_ICGN2D):
 
 
 class ICGN2D2(_ICGN2D):
+    _order = 2
+
+
+class _ICLM2D(_ICGN2D):
+    """ICLM2D1 / ICLM2D2(int rx, int ry, float conv, float stop, int threads), reference src/oc_iclm.h:56-75,110-130."""
+
+    def __init__(self, rx, ry, conv_criterion, stop_condition, thread_number=0, engine=None):
+        super().__init__(rx, ry, conv_criterion, stop_condition, thread_number, engine)
+        self.damping = (100.0, 0.1, 10.0)
+
+    def set_damping(self, lambda_, alpha, beta):
+        self.damping = (float(lambda_), float(alpha), float(beta))
+
+    def compute(self, poi_queue):
+        self.engine.iclm2d(self._order, poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion,
+                           self.stop_condition, self.damping)
+        return poi_queue
+
+    setDamping = set_damping
+
+
+class ICLM2D1(_ICLM2D):
+    _order = 1
+
+
+class ICLM2D2(_ICLM2D):
     _order = 2
 
 

@@ -46,9 +46,10 @@ __host__ __device__ inline int icgn2d_tile_floats(int rx, int ry) {
 	const int a = icgn2d_ref_w(rx) * icgn2d_ref_h(ry), b = icgn2d_tar_w(rx) * icgn2d_tar_h(ry);
 	return round_up32(a > b ? a : b);
 }
-__host__ __device__ inline int icgn2d_warp_floats(int rx, int ry) {
+// lm: the Levenberg-Marquardt variant keeps the undamped Hessian (<= 78 floats) at the end of the slab
+__host__ __device__ inline int icgn2d_warp_floats(int rx, int ry, bool lm) {
 	const int n = (2 * rx + 1) * (2 * ry + 1);
-	return 32 + icgn2d_tile_floats(rx, ry) + round_up32(3 * n);
+	return 32 + icgn2d_tile_floats(rx, ry) + round_up32(3 * n) + (lm ? 96 : 0);
 }
 
 // Shape functions: sd = g_a * phi_i, phi = [1, x, y, x^2/2, xy, y^2/2] (first 3 for NP == 6);
@@ -185,10 +186,14 @@ __device__ __forceinline__ float bicubic_sample(const float* tile, int TW, int t
 
 // RC > 0: subset radius known at compile time (rx == ry == RC), so tile pitches and trip counts fold
 // into immediates; RC == 0: any radii at run time.
-template <int NP, int RC>
+// LM: inverse-compositional Levenberg-Marquardt siblings ICLM2D1 / ICLM2D2 (reference src/oc_iclm.cpp:150-358,
+// :502-730): the Hessian is damped with lambda*I and re-factorised every iteration, a step is accepted only
+// when ZNSSD decreased, and out-of-range samples are NOT rejected (the interpolant's -1 is used as a value).
+template <int NP, int RC, bool LM>
 __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
 	float conv_criterion, float stop_condition, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_ref,
-	const __grid_constant__ CUtensorMap tm_tar, int use_tma, const float* __restrict__ center_offsets) {
+	const __grid_constant__ CUtensorMap tm_tar, int use_tma, const float* __restrict__ center_offsets, float lm_lambda, float lm_alpha,
+	float lm_beta) {
 	extern __shared__ __align__(128) float smem[];
 	constexpr int NH = NP * (NP + 1) / 2;
 	constexpr int NPHI = NP / 2;           // 3 or 6 shape monomials per displacement component
@@ -204,10 +209,11 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 	const int ntail = rem * sh;
 	const int RW = icgn2d_ref_w(rx), RH = icgn2d_ref_h(ry);
 	const int TW = icgn2d_tar_w(rx), TH = icgn2d_tar_h(ry);
-	float* slab = smem + (size_t)warp * icgn2d_warp_floats(rx, ry);
+	float* slab = smem + (size_t)warp * icgn2d_warp_floats(rx, ry, LM);
 	uint64_t* bar = (uint64_t*)slab;
 	float* T = slab + 32;
 	float* sC = T + icgn2d_tile_floats(rx, ry); // per-sample constants, interleaved {R, gx, gy} (12-byte lane stride: conflict-free)
+	float* sH = sC + round_up32(3 * N);         // LM only: the undamped Hessian, packed lower triangle
 	uint32_t bar_phase = 0;
 	if (use_tma) {
 		if (lane == 0) mbar_init(bar, 1);
@@ -413,7 +419,16 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 						if (l <= k) H[k * (k + 1) / 2 + l] = phi_c(i) * phi_c(j) * M[pair_idx(a, b)][mono(phi_p(i) + phi_p(j), phi_q(i) + phi_q(j))];
 					}
 			}
-		cholesky_packed<NP>(H);
+		if constexpr (LM) {
+			if (lane == 0) {
+#pragma unroll
+				for (int k = 0; k < NH; k++) sH[k] = H[k];
+			}
+			__syncwarp();
+		} else {
+			cholesky_packed<NP>(H);
+		}
+		float lm_cur = 0.f, znssd0 = 4.f; // src/oc_iclm.cpp:234-235
 
 		// ---------------- stage the target tile over the reference tile ----------------
 		__syncwarp();
@@ -552,7 +567,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					pc += 3 * sw;
 					yl += 1.f;
 				}
-				if (tmin < neg_limit) invalid = true;
+				if (!LM && tmin < neg_limit) invalid = true;
 			} else {
 				for (int r = 0; r < sh; r++) {
 					const float yl = (float)(r - ry) - oy;
@@ -567,11 +582,11 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					if (lane_on) {
 						const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
 						const bool ok = fast || ((X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax)); // NaN fails
-						if (!ok) {
+						if (!ok && !LM) {
 							invalid = true;
 						} else {
-							const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast);
-							if (t < neg_limit) invalid = true;
+							const float t = ok ? bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast) : -1.f; // BicubicBspline::compute returns -1 outside
+							if (!LM && t < neg_limit) invalid = true;
 							const float* pc = sC + 3 * (r * sw + lane);
 							const float R = pc[0];
 							const float d = t - R;
@@ -617,11 +632,11 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				}
 				const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi);
 				const bool ok = fast || ((X >= 1.f) && (Y >= 1.f) && (X < xmax) && (Y < ymax));
-				if (!ok) {
+				if (!ok && !LM) {
 					invalid = true;
 				} else {
-					const float t = bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast);
-					if (t < neg_limit) invalid = true;
+					const float t = ok ? bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast) : -1.f;
+					if (!LM && t < neg_limit) invalid = true;
 					const float* pc = sC + 3 * (r * sw + c);
 					const float R = pc[0];
 					const float d = t - R;
@@ -656,6 +671,19 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			float b[NP];
 #pragma unroll
 			for (int k = 0; k < NP; k++) b[k] = factor * (SF[k] + SD[k] - dbar * S[k]) - SF[k];
+			bool accept = true;
+			if constexpr (LM) {
+				const float znssd = 2.f - 2.f * zncc;
+				if (iteration == 1) lm_cur = powf(lm_lambda, znssd / znssd0) - 1.f; // src/oc_iclm.cpp:258-263
+#pragma unroll
+				for (int k = 0; k < NH; k++) H[k] = sH[k];
+#pragma unroll
+				for (int k = 0; k < NP; k++) H[k * (k + 1) / 2 + k] += lm_cur; // hessian + lambda * I, :266
+				cholesky_packed<NP>(H);
+				accept = znssd < znssd0; // :292-310
+				if (accept) { lm_cur *= lm_alpha; znssd0 = znssd; }
+				else lm_cur *= lm_beta;
+			}
 			cholesky_solve<NP>(H, b, dp);
 			if constexpr (NP == 6) {
 				// W <- W * W(dp)^-1, 3x3 affine (src/oc_icgn.cpp:290)
@@ -666,14 +694,16 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				const float i10 = -d * id, i11 = (1.f + a) * id, i12 = (cc * d - (1.f + a) * ff) * id;
 				const float n00 = A[0] * i00 + A[1] * i10, n01 = A[0] * i01 + A[1] * i11, n02 = A[0] * i02 + A[1] * i12 + A[2];
 				const float n10 = A[3] * i00 + A[4] * i10, n11 = A[3] * i01 + A[4] * i11, n12 = A[3] * i02 + A[4] * i12 + A[5];
-				A[0] = n00; A[1] = n01; A[2] = n02; A[3] = n10; A[4] = n11; A[5] = n12;
+				if (accept) { A[0] = n00; A[1] = n01; A[2] = n02; A[3] = n10; A[4] = n11; A[5] = n12; }
 				const float rx2 = (float)(rx * rx), ry2 = (float)(ry * ry);
 				dp_norm = dp[0] * dp[0] + dp[1] * dp[1] * rx2 + dp[2] * dp[2] * ry2
 					+ dp[3] * dp[3] + dp[4] * dp[4] * rx2 + dp[5] * dp[5] * ry2; // src/oc_icgn.cpp:296-306
 			} else {
-				float Mw[30];
-				warp2d2_matrix(dp, Mw);
-				right_divide_2x6(A, Mw); // rows 3,4 of W * W(dp)^-1 (src/oc_icgn.cpp:831)
+				if (accept) {
+					float Mw[30];
+					warp2d2_matrix(dp, Mw);
+					right_divide_2x6(A, Mw); // rows 3,4 of W * W(dp)^-1 (src/oc_icgn.cpp:831)
+				}
 				const int rx2 = rx * rx, ry2 = ry * ry;
 				const float rxy2 = (float)(rx2 * ry2);
 				const float rx4 = (float)(int)((float)(rx2 * rx2) * 0.25f); // float->int truncation, src/oc_icgn.cpp:840-841
@@ -728,8 +758,9 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 // Returns 0, -1 when one warp's slab does not fit in shared memory, -2 on a CUDA error.
 // d_counter: one int of device memory owned by the context (work queue head).
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
-	size_t smem_optin, int* d_counter, const float* d_center_offsets, cudaStream_t stream, cudaError_t* err) {
-	const size_t per_warp = (size_t)icgn2d_warp_floats(rx, ry) * sizeof(float);
+	size_t smem_optin, int* d_counter, const float* d_center_offsets, const float* lm_damping, cudaStream_t stream, cudaError_t* err) {
+	const bool lm = lm_damping != nullptr;
+	const size_t per_warp = (size_t)icgn2d_warp_floats(rx, ry, lm) * sizeof(float);
 	int best_wpb = 0, best_warps = 0;
 	for (int wpb = 4; wpb >= 1; wpb >>= 1) {
 		size_t need = per_warp * wpb;
@@ -747,9 +778,10 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	const int dims[2] = { img.w, img.h };
 	const int box_ref[2] = { icgn2d_ref_w(rx), icgn2d_ref_h(ry) }, box_tar[2] = { icgn2d_tar_w(rx), icgn2d_tar_h(ry) };
 	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm_ref, img.ref, 2, dims, box_ref) && tma_make_map(&tm_tar, img.tar, 2, dims, box_tar);
-	void (*kern)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int, const float*);
-	if (np == 6) kern = (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16> : icgn2d_kernel<6, 0>;
-	else kern = (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20> : icgn2d_kernel<12, 0>;
+	void (*kern)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int, const float*, float, float, float);
+	if (lm) kern = (np == 6) ? icgn2d_kernel<6, 0, true> : icgn2d_kernel<12, 0, true>;
+	else if (np == 6) kern = (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16, false> : icgn2d_kernel<6, 0, false>;
+	else kern = (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20, false> : icgn2d_kernel<12, 0, false>;
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
 	*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
@@ -758,7 +790,8 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	long long resident = (long long)sm_count * (best_warps / best_wpb);
 	int grid = (int)(blocks_needed < resident ? blocks_needed : resident); // persistent: one wave
 	if (grid < 1) grid = 1;
-	kern<<<grid, best_wpb * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, d_counter, tm_ref, tm_tar, use_tma, d_center_offsets);
+	kern<<<grid, best_wpb * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, d_counter, tm_ref, tm_tar, use_tma, d_center_offsets,
+		lm ? lm_damping[0] : 0.f, lm ? lm_damping[1] : 0.f, lm ? lm_damping[2] : 0.f);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;
 }

@@ -474,7 +474,8 @@ int ocb_icgn2d_prepare(ocb_ctx* ctx) {
 	return OCB_OK;
 }
 
-static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, const float* d_offsets = nullptr) {
+static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, const float* d_offsets = nullptr,
+	const float* lm_damping = nullptr) {
 	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "icgn2d: images not set");
 	if (!ctx->prepared2) return set_error(ctx, OCB_ERR_STATE, "icgn2d: prepare() has not been called since setImages()");
@@ -482,7 +483,8 @@ static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int
 	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "icgn2d: too many POIs in one call");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	cudaError_t err = cudaSuccess;
-	int rc = ocb::icgn2d_launch(np, ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->d_counter, d_offsets, ctx->stream, &err);
+	int rc = ocb::icgn2d_launch(np, ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->d_counter, d_offsets, lm_damping,
+		ctx->stream, &err);
 	if (rc == -1) return set_error(ctx, OCB_ERR_UNSUPPORTED, "icgn2d: subset radius (%d,%d) exceeds the shared-memory design limit", rx, ry);
 	if (rc) return set_error(ctx, OCB_ERR_CUDA, "icgn2d launch failed: %s", cudaGetErrorString(err));
 	ctx->launches++;
@@ -569,6 +571,25 @@ int ocb_icgn2d_ex(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry
 		for (size_t k = 0; k < idx.size(); k++) memcpy(q + idx[k] * OCB_POI2D_FLOATS, &gq[k * OCB_POI2D_FLOATS], OCB_POI2D_FLOATS * sizeof(float));
 	}
 	return OCB_OK;
+}
+
+// ---- ICLM ----------------------------------------------------------------
+int ocb_iclm2d_dev(ocb_ctx* ctx, int order, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, float lambda, float alpha, float beta) {
+	if (order != 1 && order != 2) return set_error(ctx, OCB_ERR_ARG, "iclm2d: order must be 1 or 2");
+	const float damping[3] = { lambda, alpha, beta };
+	return icgn2d_dev(ctx, order == 1 ? 6 : 12, d_poi2d, n, rx, ry, conv, stop, nullptr, damping);
+}
+
+int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, float lambda, float alpha, float beta) {
+	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "iclm2d: bad arguments");
+	if (order != 1 && order != 2) return set_error(ctx, OCB_ERR_ARG, "iclm2d: order must be 1 or 2");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
+	if ((rc = ocb_iclm2d_dev(ctx, order, ctx->d_poi, n, rx, ry, conv, stop, lambda, alpha, beta))) return rc;
+	return unstage_pois(ctx, poi2d, bytes);
 }
 
 int ocb_icgn3d_prepare(ocb_ctx* ctx) {

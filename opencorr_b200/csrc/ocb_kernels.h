@@ -34,7 +34,7 @@ inline bool fft_plan_axis(int n, FftAxis* ax) {
 
 // icgn2d.cu
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
-	size_t smem_optin, int* d_counter, const float* d_center_offsets, cudaStream_t stream, cudaError_t* err);
+	size_t smem_optin, int* d_counter, const float* d_center_offsets, const float* lm_damping, cudaStream_t stream, cudaError_t* err);
 // fftcc.cu
 size_t fftcc2d_smem_bytes(int rx, int ry);
 int fftcc2d_launch(const Image2D& img, float* d_pois, size_t n, int rx, int ry, const FftAxis& ax, const FftAxis& ay,

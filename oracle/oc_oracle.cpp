@@ -471,12 +471,17 @@ struct Scratch2D {
 };
 
 // ICGN2D1::compute(POI2D*) src/oc_icgn.cpp:144-341 (NP=6) and ICGN2D2::compute(POI2D*) :685-898 (NP=12).
+// (template header follows the comment block below)
 // With a centre offset (off_x, off_y) this is compute(POI2D*, Point2D& center_offset), :353-547 / :910-1126:
 // local coordinates become (int - offset) and the target subset is centred at poi + offset.
 // self_adaptive: the radius comes from the POI record (:152-158).
+// damping != nullptr selects the Levenberg-Marquardt siblings ICLM2D1::compute (src/oc_iclm.cpp:150-358)
+// and ICLM2D2::compute (:502-730): damping = {lambda, alpha, beta} (oc_iclm.h:32-37); the Hessian is damped
+// with current_lambda * I and re-inverted every iteration, a step is accepted only if ZNSSD decreased, and
+// -- unlike IC-GN -- out-of-range samples (-1) are NOT rejected.
 template <class T, int NP>
 void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion, float stop_condition, Scratch2D<T>& s,
-	float off_x = 0.f, float off_y = 0.f, bool self_adaptive = false) {
+	float off_x = 0.f, float off_y = 0.f, bool self_adaptive = false, const float* damping = nullptr) {
 	float px = poi[P2_X], py = poi[P2_Y];
 	float* def = poi + P2_DEF;
 	if (self_adaptive) {
@@ -531,7 +536,8 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 				}
 		}
 	T invH[NP * NP];
-	inverse_lu<T, NP>(H, invH);
+	if (!damping) inverse_lu<T, NP>(H, invH);
+	T current_lambda = 0, znssd0 = 4; // src/oc_iclm.cpp:234-235
 
 	// initial guess: first-order terms only, also for ICGN2D2 (:216, :765-770)
 	float p_init_u = def[D2_U], p_init_v = def[D2_V];
@@ -570,7 +576,7 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 				if (val < 0) any_negative = true;
 				s.tar[r * sw + col] = val;
 			}
-		if (any_negative) { // :251-255
+		if (any_negative && !damping) { // :251-255 (the ICLM siblings have no such test)
 			poi[P2_ZNCC] = -3.f;
 			return;
 		}
@@ -588,15 +594,28 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 		for (int i = 0; i < NP; i++) num[i] = 0;
 		for (int i = 0; i < n; i++)
 			for (int k = 0; k < NP; k++) num[k] += s.sd[(size_t)i * NP + k] * s.err[i];
+		bool accept = true;
+		if (damping) { // src/oc_iclm.cpp:258-266, :292-310
+			if (iteration_counter == 1) current_lambda = (T)(std::pow((T)damping[0], znssd / znssd0) - (T)1);
+			T Hd[NP * NP];
+			for (int i = 0; i < NP * NP; i++) Hd[i] = H[i];
+			for (int i = 0; i < NP; i++) Hd[i * NP + i] += current_lambda;
+			inverse_lu<T, NP>(Hd, invH);
+		}
 		for (int i = 0; i < NP; i++) {
 			dp[i] = 0;
 			for (int j = 0; j < NP; j++) dp[i] += invH[i * NP + j] * num[j];
+		}
+		if (damping) {
+			accept = znssd < znssd0;
+			if (accept) { current_lambda = current_lambda * (T)damping[1]; znssd0 = znssd; }
+			else current_lambda = current_lambda * (T)damping[2];
 		}
 		if (NP == 6) {
 			warp2d1_set(dp, Winc);
 			inverse3<T>(Winc, Winv);
 			matmul<T, 3>(W, Winv, Wnew);
-			for (int i = 0; i < 9; i++) W[i] = Wnew[i];
+			if (accept) for (int i = 0; i < 9; i++) W[i] = Wnew[i];
 			warp2d1_get(W, pcur);
 			int rx2 = rx * rx, ry2 = ry * ry;
 			dp_norm_max = dp[0] * dp[0] + dp[1] * dp[1] * rx2 + dp[2] * dp[2] * ry2
@@ -605,7 +624,7 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 			warp2d2_set(dp, Winc);
 			inverse_lu<T, WN>(Winc, Winv);
 			matmul<T, WN>(W, Winv, Wnew);
-			for (int i = 0; i < WN * WN; i++) W[i] = Wnew[i];
+			if (accept) for (int i = 0; i < WN * WN; i++) W[i] = Wnew[i];
 			warp2d2_get(W, pcur);
 			int rx2 = rx * rx, ry2 = ry * ry, rxy2 = rx2 * ry2;
 			int rx4 = rx2 * rx2 * 0.25f, ry4 = ry2 * ry2 * 0.25f; // float->int truncation, :840-841
@@ -966,13 +985,14 @@ void run_fftcc2d(const Ctx2D& c, float* pois, long n, int rx, int ry) {
 	}
 }
 template <class T, int NP>
-void run_icgn2d(const Ctx2D& c, float* pois, long n, int rx, int ry, float conv, float stop, const float* offsets = nullptr, bool self_adaptive = false) {
+void run_icgn2d(const Ctx2D& c, float* pois, long n, int rx, int ry, float conv, float stop, const float* offsets = nullptr, bool self_adaptive = false,
+	const float* damping = nullptr) {
 #pragma omp parallel num_threads(c.threads)
 	{
 		Scratch2D<T> s;
 #pragma omp for schedule(dynamic, 64)
 		for (long i = 0; i < n; i++)
-			icgn2d_poi<T, NP>(c, pois + i * P2_N, rx, ry, conv, stop, s, offsets ? offsets[2 * i] : 0.f, offsets ? offsets[2 * i + 1] : 0.f, self_adaptive);
+			icgn2d_poi<T, NP>(c, pois + i * P2_N, rx, ry, conv, stop, s, offsets ? offsets[2 * i] : 0.f, offsets ? offsets[2 * i + 1] : 0.f, self_adaptive, damping);
 	}
 }
 template <class T>
@@ -1056,6 +1076,20 @@ int oco_icgn2d_ex(void* h, int order, float* pois, long n, int rx, int ry, float
 	} else {
 		if (exact) run_icgn2d<double, 12>(*c, pois, n, rx, ry, conv, stop, offsets, self_adaptive != 0);
 		else run_icgn2d<float, 12>(*c, pois, n, rx, ry, conv, stop, offsets, self_adaptive != 0);
+	}
+	return 0;
+}
+
+// ICLM2D1::compute(queue) src/oc_iclm.cpp:360-368, ICLM2D2::compute(queue) :732-740; damping = {lambda, alpha, beta}
+int oco_iclm2d(void* h, int order, float* pois, long n, int rx, int ry, float conv, float stop, const float* damping, int exact) {
+	Ctx2D* c = (Ctx2D*)h;
+	if (!c->prepared || !damping) return -1;
+	if (order == 1) {
+		if (exact) run_icgn2d<double, 6>(*c, pois, n, rx, ry, conv, stop, nullptr, false, damping);
+		else run_icgn2d<float, 6>(*c, pois, n, rx, ry, conv, stop, nullptr, false, damping);
+	} else {
+		if (exact) run_icgn2d<double, 12>(*c, pois, n, rx, ry, conv, stop, nullptr, false, damping);
+		else run_icgn2d<float, 12>(*c, pois, n, rx, ry, conv, stop, nullptr, false, damping);
 	}
 	return 0;
 }

@@ -47,6 +47,9 @@ def lib():
         L.oco_icgn2d_ex.restype = ctypes.c_int
         L.oco_icgn2d_ex.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_float, ctypes.c_float, _f32p, ctypes.c_int, ctypes.c_int]
+        L.oco_iclm2d.restype = ctypes.c_int
+        L.oco_iclm2d.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_float, ctypes.c_float, _f32p, ctypes.c_int]
         L.oco_create3d.restype = ctypes.c_void_p
         L.oco_create3d.argtypes = [_f32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.oco_destroy3d.argtypes = [ctypes.c_void_p]
@@ -143,6 +146,17 @@ class Oracle2D:
             assert off.shape[0] == pois.shape[0]
         rc = lib().oco_icgn2d_ex(self._h, order, _p(pois), pois.shape[0], rx, ry, conv, stop,
                                  _p(off) if off is not None else None, int(self_adaptive), int(exact))
+        assert rc == 0
+        return pois
+
+
+    def iclm2d(self, order, pois, rx, ry, conv=0.001, stop=10, damping=(100.0, 0.1, 10.0), exact=False):
+        """ICLM2D1 / ICLM2D2 (inverse-compositional Levenberg-Marquardt), reference src/oc_iclm.cpp."""
+        assert pois.dtype == np.float32 and pois.flags.c_contiguous and pois.shape[1] == 25
+        if not self._prepared:
+            self.prepare()
+        d = _c32(damping).reshape(3)
+        rc = lib().oco_iclm2d(self._h, order, _p(pois), pois.shape[0], rx, ry, conv, stop, _p(d), int(exact))
         assert rc == 0
         return pois
 

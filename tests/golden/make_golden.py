@@ -7,6 +7,7 @@ fixtures, examples/2d_dic and examples/dvc); no reference source code.
 Outputs
   oht_cfrp_0.bmp, oht_cfrp_4.bmp    the 2D example pair (280x900, 8-bit), verbatim
   oht_cfrp_4_fftcc_icgn1_r16.npz    every 23rd row of the shipped result table + deformation table
+  oht_cfrp_4_fftcc_iclm1_r16.npz    the same rows of the shipped ICLM2D1 table
   al_foam4_crop.npz                 z-slices [18,118) of the DVC example pair as uint8 (values are
                                     integral, 52..202) + the shipped CPU and GPU result rows of the
                                     196 POIs with z in {60,65,70,75}.  The 15-tap prefilter and the
@@ -32,6 +33,11 @@ def main():
                         columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence".split(",")),
                         table=tab[sel, :9], deformation_columns=np.array("x,y,u,ux,uy,v,vx,vy".split(",")),
                         deformation=dtab[sel, :8], rows=sel)
+
+    # ICLM2D1 table shipped by the reference (examples/2d_dic/oht_cfrp_4_fftcc_iclm1_r16.csv, same POIs)
+    itab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_fftcc_iclm1_r16.csv"), delimiter=",", skip_header=1)
+    np.savez_compressed(os.path.join(OUT, "oht_cfrp_4_fftcc_iclm1_r16.npz"),
+                        columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence".split(",")), table=itab[sel, :9], rows=sel)
 
     def load(p):
         d = np.fromfile(p, dtype=np.int32, count=3)

@@ -62,3 +62,24 @@ def test_shim_demo(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     _, tab = _read_table(out_csv)
     assert tab.shape[0] > 1000 and (tab[:, 6] > 0.9).mean() > 0.9
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "test_2d_dic_fftcc_iclm1")), reason="example binary not built")
+def test_reference_2d_iclm_example_runs_unchanged(tmp_path):
+    """examples/test_2d_dic_fftcc_iclm1.cpp of the reference, compiled unchanged against the shim."""
+    data = tmp_path / "d:" / "dic_tests" / "2d_dic"
+    data.mkdir(parents=True)
+    for name in ("oht_cfrp_0.bmp", "oht_cfrp_4.bmp"):
+        shutil.copyfile(os.path.join(util.GOLDEN, name), data / name)
+    out = subprocess.run([os.path.join(BIN, "test_2d_dic_fftcc_iclm1")], cwd=tmp_path, stdin=subprocess.DEVNULL,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    _, tab = _read_table(data / "oht_cfrp_4_fftcc_iclm1_r16.csv")
+    g = util.oht_cfrp_iclm_golden()
+    gold, rows = g["table"], g["rows"]
+    mine = tab[rows]
+    same = (mine[:, 4] == gold[:, 4]) & (mine[:, 5] == gold[:, 5])
+    ok = same & (gold[:, 6] >= 0) & (mine[:, 7] == gold[:, 7])
+    assert ok.sum() > 0.9 * len(gold)
+    d = np.abs(mine[ok][:, 2:4] - gold[ok][:, 2:4]).max(1)
+    assert np.percentile(d, 98) < 1e-4 and d.max() < 1.5e-3

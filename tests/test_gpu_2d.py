@@ -370,3 +370,62 @@ def test_u8_image_upload_gives_identical_results(engine):
         icgn.compute(q)
         res.append(q)
     assert np.array_equal(res[0], res[1])
+
+
+def _iclm_compare(q_gpu, q_cpu, label):
+    """ICLM parity: sentinel codes, guesses and iteration counts as for IC-GN; displacements within 1e-4 px
+    for >= 98 % of the POIs and within conv (1e-3 px) for all -- at convergence the accept/reject test of the
+    last step (`znssd < znssd0`, src/oc_iclm.cpp:292) is decided by rounding (see test_oracle_golden)."""
+    assert np.array_equal(q_gpu[:, 14:16], q_cpu[:, 14:16])
+    neg = (q_gpu[:, 16] < 0) | (q_cpu[:, 16] < 0)
+    it_same = q_gpu[:, 17] == q_cpu[:, 17]
+    assert it_same.mean() > 0.95, label
+    assert np.array_equal(q_gpu[neg & it_same, 16], q_cpu[neg & it_same, 16]), label
+    ok = ~neg & it_same
+    d = np.abs(q_gpu[ok][:, [2, 8]] - q_cpu[ok][:, [2, 8]]).max(1)
+    assert (d < 1e-4).mean() >= 0.98, (label, float((d < 1e-4).mean()))
+    assert d.max() < 1.5e-3, (label, float(d.max()))
+    assert np.abs(q_gpu[ok, 16] - q_cpu[ok, 16]).max() < 1e-5, label
+
+
+@pytest.mark.parametrize("order,second", [(1, False), (2, True)])
+def test_iclm2d_matches_oracle(engine, order, second):
+    ref, tar = synth.speckle_pair_2d(512, 512, second_order=second)
+    xy = synth.grid_2d(64, 64, 16, 12, 24, 31)
+    q = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, 16, 16)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    iclm = (ob.ICLM2D1 if order == 1 else ob.ICLM2D2)(16, 16, 0.001, 10, engine=engine)
+    iclm.set_images(ref, tar)
+    iclm.prepare()
+    iclm.compute(q_gpu)
+    o.iclm2d(order, q_cpu, 16, 16, 0.001, 10)
+    _iclm_compare(q_gpu, q_cpu, "iclm order %d" % order)
+    # non-default damping
+    q_gpu, q_cpu = q.copy(), q.copy()
+    iclm.set_damping(10.0, 0.5, 4.0)
+    iclm.compute(q_gpu)
+    o.iclm2d(order, q_cpu, 16, 16, 0.001, 10, damping=(10.0, 0.5, 4.0))
+    _iclm_compare(q_gpu, q_cpu, "iclm order %d damping" % order)
+
+
+def test_iclm2d1_golden_table(engine):
+    """FFTCC2D -> ICLM2D1 vs the reference's shipped examples/2d_dic/oht_cfrp_4_fftcc_iclm1_r16.csv."""
+    ref, tar = util.oht_cfrp_pair()
+    tab = util.oht_cfrp_iclm_golden()["table"]
+    q = ob.make_poi2d(tab[:, 0:2])
+    f = ob.FFTCC2D(16, 16, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q)
+    iclm = ob.ICLM2D1(16, 16, 0.001, 10, engine=engine)
+    iclm.set_images(ref, tar)
+    iclm.prepare()
+    iclm.compute(q)
+    same = (q[:, 14] == tab[:, 4]) & (q[:, 15] == tab[:, 5])
+    assert same.mean() > 0.998
+    ok = same & (tab[:, 6] >= 0) & (q[:, 17] == tab[:, 7])
+    assert ok.sum() > 0.9 * len(tab)
+    d = np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max(1)
+    assert np.percentile(d, 98) < 1e-4 and d.max() < 1.5e-3
+    assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 1e-5

@@ -77,3 +77,7 @@ def compare_3d(a, b, label="", tol_disp=1e-4, tol_zncc=1e-5, max_iter_mismatch_f
     assert d <= tol_disp, "%s max |du,dv,dw| = %.3g > %.3g" % (label, d, tol_disp)
     assert dz <= tol_zncc, "%s max |dZNCC| = %.3g > %.3g" % (label, dz, tol_zncc)
     return dict(n=len(a), n_compared=int(ok.sum()), iter_mismatch_frac=float(frac), max_disp=float(d), max_zncc=float(dz))
+
+
+def oht_cfrp_iclm_golden():
+    return np.load(os.path.join(GOLDEN, "oht_cfrp_4_fftcc_iclm1_r16.npz"))
