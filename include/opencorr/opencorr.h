@@ -342,6 +342,7 @@ namespace opencorr
 			const void* tar_key = nullptr;
 			unsigned long long ref_gen = 0, tar_gen = 0;
 			bool prepared = false;
+			bool prepared_nr = false;
 
 			static Engine& get()
 			{
@@ -374,6 +375,7 @@ namespace opencorr
 				check(ocb_set_images_2d(context(), ref->eg_mat.data.data(), tar->eg_mat.data.data(), ref->width, ref->height, 0));
 				ref_key = ref; tar_key = tar; ref_gen = ref->generation; tar_gen = tar->generation;
 				prepared = false;
+				prepared_nr = false;
 			}
 			void useImages(Image3D* ref, Image3D* tar)
 			{
@@ -383,6 +385,7 @@ namespace opencorr
 				check(ocb_set_images_3d(context(), **ref->vol_mat, **tar->vol_mat, ref->dim_x, ref->dim_y, ref->dim_z));
 				ref_key = ref; tar_key = tar; ref_gen = ref->generation; tar_gen = tar->generation;
 				prepared = false;
+				prepared_nr = false;
 			}
 		};
 	} // namespace b200
@@ -640,6 +643,124 @@ namespace opencorr
 			: b200::ICLM2D<2>(subset_radius_x, subset_radius_y, conv_criterion, stop_condition, thread_number) {}
 	};
 
+	// Strain (reference src/oc_strain.h:33-70, src/oc_strain.cpp): least-squares plane fit of the displacement field
+	// over each POI's neighbourhood.  prepare() builds kd-trees in the reference; here the spatial binning is part of
+	// the GPU call, so prepare() is empty.  The stereo (POI2DS) overloads are out of scope.
+	class Strain
+	{
+	protected:
+		float subregion_radius;
+		int neighbor_number_min;
+		float zncc_threshold;
+		int description;
+		int approximation;
+		int thread_number;
+
+	public:
+		Strain(float subregion_radius, int neighbor_number_min, int thread_number)
+		{
+			this->subregion_radius = subregion_radius;
+			this->neighbor_number_min = neighbor_number_min;
+			zncc_threshold = 0.9f; // src/oc_strain.cpp:38-40
+			description = 1;
+			approximation = 1;
+			this->thread_number = thread_number;
+		}
+		~Strain() {}
+		float getSubregionRadius() const { return subregion_radius; }
+		int getNeighborMin() const { return neighbor_number_min; }
+		float getZnccThreshold() const { return zncc_threshold; }
+		void setSubregionRadius(float subregion_radius) { this->subregion_radius = subregion_radius; }
+		void setNeighborMin(int neighbor_number_min) { this->neighbor_number_min = neighbor_number_min; }
+		void setZnccThreshold(float zncc_threshold) { this->zncc_threshold = zncc_threshold; }
+		void setDescription(int description) { this->description = description; }
+		void setApproximation(int approximation) { this->approximation = approximation; }
+
+		void prepare(std::vector<POI2D>&) {}
+		void prepare(std::vector<POI3D>&) {}
+
+		void compute(std::vector<POI2D>& poi_queue)
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.check(ocb_strain2d(e.context(), poi_queue.data(), poi_queue.size(), subregion_radius, neighbor_number_min, zncc_threshold, approximation));
+		}
+		void compute(std::vector<POI3D>& poi_queue)
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.check(ocb_strain3d(e.context(), poi_queue.data(), poi_queue.size(), subregion_radius, neighbor_number_min, zncc_threshold, approximation));
+		}
+		// single-POI overloads (src/oc_strain.cpp:158-237, :373-474); `poi` must be an element of `poi_queue`
+		// (the reference searches the tree built from the queue by prepare()).  One POI per call is a poor fit for a
+		// GPU: prefer the queue overloads.
+		void compute(POI2D* poi, std::vector<POI2D>& poi_queue)
+		{
+			if (poi < poi_queue.data() || poi >= poi_queue.data() + poi_queue.size()) throw std::string("opencorr_b200: Strain::compute(poi, queue) needs poi inside queue");
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.check(ocb_strain2d_single(e.context(), poi_queue.data(), poi_queue.size(), (size_t)(poi - poi_queue.data()), subregion_radius, neighbor_number_min,
+				zncc_threshold, approximation));
+		}
+		void compute(POI3D* poi, std::vector<POI3D>& poi_queue)
+		{
+			if (poi < poi_queue.data() || poi >= poi_queue.data() + poi_queue.size()) throw std::string("opencorr_b200: Strain::compute(poi, queue) needs poi inside queue");
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.check(ocb_strain3d_single(e.context(), poi_queue.data(), poi_queue.size(), (size_t)(poi - poi_queue.data()), subregion_radius, neighbor_number_min,
+				zncc_threshold, approximation));
+		}
+	};
+
+	// NR2D1 (forward-additive Newton-Raphson), reference src/oc_nr.h:46-71, src/oc_nr.cpp:66-334
+	class NR2D1 : public DIC
+	{
+	private:
+		float conv_criterion;
+		float stop_condition;
+
+	public:
+		NR2D1(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
+		{
+			this->subset_radius_x = subset_radius_x;
+			this->subset_radius_y = subset_radius_y;
+			this->conv_criterion = conv_criterion;
+			this->stop_condition = stop_condition;
+			this->thread_number = thread_number;
+		}
+		~NR2D1() {}
+		void setIteration(float conv_criterion, float stop_condition)
+		{
+			this->conv_criterion = conv_criterion;
+			this->stop_condition = stop_condition;
+		}
+		void setIteration(POI2D* poi) // src/oc_nr.cpp:113-117
+		{
+			conv_criterion = poi->result.convergence;
+			stop_condition = (float)(int)poi->result.iteration;
+		}
+		void prepare()
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.useImages(ref_img, tar_img);
+			e.check(ocb_nr2d_prepare(e.context()));
+			e.prepared_nr = true;
+		}
+		void compute(POI2D* poi) { run(poi, 1); }
+		void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+
+	private:
+		void run(POI2D* p, size_t n)
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.useImages(ref_img, tar_img);
+			if (!e.prepared_nr) throw std::string("opencorr_b200: prepare() must be called before compute()");
+			e.check(ocb_nr2d1(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
+		}
+	};
+
 	class ICGN3D1 : public DVC
 	{
 	private:
@@ -736,6 +857,37 @@ namespace opencorr
 		w_x = 22, w_y = 23, w_z = 24,
 	};
 
+	namespace b200
+	{
+		// Reads the numeric rows of a delimiter-separated table written by saveTable2D/saveTable3D (header line skipped;
+		// empty fields skipped like the reference's loaders, src/oc_io.cpp:264-283).  Rows shorter than `min_cols` are
+		// padded with zeros: the result tables shipped with the reference predate the subset_rx/ry(/rz) columns.
+		inline std::vector<std::vector<float>> readTable(const std::string& file_path, const std::string& delimiter, size_t min_cols)
+		{
+			std::ifstream file_in(file_path);
+			if (!file_in.is_open()) throw std::string("failed to open csv file " + file_path);
+			std::vector<std::vector<float>> rows;
+			std::string line;
+			std::getline(file_in, line);
+			while (std::getline(file_in, line)) {
+				if (!line.empty() && line.back() == '\r') line.pop_back();
+				std::vector<float> key_buffer;
+				size_t position1 = 0, position2 = 0;
+				do {
+					position2 = line.find(delimiter, position1);
+					if (position2 == std::string::npos) position2 = line.length();
+					const std::string variable = line.substr(position1, position2 - position1);
+					if (!variable.empty()) key_buffer.push_back(std::stof(variable));
+					position1 = position2 + delimiter.length();
+				} while (position2 < line.length() && position1 < line.length());
+				if (key_buffer.empty()) continue;
+				if (key_buffer.size() < min_cols) key_buffer.resize(min_cols, 0.f);
+				rows.push_back(std::move(key_buffer));
+			}
+			return rows;
+		}
+	} // namespace b200
+
 	class IO2D
 	{
 	private:
@@ -756,6 +908,22 @@ namespace opencorr
 		void setWidth(int width) { this->width = width; }
 		void setHeight(int height) { this->height = height; }
 
+		// src/oc_io.cpp:249-316
+		std::vector<POI2D> loadTable2D()
+		{
+			std::vector<POI2D> poi_queue;
+			for (const std::vector<float>& k : b200::readTable(file_path, delimiter, 15)) {
+				POI2D poi(k[0], k[1]);
+				poi.deformation.u = k[2];
+				poi.deformation.v = k[3];
+				for (int i = 0; i < 6; i++) poi.result.r[i] = k[4 + i];
+				for (int i = 0; i < 3; i++) poi.strain.e[i] = k[10 + i];
+				poi.subset_radius.x = k[13];
+				poi.subset_radius.y = k[14];
+				poi_queue.push_back(poi);
+			}
+			return poi_queue;
+		}
 		// src/oc_io.cpp:318-373
 		void saveTable2D(std::vector<POI2D>& poi_queue)
 		{
@@ -839,6 +1007,27 @@ namespace opencorr
 		void setDimY(int dim_y) { this->dim_y = dim_y; }
 		void setDimZ(int dim_z) { this->dim_z = dim_z; }
 
+		// src/oc_io.cpp:920-1002
+		std::vector<POI3D> loadTable3D()
+		{
+			std::vector<POI3D> poi_queue;
+			for (const std::vector<float>& k : b200::readTable(file_path, delimiter, 31)) {
+				POI3D poi(k[0], k[1], k[2]);
+				poi.deformation.u = k[3];
+				poi.deformation.v = k[4];
+				poi.deformation.w = k[5];
+				for (int i = 0; i < 7; i++) poi.result.r[i] = k[6 + i];
+				poi.deformation.ux = k[13]; poi.deformation.uy = k[14]; poi.deformation.uz = k[15];
+				poi.deformation.vx = k[16]; poi.deformation.vy = k[17]; poi.deformation.vz = k[18];
+				poi.deformation.wx = k[19]; poi.deformation.wy = k[20]; poi.deformation.wz = k[21];
+				for (int i = 0; i < 6; i++) poi.strain.e[i] = k[22 + i];
+				poi.subset_radius.x = k[28];
+				poi.subset_radius.y = k[29];
+				poi.subset_radius.z = k[30];
+				poi_queue.push_back(poi);
+			}
+			return poi_queue;
+		}
 		// src/oc_io.cpp:1004-1089
 		void saveTable3D(std::vector<POI3D>& poi_queue)
 		{

@@ -126,6 +126,27 @@ int ocb_icgn2d_ex_dev(ocb_ctx* ctx, int order, void* d_poi2d, size_t n, int rx, 
 int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, float lambda, float alpha, float beta);
 int ocb_iclm2d_dev(ocb_ctx* ctx, int order, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, float lambda, float alpha, float beta);
 
+/* ---- NR2D1, forward-additive Newton-Raphson: NR2D1::prepare src/oc_nr.cpp:119-156
+ *      (nothing is precomputed here: the target gradients and the three bicubic interpolants are evaluated
+ *      on chip), NR2D1::compute(std::vector<POI2D>&) :327-334 (per POI :160-325). */
+int ocb_nr2d_prepare(ocb_ctx* ctx);
+int ocb_nr2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, float stop);
+int ocb_nr2d1_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop);
+
+/* ---- Strain post-processing of a POI queue: Strain::prepare + Strain::compute(queue),
+ *      src/oc_strain.cpp:100-111,150-156,239-250 (POI2D; per POI :158-237) and :476-487 (POI3D; per POI :373-474).
+ *      radius = subregion_radius, min_neighbors = neighbor_number_min (constructor :32-36), zncc_threshold = setZnccThreshold
+ *      (default 0.9, :38), approximation = setApproximation: 1 Cauchy (default), 2 Green.  Writes strain.exx.. of every POI
+ *      whose own ZNCC and enough neighbours' ZNCC pass the threshold; other records are left untouched.
+ *      The stereo variant (POI2DS) is out of scope. */
+int ocb_strain2d(ocb_ctx* ctx, void* poi2d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
+int ocb_strain3d(ocb_ctx* ctx, void* poi3d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
+/* Strain::compute(POI2D* poi, queue) / (POI3D* poi, queue) for the queue member `index`: fitted whatever its own ZNCC. */
+int ocb_strain2d_single(ocb_ctx* ctx, void* poi2d, size_t n, size_t index, float radius, int min_neighbors, float zncc_threshold, int approximation);
+int ocb_strain3d_single(ocb_ctx* ctx, void* poi3d, size_t n, size_t index, float radius, int min_neighbors, float zncc_threshold, int approximation);
+int ocb_strain2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
+int ocb_strain3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
+
 /* ---- inspection (parity tests of the prepare() products) ----------------------------------- */
 /* Copy the device tables built by ocb_icgn3d_prepare() to host buffers of dim_x*dim_y*dim_z
  * floats each; any pointer may be NULL. */

@@ -170,6 +170,24 @@ class Engine:
         self._ck(self._lib.ocb_iclm2d(self._ctx, int(order), _vp(q), q.shape[0], rx, ry, conv, stop,
                                       float(damping[0]), float(damping[1]), float(damping[2])))
 
+    def strain(self, q, radius, min_neighbors, zncc_threshold=0.9, approximation=1):
+        """Strain::prepare + compute(queue) (reference src/oc_strain.cpp) on a POI2D [n,25] or POI3D [n,31] queue."""
+        if q.ndim == 2 and q.shape[1] == POI3D_FLOATS:
+            _check_queue(q, POI3D_FLOATS)
+            fn = self._lib.ocb_strain3d
+        else:
+            _check_queue(q, POI2D_FLOATS)
+            fn = self._lib.ocb_strain2d
+        self._ck(fn(self._ctx, _vp(q), q.shape[0], float(radius), int(min_neighbors), float(zncc_threshold), int(approximation)))
+
+    def nr2d_prepare(self):
+        self._ck(self._lib.ocb_nr2d_prepare(self._ctx))
+
+    def nr2d1(self, q, rx, ry, conv, stop):
+        """NR2D1 (reference src/oc_nr.cpp:160-334)."""
+        _check_queue(q, POI2D_FLOATS)
+        self._ck(self._lib.ocb_nr2d1(self._ctx, _vp(q), q.shape[0], rx, ry, conv, stop))
+
     def icgn3d1(self, q, rx, ry, rz, conv, stop):
         _check_queue(q, POI3D_FLOATS)
         self._ck(self._lib.ocb_icgn3d1(self._ctx, _vp(q), q.shape[0], rx, ry, rz, conv, stop))
@@ -344,6 +362,68 @@ class ICLM2D1(_ICLM2D):
 
 class ICLM2D2(_ICLM2D):
     _order = 2
+
+
+class NR2D1(_DIC):
+    """NR2D1(int rx, int ry, float conv, float stop, int threads), reference src/oc_nr.h:46-71."""
+
+    def __init__(self, rx, ry, conv_criterion, stop_condition, thread_number=0, engine=None):
+        super().__init__(rx, ry, thread_number, engine)
+        self.conv_criterion = float(conv_criterion)
+        self.stop_condition = float(stop_condition)
+
+    def set_iteration(self, conv_criterion, stop_condition):
+        self.conv_criterion, self.stop_condition = float(conv_criterion), float(stop_condition)
+
+    def prepare(self):
+        self.engine.nr2d_prepare()
+
+    def compute(self, poi_queue):
+        self.engine.nr2d1(poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion, self.stop_condition)
+        return poi_queue
+
+    setIteration = set_iteration
+
+
+class Strain:
+    """Strain(float subregion_radius, int neighbor_number_min, int thread_number), reference src/oc_strain.h:33-70."""
+
+    def __init__(self, subregion_radius, neighbor_number_min, thread_number=0, engine=None):
+        self.engine = engine if engine is not None else default_engine()
+        self.subregion_radius = float(subregion_radius)
+        self.neighbor_number_min = int(neighbor_number_min)
+        self.zncc_threshold = 0.9  # src/oc_strain.cpp:38-40
+        self.description = 1
+        self.approximation = 1
+        self.thread_number = thread_number
+
+    def set_subregion_radius(self, r):
+        self.subregion_radius = float(r)
+
+    def set_neighbor_min(self, k):
+        self.neighbor_number_min = int(k)
+
+    def set_zncc_threshold(self, t):
+        self.zncc_threshold = float(t)
+
+    def set_description(self, d):
+        self.description = int(d)
+
+    def set_approximation(self, a):
+        self.approximation = int(a)
+
+    def prepare(self, poi_queue):
+        """The reference builds its kd-trees here; the grid binning happens inside compute()."""
+
+    def compute(self, poi_queue):
+        self.engine.strain(poi_queue, self.subregion_radius, self.neighbor_number_min, self.zncc_threshold, self.approximation)
+        return poi_queue
+
+    setSubregionRadius = set_subregion_radius
+    setNeighborMin = set_neighbor_min
+    setZnccThreshold = set_zncc_threshold
+    setDescription = set_description
+    setApproximation = set_approximation
 
 
 class ICGN3D1(_DVC):

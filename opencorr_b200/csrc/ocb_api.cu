@@ -59,6 +59,7 @@ struct ocb_ctx {
 	size_t own2_elems = 0;
 	ocb::Image2D img2{ nullptr, nullptr, 0, 0 };
 	bool prepared2 = false;
+	bool prepared_nr2 = false;
 
 	// 3D images + tables
 	float* own_ref3 = nullptr;
@@ -85,6 +86,8 @@ struct ocb_ctx {
 	size_t d_u8_bytes = 0;
 	float* d_off = nullptr; // centre offsets (2 floats per POI)
 	size_t d_off_bytes = 0;
+	void* d_strain_ws = nullptr; // Strain: sort keys / compact neighbour arrays / cub scratch
+	size_t d_strain_ws_bytes = 0;
 };
 
 static int set_error(ocb_ctx* ctx, int code, const char* fmt, ...) {
@@ -209,6 +212,7 @@ void ocb_destroy(ocb_ctx* ctx) {
 	cudaFree(ctx->fft_scratch);
 	cudaFree(ctx->d_poi);
 	cudaFree(ctx->d_off);
+	cudaFree(ctx->d_strain_ws);
 	cudaFree(ctx->d_u8);
 	cudaFree(ctx->d_counter);
 	cudaStreamDestroy(ctx->own_stream);
@@ -243,6 +247,7 @@ int ocb_set_images_2d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, 
 	if (!ctx || !d_ref || !d_tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d: bad arguments");
 	ctx->img2 = ocb::Image2D{ d_ref, d_tar, width, height };
 	ctx->prepared2 = false;
+	ctx->prepared_nr2 = false;
 	return OCB_OK;
 }
 
@@ -590,6 +595,93 @@ int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, f
 	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
 	if ((rc = ocb_iclm2d_dev(ctx, order, ctx->d_poi, n, rx, ry, conv, stop, lambda, alpha, beta))) return rc;
 	return unstage_pois(ctx, poi2d, bytes);
+}
+
+// ---- NR2D1 ---------------------------------------------------------------
+int ocb_nr2d_prepare(ocb_ctx* ctx) {
+	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "nr2d_prepare: images not set");
+	ctx->prepared_nr2 = true; // target gradients and the three interpolants are evaluated on chip per POI
+	return OCB_OK;
+}
+
+int ocb_nr2d1_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop) {
+	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "nr2d1: bad arguments");
+	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "nr2d1: images not set");
+	if (!ctx->prepared_nr2) return set_error(ctx, OCB_ERR_STATE, "nr2d1: prepare() has not been called since setImages()");
+	if (n == 0) return OCB_OK;
+	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "nr2d1: too many POIs in one call");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	cudaError_t err = cudaSuccess;
+	int rc = ocb::nr2d1_launch(ctx->img2, (float*)d_poi2d, n, rx, ry, conv, stop, ctx->sm_count, ctx->smem_optin, ctx->d_counter, ctx->stream, &err);
+	if (rc == -1) return set_error(ctx, OCB_ERR_UNSUPPORTED, "nr2d1: subset radius (%d,%d) exceeds the shared-memory design limit", rx, ry);
+	if (rc) return set_error(ctx, OCB_ERR_CUDA, "nr2d1 launch failed: %s", cudaGetErrorString(err));
+	ctx->launches++;
+	return OCB_OK;
+}
+
+int ocb_nr2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, float stop) {
+	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "nr2d1: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
+	if ((rc = ocb_nr2d1_dev(ctx, ctx->d_poi, n, rx, ry, conv, stop))) return rc;
+	return unstage_pois(ctx, poi2d, bytes);
+}
+
+// ---- Strain ---------------------------------------------------------------
+static int strain_dev(ocb_ctx* ctx, int dim, void* d_poi, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation,
+	long long only = -1) {
+	if (!ctx || (!d_poi && n) || only >= (long long)n) return set_error(ctx, OCB_ERR_ARG, "strain: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "strain: too many POIs in one call");
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const size_t need = ocb::strain_workspace_bytes(n);
+	if (need > ctx->d_strain_ws_bytes) {
+		if (ctx->d_strain_ws) cudaFree(ctx->d_strain_ws);
+		ctx->d_strain_ws = nullptr;
+		ctx->d_strain_ws_bytes = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->d_strain_ws, need));
+		ctx->d_strain_ws_bytes = need;
+	}
+	cudaError_t err = cudaSuccess;
+	int rc = ocb::strain_launch(dim, (float*)d_poi, n, radius, min_neighbors, zncc_threshold, approximation, only, ctx->d_strain_ws, ctx->sm_count, ctx->stream,
+		&err, &ctx->launches);
+	if (rc) return set_error(ctx, OCB_ERR_CUDA, "strain launch failed: %s", cudaGetErrorString(err));
+	return OCB_OK;
+}
+
+static int strain_host(ocb_ctx* ctx, int dim, void* poi, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation,
+	long long only = -1) {
+	if (!ctx || (!poi && n)) return set_error(ctx, OCB_ERR_ARG, "strain: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * (dim == 2 ? OCB_POI2D_FLOATS : OCB_POI3D_FLOATS) * sizeof(float);
+	if ((rc = stage_pois(ctx, poi, bytes))) return rc;
+	if ((rc = strain_dev(ctx, dim, ctx->d_poi, n, radius, min_neighbors, zncc_threshold, approximation, only))) return rc;
+	return unstage_pois(ctx, poi, bytes);
+}
+
+int ocb_strain2d(ocb_ctx* ctx, void* poi2d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_host(ctx, 2, poi2d, n, radius, min_neighbors, zncc_threshold, approximation);
+}
+int ocb_strain3d(ocb_ctx* ctx, void* poi3d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_host(ctx, 3, poi3d, n, radius, min_neighbors, zncc_threshold, approximation);
+}
+int ocb_strain2d_single(ocb_ctx* ctx, void* poi2d, size_t n, size_t index, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_host(ctx, 2, poi2d, n, radius, min_neighbors, zncc_threshold, approximation, (long long)index);
+}
+int ocb_strain3d_single(ocb_ctx* ctx, void* poi3d, size_t n, size_t index, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_host(ctx, 3, poi3d, n, radius, min_neighbors, zncc_threshold, approximation, (long long)index);
+}
+int ocb_strain2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_dev(ctx, 2, d_poi2d, n, radius, min_neighbors, zncc_threshold, approximation);
+}
+int ocb_strain3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_dev(ctx, 3, d_poi3d, n, radius, min_neighbors, zncc_threshold, approximation);
 }
 
 int ocb_icgn3d_prepare(ocb_ctx* ctx) {

@@ -35,6 +35,13 @@ inline bool fft_plan_axis(int n, FftAxis* ax) {
 // icgn2d.cu
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
 	size_t smem_optin, int* d_counter, const float* d_center_offsets, const float* lm_damping, cudaStream_t stream, cudaError_t* err);
+// nr2d.cu
+int nr2d1_launch(const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count, size_t smem_optin,
+	int* d_counter, cudaStream_t stream, cudaError_t* err);
+// strain.cu
+size_t strain_workspace_bytes(size_t n);
+int strain_launch(int dim, float* d_pois, size_t n, float radius, int k_min, float zncc_threshold, int approximation, long long only, void* workspace,
+	int sm_count, cudaStream_t stream, cudaError_t* err, long long* launches);
 // fftcc.cu
 size_t fftcc2d_smem_bytes(int rx, int ry);
 int fftcc2d_launch(const Image2D& img, float* d_pois, size_t n, int rx, int ry, const FftAxis& ax, const FftAxis& ay,

@@ -27,11 +27,13 @@
 // exx,eyy,exy | subset_rx,subset_ry}; POI3D = 31 floats {x,y,z | p[12] | u0,v0,w0,zncc,
 // iteration,convergence,feature | e[6] | subset_rx,ry,rz}.
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 #include <omp.h>
 
@@ -247,15 +249,18 @@ struct Ctx2D {
 	std::vector<float> gx, gy;    // Gradient2D4 of ref
 	std::vector<float> lut;       // BicubicBspline coefficient[h][w][4][4] of tar
 	bool prepared = false;
+	// what NR2D1::prepare() builds (src/oc_nr.cpp:119-156): gradients of TAR and the LUTs of both gradient maps
+	std::vector<float> tgx, tgy, lut_tgx, lut_tgy;
+	bool prepared_nr = false;
 };
 
 // Gradient2D4::getGradientX/Y, src/oc_gradient.cpp:37-79.  Borders (2 px) stay zero.
-void gradient2d(const Ctx2D& c, std::vector<float>& gx, std::vector<float>& gy) {
+void gradient2d(const Ctx2D& c, const std::vector<float>& src, std::vector<float>& gx, std::vector<float>& gy) {
 	const float first_factor = 1.f / 12.f, second_factor = 2.f / 3.f; // oc_gradient.cpp:21-22
 	int h = c.h, w = c.w;
 	gx.assign((size_t)h * w, 0.f);
 	gy.assign((size_t)h * w, 0.f);
-	const float* f = c.ref.data();
+	const float* f = src.data();
 #pragma omp parallel for num_threads(c.threads)
 	for (int r = 0; r < h; r++) {
 		for (int col = 2; col < w - 2; col++) {
@@ -288,10 +293,10 @@ const float BC_MATRIX[4][4] = {
 	{ 0.0f, 1.0f, 0.0f, 0.0f } };
 
 // BicubicBspline::prepare, src/oc_cubic_bspline.cpp:84-132: 16 floats per pixel LUT.
-void bicubic_prepare(Ctx2D& c) {
+void bicubic_prepare(const Ctx2D& c, const std::vector<float>& src, std::vector<float>& lut) {
 	int h = c.h, w = c.w;
-	c.lut.assign((size_t)h * w * 16, 0.f);
-	const float* img = c.tar.data();
+	lut.assign((size_t)h * w * 16, 0.f);
+	const float* img = src.data();
 #pragma omp parallel for num_threads(c.threads)
 	for (int r = 1; r < h - 2; r++) {
 		for (int col = 1; col < w - 2; col++) {
@@ -306,7 +311,7 @@ void bicubic_prepare(Ctx2D& c) {
 						for (int n = 0; n < 4; n++) acc += BC_MATRIX[l][m] * BC_MATRIX[k][n] * q[n][m];
 					p[k][l] = acc;
 				}
-			float* dst = &c.lut[((size_t)r * w + col) * 16];
+			float* dst = &lut[((size_t)r * w + col) * 16];
 			for (int k = 0; k < 4; k++)
 				for (int l = 0; l < 4; l++) dst[k * 4 + l] = p[3 - k][3 - l];
 		}
@@ -315,18 +320,20 @@ void bicubic_prepare(Ctx2D& c) {
 
 // BicubicBspline::compute, src/oc_cubic_bspline.cpp:134-181.
 template <class T>
-inline T bicubic_eval(const Ctx2D& c, T x, T y) {
+inline T bicubic_eval(const Ctx2D& c, const std::vector<float>& lut, T x, T y) {
 	if (x < 1 || y < 1 || x >= c.w - 2 || y >= c.h - 2 || is_nan(x) || is_nan(y)) return (T)-1;
 	int xi = (int)std::floor(x), yi = (int)std::floor(y);
 	T xd = x - xi, yd = y - yi;
 	T x2 = xd * xd, y2 = yd * yd, x3 = x2 * xd, y3 = y2 * yd;
-	const float* k = &c.lut[((size_t)yi * c.w + xi) * 16];
+	const float* k = &lut[((size_t)yi * c.w + xi) * 16];
 	T value = (T)k[0] + (T)k[1] * xd + (T)k[2] * x2 + (T)k[3] * x3
 		+ (T)k[4] * yd + (T)k[5] * yd * xd + (T)k[6] * yd * x2 + (T)k[7] * yd * x3
 		+ (T)k[8] * y2 + (T)k[9] * y2 * xd + (T)k[10] * y2 * x2 + (T)k[11] * y2 * x3
 		+ (T)k[12] * y3 + (T)k[13] * y3 * xd + (T)k[14] * y3 * x2 + (T)k[15] * y3 * x3;
 	return value;
 }
+template <class T>
+inline T bicubic_eval(const Ctx2D& c, T x, T y) { return bicubic_eval<T>(c, c.lut, x, y); }
 
 // FFTCC2D::compute(POI2D*), src/oc_fftcc.cpp:177-275.
 // per-thread scratch of the FFT-CC stage (the reference's FFTW instance pool, src/oc_fftcc.cpp:141-163)
@@ -467,7 +474,7 @@ inline void warp3d1_get(const T* W, T* p) { // :416-433
 // Per-thread scratch for 2D IC-GN (the reference's ICGN2D1_/ICGN2D2_, src/oc_icgn.h:30-43,85-98)
 template <class T>
 struct Scratch2D {
-	std::vector<T> ref, tar, err, sd;
+	std::vector<T> ref, tar, err, sd, gxw, gyw;
 };
 
 // ICGN2D1::compute(POI2D*) src/oc_icgn.cpp:144-341 (NP=6) and ICGN2D2::compute(POI2D*) :685-898 (NP=12).
@@ -649,6 +656,109 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 	poi[P2_CONV] = (float)dp_norm_max;
 	poi[P2_RX] = (float)rx;
 	poi[P2_RY] = (float)ry;
+	if (poi[P2_CONV] >= conv_criterion && poi[P2_ITER] >= stop_condition) poi[P2_ZNCC] = -4.f;
+	if (is_nan(poi[P2_ZNCC]) || is_nan(def[D2_U]) || is_nan(def[D2_V])) {
+		def[D2_U] = poi[P2_U0];
+		def[D2_V] = poi[P2_V0];
+		poi[P2_ZNCC] = -5.f;
+	}
+}
+
+// NR2D1::compute(POI2D*), src/oc_nr.cpp:160-325: forward-additive Newton-Raphson, first-order shape function.
+// Every iteration re-samples the target AND both target-gradient maps (three BicubicBspline tables,
+// prepare :119-156), rebuilds the full 6x6 Hessian from the warped gradients, and adds dp to p.
+// Differences from IC-GN worth pinning: the guard writes -1 (not -3) (:170); out-of-range samples (-1) are
+// used as values, there is no negative-sample test; the error image is ref*(|t|/|r|) - tar and ZNSSD is
+// normalised by |t|^2 (:244-247).
+template <class T>
+void nr2d1_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion, float stop_condition, Scratch2D<T>& s) {
+	float px = poi[P2_X], py = poi[P2_Y];
+	float* def = poi + P2_DEF;
+	if (py - ry < 0 || px - rx < 0 || py + ry > c.h - 1 || px + rx > c.w - 1
+		|| std::fabs(def[D2_U]) >= c.w || std::fabs(def[D2_V]) >= c.h
+		|| poi[P2_ZNCC] < 0 || is_nan(def[D2_U]) || is_nan(def[D2_V])) {
+		poi[P2_ZNCC] = poi[P2_ZNCC] < -1 ? poi[P2_ZNCC] : -1.f; // :170
+	} else {
+		int sw = 2 * rx + 1, sh = 2 * ry + 1, n = sw * sh;
+		s.ref.resize(n); s.tar.resize(n); s.err.resize(n); s.sd.resize((size_t)n * 6);
+		std::vector<T>& tgx = s.gxw; std::vector<T>& tgy = s.gyw;
+		tgx.resize(n); tgy.resize(n);
+		int uly = (int)(py - ry), ulx = (int)(px - rx);
+		T mean = 0;
+		for (int r = 0; r < sh; r++)
+			for (int col = 0; col < sw; col++) {
+				T v = c.ref[(size_t)(uly + r) * c.w + (ulx + col)];
+				s.ref[r * sw + col] = v;
+				mean += v;
+			}
+		mean /= n;
+		T sq = 0;
+		for (int i = 0; i < n; i++) { s.ref[i] -= mean; sq += s.ref[i] * s.ref[i]; }
+		T ref_mean_norm = std::sqrt(sq);
+
+		float p_init_u = def[D2_U], p_init_v = def[D2_V];
+		T p[6] = { (T)def[D2_U], (T)def[D2_UX], (T)def[D2_UY], (T)def[D2_V], (T)def[D2_VX], (T)def[D2_VY] };
+		T W[9], dp[6];
+		int iteration_counter = 0;
+		T dp_norm_max = 0, znssd = 0;
+		do {
+			iteration_counter++;
+			warp2d1_set(p, W);
+			for (int r = 0; r < sh; r++)
+				for (int col = 0; col < sw; col++) {
+					T xl = (T)(col - rx), yl = (T)(r - ry);
+					T wx = W[0] * xl + W[1] * yl + W[2] * (T)1;
+					T wy = W[3] * xl + W[4] * yl + W[5] * (T)1;
+					T gxp = (T)px + wx, gyp = (T)py + wy;
+					s.tar[r * sw + col] = bicubic_eval<T>(c, c.lut, gxp, gyp);
+					tgx[r * sw + col] = bicubic_eval<T>(c, c.lut_tgx, gxp, gyp);
+					tgy[r * sw + col] = bicubic_eval<T>(c, c.lut_tgy, gxp, gyp);
+				}
+			T tmean = 0;
+			for (int i = 0; i < n; i++) tmean += s.tar[i];
+			tmean /= n;
+			T tsq = 0;
+			for (int i = 0; i < n; i++) { s.tar[i] -= tmean; tsq += s.tar[i] * s.tar[i]; }
+			T tar_mean_norm = std::sqrt(tsq);
+			T H[36], invH[36];
+			for (int i = 0; i < 36; i++) H[i] = 0;
+			for (int r = 0; r < sh; r++)
+				for (int col = 0; col < sw; col++) {
+					T xl = (T)(col - rx), yl = (T)(r - ry);
+					T gx = tgx[r * sw + col], gy = tgy[r * sw + col];
+					T* sd = &s.sd[(size_t)(r * sw + col) * 6];
+					sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl;
+					sd[3] = gy; sd[4] = gy * xl; sd[5] = gy * yl;
+					for (int i = 0; i < 6; i++)
+						for (int j = 0; j < 6; j++) H[i * 6 + j] += sd[i] * sd[j];
+				}
+			inverse_lu<T, 6>(H, invH);
+			T factor = tar_mean_norm / ref_mean_norm;
+			T esq = 0;
+			for (int i = 0; i < n; i++) { s.err[i] = s.ref[i] * factor - s.tar[i]; esq += s.err[i] * s.err[i]; }
+			znssd = esq / (tar_mean_norm * tar_mean_norm);
+			T num[6] = { 0, 0, 0, 0, 0, 0 };
+			for (int i = 0; i < n; i++)
+				for (int k = 0; k < 6; k++) num[k] += s.sd[(size_t)i * 6 + k] * s.err[i];
+			for (int i = 0; i < 6; i++) {
+				dp[i] = 0;
+				for (int j = 0; j < 6; j++) dp[i] += invH[i * 6 + j] * num[j];
+			}
+			for (int i = 0; i < 6; i++) p[i] += dp[i];
+			int rx2 = rx * rx, ry2 = ry * ry;
+			dp_norm_max = dp[0] * dp[0] + dp[1] * dp[1] * rx2 + dp[2] * dp[2] * ry2
+				+ dp[3] * dp[3] + dp[4] * dp[4] * rx2 + dp[5] * dp[5] * ry2;
+			dp_norm_max = std::sqrt(dp_norm_max);
+		} while (iteration_counter < stop_condition && dp_norm_max >= conv_criterion);
+		def[D2_U] = (float)p[0]; def[D2_UX] = (float)p[1]; def[D2_UY] = (float)p[2];
+		def[D2_V] = (float)p[3]; def[D2_VX] = (float)p[4]; def[D2_VY] = (float)p[5];
+		poi[P2_U0] = p_init_u;
+		poi[P2_V0] = p_init_v;
+		poi[P2_ZNCC] = (float)((T)0.5 * ((T)2 - znssd));
+		poi[P2_ITER] = (float)iteration_counter;
+		poi[P2_CONV] = (float)dp_norm_max;
+	}
+	// evaluated for every POI, also the guarded ones (:314-324)
 	if (poi[P2_CONV] >= conv_criterion && poi[P2_ITER] >= stop_condition) poi[P2_ZNCC] = -4.f;
 	if (is_nan(poi[P2_ZNCC]) || is_nan(def[D2_U]) || is_nan(def[D2_V])) {
 		def[D2_U] = poi[P2_U0];
@@ -996,6 +1106,15 @@ void run_icgn2d(const Ctx2D& c, float* pois, long n, int rx, int ry, float conv,
 	}
 }
 template <class T>
+void run_nr2d1(const Ctx2D& c, float* pois, long n, int rx, int ry, float conv, float stop) {
+#pragma omp parallel num_threads(c.threads)
+	{
+		Scratch2D<T> s;
+#pragma omp for schedule(dynamic, 64)
+		for (long i = 0; i < n; i++) nr2d1_poi<T>(c, pois + i * P2_N, rx, ry, conv, stop, s);
+	}
+}
+template <class T>
 void run_fftcc3d(const Ctx3D& c, float* pois, long n, int rx, int ry, int rz) {
 	FFT<T> fx, fy, fz;
 	fx.plan(2 * rx); fy.plan(2 * ry); fz.plan(2 * rz);
@@ -1016,6 +1135,192 @@ void run_icgn3d1(const Ctx3D& c, float* pois, long n, int rx, int ry, int rz, fl
 	}
 }
 
+// ----------------------------------------------------------------------------------------------
+// Strain (reference src/oc_strain.cpp): per-POI least-squares plane fit of the displacement field over the
+// neighbours found by NearestNeighbor (src/oc_nearest_neighbor.cpp: a nanoflann kd-tree, third-party header
+// not vendored in the reference tree; nanoflann >= 1.5.0 semantics restated: radiusSearch returns the points
+// with squared L2 distance STRICTLY below radius^2 -- RadiusResultSet::addPoint `if (dist < radius)` -- and
+// knnSearch the k nearest, ties in unspecified order; here ties go to the lower index).
+// Strain::compute(POI2D*, queue) :158-237, Strain::compute(POI3D*, queue) :373-474, batch :239-250 / :476-487.
+// D = 2: POI2D records (25 floats), strain = {exx, eyy, exy}; D = 3: POI3D (31 floats), {exx, eyy, ezz, exy, eyz, ezx}.
+// ----------------------------------------------------------------------------------------------
+template <int D> struct StrainLayout;
+template <> struct StrainLayout<2> { enum { NF = P2_N, ZNCC = P2_ZNCC, STRAIN = P2_STRAIN, U = P2_DEF + D2_U, V = P2_DEF + D2_V, W = -1 }; };
+template <> struct StrainLayout<3> { enum { NF = P3_N, ZNCC = P3_ZNCC, STRAIN = P3_STRAIN, U = P3_DEF + 0, V = P3_DEF + 4, W = P3_DEF + 8 }; };
+
+// least squares A x = b_k for NB right-hand sides by column-pivoted Householder QR (what Eigen's
+// colPivHouseholderQr().solve does), A is m x C row-major in `a`, b is m x NB row-major; destroys both.
+template <class T, int C, int NB>
+void lsq_qr(std::vector<T>& a, std::vector<T>& b, int m, T x[NB][C]) {
+	int perm[C];
+	for (int j = 0; j < C; j++) perm[j] = j;
+	int rank = 0;
+	T first_norm = 0;
+	for (int k = 0; k < C && k < m; k++) {
+		// pivot: remaining column with the largest norm
+		int best = k;
+		T bestn = -1;
+		for (int j = k; j < C; j++) {
+			T s = 0;
+			for (int i = k; i < m; i++) s += a[(size_t)i * C + j] * a[(size_t)i * C + j];
+			if (s > bestn) { bestn = s; best = j; }
+		}
+		if (k == 0) first_norm = bestn;
+		if (bestn <= first_norm * (T)1e-12) break; // rank deficient: remaining unknowns stay 0
+		if (best != k) {
+			for (int i = 0; i < m; i++) std::swap(a[(size_t)i * C + k], a[(size_t)i * C + best]);
+			std::swap(perm[k], perm[best]);
+		}
+		T alpha = std::sqrt(bestn);
+		if (a[(size_t)k * C + k] > 0) alpha = -alpha;
+		std::vector<T> v(m - k);
+		for (int i = k; i < m; i++) v[i - k] = a[(size_t)i * C + k];
+		v[0] -= alpha;
+		T vn = 0;
+		for (T e : v) vn += e * e;
+		if (vn > 0) {
+			for (int j = k; j < C; j++) {
+				T d = 0;
+				for (int i = k; i < m; i++) d += v[i - k] * a[(size_t)i * C + j];
+				d = (T)2 * d / vn;
+				for (int i = k; i < m; i++) a[(size_t)i * C + j] -= d * v[i - k];
+			}
+			for (int j = 0; j < NB; j++) {
+				T d = 0;
+				for (int i = k; i < m; i++) d += v[i - k] * b[(size_t)i * NB + j];
+				d = (T)2 * d / vn;
+				for (int i = k; i < m; i++) b[(size_t)i * NB + j] -= d * v[i - k];
+			}
+		}
+		rank++;
+	}
+	for (int j = 0; j < NB; j++) {
+		T y[C];
+		for (int k = 0; k < C; k++) y[k] = 0;
+		for (int k = rank - 1; k >= 0; k--) {
+			T s = b[(size_t)k * NB + j];
+			for (int l = k + 1; l < rank; l++) s -= a[(size_t)k * C + l] * y[l];
+			y[k] = s / a[(size_t)k * C + k];
+		}
+		for (int k = 0; k < C; k++) x[j][perm[k]] = y[k];
+	}
+}
+
+template <class T, int D>
+void run_strain(float* pois, long n, float radius, int k_min, float zncc_threshold, int approximation, int threads) {
+	typedef StrainLayout<D> L;
+	const int NF = L::NF;
+	// uniform grid over the POI positions, cell edge = radius
+	float lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+	for (int d = 0; d < D; d++) { lo[d] = 1e30f; hi[d] = -1e30f; }
+	for (long i = 0; i < n; i++)
+		for (int d = 0; d < D; d++) { lo[d] = std::min(lo[d], pois[i * NF + d]); hi[d] = std::max(hi[d], pois[i * NF + d]); }
+	const float cell = radius > 0 ? radius : 1.f;
+	long nc[3] = { 1, 1, 1 };
+	for (int d = 0; d < D; d++) nc[d] = (long)std::floor((hi[d] - lo[d]) / cell) + 1;
+	auto cell_of = [&](const float* p, long* c) { for (int d = 0; d < 3; d++) c[d] = d < D ? (long)std::floor((p[d] - lo[d]) / cell) : 0; };
+	std::vector<long> start((size_t)(nc[0] * nc[1] * nc[2]) + 1, 0), order(n);
+	for (long i = 0; i < n; i++) { long c[3]; cell_of(pois + i * NF, c); start[(c[2] * nc[1] + c[1]) * nc[0] + c[0] + 1]++; }
+	for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+	{
+		std::vector<long> fill(start.begin(), start.end() - 1);
+		for (long i = 0; i < n; i++) { long c[3]; cell_of(pois + i * NF, c); order[fill[(c[2] * nc[1] + c[1]) * nc[0] + c[0]]++] = i; }
+	}
+	std::vector<float> out((size_t)n * (D == 2 ? 3 : 6));
+	std::vector<char> done(n, 0);
+	const float r2 = radius * radius;
+#pragma omp parallel num_threads(threads)
+	{
+		std::vector<long> fit;
+		std::vector<std::pair<float, long>> cand;
+		std::vector<T> A, B;
+#pragma omp for schedule(dynamic, 64)
+		for (long i = 0; i < n; i++) {
+			const float* p = pois + i * NF;
+			if (!(p[L::ZNCC] >= zncc_threshold)) continue; // :244-248
+			long c[3];
+			cell_of(p, c);
+			fit.clear();
+			long found = 0;
+			for (long cz = std::max(0l, c[2] - 1); cz <= std::min(nc[2] - 1, c[2] + 1); cz++)
+				for (long cy = std::max(0l, c[1] - 1); cy <= std::min(nc[1] - 1, c[1] + 1); cy++)
+					for (long cx = std::max(0l, c[0] - 1); cx <= std::min(nc[0] - 1, c[0] + 1); cx++) {
+						long ci = (cz * nc[1] + cy) * nc[0] + cx;
+						for (long s = start[ci]; s < start[ci + 1]; s++) {
+							long j = order[s];
+							const float* q = pois + j * NF;
+							float d2 = 0.f; // L2_Simple_Adaptor: float accumulation over the 3 coordinates
+							for (int d = 0; d < D; d++) { float df = p[d] - q[d]; d2 += df * df; }
+							if (d2 < r2) {
+								found++;
+								if (q[L::ZNCC] >= zncc_threshold) fit.push_back(j);
+							}
+						}
+					}
+			if (found < k_min) { // KNN fallback :183-196
+				fit.clear();
+				cand.clear();
+				for (long j = 0; j < n; j++) {
+					const float* q = pois + j * NF;
+					float d2 = 0.f;
+					for (int d = 0; d < D; d++) { float df = p[d] - q[d]; d2 += df * df; }
+					cand.push_back(std::make_pair(d2, j));
+				}
+				long k = std::min((long)k_min, n);
+				std::partial_sort(cand.begin(), cand.begin() + k, cand.end());
+				for (long t = 0; t < k; t++)
+					if (pois[cand[t].second * NF + L::ZNCC] >= zncc_threshold) fit.push_back(cand[t].second);
+			}
+			std::sort(fit.begin(), fit.end());
+			const int m = (int)fit.size();
+			if (m < k_min) continue; // :200-201
+			constexpr int C = D + 1;
+			A.resize((size_t)m * C);
+			B.resize((size_t)m * D);
+			for (int t = 0; t < m; t++) {
+				const float* q = pois + fit[t] * NF;
+				A[(size_t)t * C] = 1;
+				for (int d = 0; d < D; d++) A[(size_t)t * C + 1 + d] = (T)(q[d] - p[d]);
+				B[(size_t)t * D] = q[L::U];
+				B[(size_t)t * D + 1] = q[L::V];
+				if (D == 3) B[(size_t)t * D + 2] = q[L::W];
+			}
+			T x[D][C];
+			lsq_qr<T, C, D>(A, B, m, x);
+			float* e = &out[(size_t)i * (D == 2 ? 3 : 6)];
+			if (D == 2) {
+				float ux = (float)x[0][1], uy = (float)x[0][2], vx = (float)x[1][1], vy = (float)x[1][2];
+				if (approximation == 2) { // Green strain :229-235
+					e[0] = ux + 0.5f * (ux * ux + vx * vx);
+					e[1] = vy + 0.5f * (uy * uy + vy * vy);
+					e[2] = 0.5f * (uy + vx + uy * ux + vy * vx);
+				} else { // Cauchy strain :222-227
+					e[0] = ux; e[1] = vy; e[2] = 0.5f * (uy + vx);
+				}
+			} else {
+				float ux = (float)x[0][1], uy = (float)x[0][2], uz = (float)x[0][3];
+				float vx = (float)x[1][1], vy = (float)x[1][2], vz = (float)x[1][3];
+				float wx = (float)x[2 % D][1], wy = (float)x[2 % D][2], wz = (float)x[2 % D][3 % C];
+				if (approximation == 2) { // :455-463
+					e[0] = ux + 0.5f * (ux * ux + vx * vx + wx * wx);
+					e[1] = vy + 0.5f * (uy * uy + vy * vy + wy * wy);
+					e[2] = wz + 0.5f * (uz * uz + vz * vz + wz * wz);
+					e[3] = 0.5f * (uy + vx + uy * ux + vy * vx + wy * wx);
+					e[4] = 0.5f * (vz + wy + uz * uy + vz * vy + wz * wy);
+					e[5] = 0.5f * (wx + uz + ux * uz + vx * vz + wx * wz);
+				} else { // :444-453
+					e[0] = ux; e[1] = vy; e[2] = wz;
+					e[3] = 0.5f * (uy + vx); e[4] = 0.5f * (vz + wy); e[5] = 0.5f * (wx + uz);
+				}
+			}
+			done[i] = 1;
+		}
+	}
+	for (long i = 0; i < n; i++)
+		if (done[i])
+			for (int k = 0; k < (D == 2 ? 3 : 6); k++) pois[i * NF + L::STRAIN + k] = out[(size_t)i * (D == 2 ? 3 : 6) + k];
+}
+
 } // namespace
 
 // ----------------------------------------------------------------------------------------------
@@ -1034,8 +1339,8 @@ void oco_destroy2d(void* h) { delete (Ctx2D*)h; }
 // ICGN2D1::prepare / ICGN2D2::prepare (src/oc_icgn.cpp:138-142, :679-683)
 void oco_prepare2d(void* h) {
 	Ctx2D* c = (Ctx2D*)h;
-	gradient2d(*c, c->gx, c->gy);
-	bicubic_prepare(*c);
+	gradient2d(*c, c->ref, c->gx, c->gy);
+	bicubic_prepare(*c, c->tar, c->lut);
 	c->prepared = true;
 }
 void oco_get_gradient2d(void* h, float* gx, float* gy) {
@@ -1094,6 +1399,22 @@ int oco_iclm2d(void* h, int order, float* pois, long n, int rx, int ry, float co
 	return 0;
 }
 
+// NR2D1::prepare (src/oc_nr.cpp:119-156) and NR2D1::compute(queue) (:327-334)
+void oco_prepare_nr2d(void* h) {
+	Ctx2D* c = (Ctx2D*)h;
+	gradient2d(*c, c->tar, c->tgx, c->tgy);
+	if (c->lut.empty()) bicubic_prepare(*c, c->tar, c->lut);
+	bicubic_prepare(*c, c->tgx, c->lut_tgx);
+	bicubic_prepare(*c, c->tgy, c->lut_tgy);
+	c->prepared_nr = true;
+}
+int oco_nr2d1(void* h, float* pois, long n, int rx, int ry, float conv, float stop, int exact) {
+	Ctx2D* c = (Ctx2D*)h;
+	if (!c->prepared_nr) return -1;
+	if (exact) run_nr2d1<double>(*c, pois, n, rx, ry, conv, stop); else run_nr2d1<float>(*c, pois, n, rx, ry, conv, stop);
+	return 0;
+}
+
 void* oco_create3d(const float* ref, const float* tar, int dim_x, int dim_y, int dim_z, int threads) {
 	Ctx3D* c = new Ctx3D;
 	c->dx = dim_x; c->dy = dim_y; c->dz = dim_z; c->threads = threads > 0 ? threads : 1;
@@ -1134,6 +1455,20 @@ int oco_icgn3d1(void* h, float* pois, long n, int rx, int ry, int rz, float conv
 	Ctx3D* c = (Ctx3D*)h;
 	if (!c->prepared) return -1;
 	if (exact) run_icgn3d1<double>(*c, pois, n, rx, ry, rz, conv, stop); else run_icgn3d1<float>(*c, pois, n, rx, ry, rz, conv, stop);
+	return 0;
+}
+// Strain::prepare + Strain::compute(queue) on POI2D (dim 2) / POI3D (dim 3) records, src/oc_strain.cpp:100-111,239-250,476-487.
+// approximation: 1 Cauchy, 2 Green (setApproximation); zncc_threshold default 0.9 (:38).
+int oco_strain(float* pois, long n, int dim, float radius, int min_neighbors, float zncc_threshold, int approximation, int threads, int exact) {
+	if (dim != 2 && dim != 3) return -1;
+	if (threads < 1) threads = 1;
+	if (dim == 2) {
+		if (exact) run_strain<double, 2>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
+		else run_strain<float, 2>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
+	} else {
+		if (exact) run_strain<double, 3>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
+		else run_strain<float, 3>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
+	}
 	return 0;
 }
 int oco_max_threads(void) { return omp_get_num_procs(); }

@@ -50,6 +50,10 @@ def lib():
         L.oco_iclm2d.restype = ctypes.c_int
         L.oco_iclm2d.argtypes = [ctypes.c_void_p, ctypes.c_int, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                  ctypes.c_float, ctypes.c_float, _f32p, ctypes.c_int]
+        L.oco_prepare_nr2d.argtypes = [ctypes.c_void_p]
+        L.oco_nr2d1.restype = ctypes.c_int
+        L.oco_nr2d1.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                                ctypes.c_float, ctypes.c_float, ctypes.c_int]
         L.oco_create3d.restype = ctypes.c_void_p
         L.oco_create3d.argtypes = [_f32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.oco_destroy3d.argtypes = [ctypes.c_void_p]
@@ -62,6 +66,9 @@ def lib():
         L.oco_icgn3d1.restype = ctypes.c_int
         L.oco_icgn3d1.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   ctypes.c_float, ctypes.c_float, ctypes.c_int]
+        L.oco_strain.restype = ctypes.c_int
+        L.oco_strain.argtypes = [_f32p, ctypes.c_long, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.oco_max_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -79,6 +86,16 @@ def max_threads():
     return int(lib().oco_max_threads())
 
 
+def strain(pois, radius, min_neighbors, zncc_threshold=0.9, approximation=1, threads=0, exact=False):
+    """Strain::prepare + Strain::compute(queue) (reference src/oc_strain.cpp) on a POI2D [n,25] / POI3D [n,31] array."""
+    assert pois.dtype == np.float32 and pois.flags.c_contiguous and pois.shape[1] in (25, 31)
+    dim = 2 if pois.shape[1] == 25 else 3
+    threads = threads if threads > 0 else max(1, max_threads() - 1)
+    rc = lib().oco_strain(_p(pois), pois.shape[0], dim, radius, min_neighbors, zncc_threshold, approximation, threads, int(exact))
+    assert rc == 0
+    return pois
+
+
 class Oracle2D:
     """ref, tar: float32 [H, W] row-major.  Mirrors FFTCC2D / ICGN2D1 / ICGN2D2 of the reference."""
 
@@ -90,6 +107,7 @@ class Oracle2D:
         self.threads = threads if threads > 0 else max(1, max_threads() - 1)
         self._h = lib().oco_create2d(_p(self.ref), _p(self.tar), self.h, self.w, self.threads)
         self._prepared = False
+        self._prepared_nr = False
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -157,6 +175,16 @@ class Oracle2D:
             self.prepare()
         d = _c32(damping).reshape(3)
         rc = lib().oco_iclm2d(self._h, order, _p(pois), pois.shape[0], rx, ry, conv, stop, _p(d), int(exact))
+        assert rc == 0
+        return pois
+
+    def nr2d1(self, pois, rx, ry, conv=0.001, stop=10, exact=False):
+        """NR2D1 (forward-additive Newton-Raphson), reference src/oc_nr.cpp:119-334."""
+        assert pois.dtype == np.float32 and pois.flags.c_contiguous and pois.shape[1] == 25
+        if not self._prepared_nr:
+            lib().oco_prepare_nr2d(self._h)
+            self._prepared_nr = True
+        rc = lib().oco_nr2d1(self._h, _p(pois), pois.shape[0], rx, ry, conv, stop, int(exact))
         assert rc == 0
         return pois
 

@@ -8,6 +8,12 @@ Outputs
   oht_cfrp_0.bmp, oht_cfrp_4.bmp    the 2D example pair (280x900, 8-bit), verbatim
   oht_cfrp_4_fftcc_icgn1_r16.npz    every 23rd row of the shipped result table + deformation table
   oht_cfrp_4_fftcc_iclm1_r16.npz    the same rows of the shipped ICLM2D1 table
+  oht_cfrp_4_fftcc_nr1_r16.npz      every 23rd row of the shipped NR2D1 table (x,y,u,v,u0,v0,ZNCC,iteration,convergence)
+                                    + a 96-row band (y in [370,560), all 100 columns, includes the specimen's hole)
+                                    of x,y,u,v,ZNCC,exx,eyy,exy for the Strain test; rows with `band_check` have
+                                    their whole 20-px neighbourhood inside the band
+  torus_strain_crop.npz             a box of the shipped DVC table examples/dvc/Torus_def_sift_icgn1_r16.csv
+                                    (x,y,z,u,v,w,ZNCC + 6 strains) for the 3D Strain test, same idea
   al_foam4_crop.npz                 z-slices [18,118) of the DVC example pair as uint8 (values are
                                     integral, 52..202) + the shipped CPU and GPU result rows of the
                                     196 POIs with z in {60,65,70,75}.  The 15-tap prefilter and the
@@ -38,6 +44,24 @@ def main():
     itab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_fftcc_iclm1_r16.csv"), delimiter=",", skip_header=1)
     np.savez_compressed(os.path.join(OUT, "oht_cfrp_4_fftcc_iclm1_r16.npz"),
                         columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence".split(",")), table=itab[sel, :9], rows=sel)
+
+    # NR2D1 + Strain table shipped by the reference (examples/2d_dic/oht_cfrp_4_fftcc_nr1_r16.csv)
+    ntab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_fftcc_nr1_r16.csv"), delimiter=",", skip_header=1)
+    band = (ntab[:, 1] >= 370) & (ntab[:, 1] < 560)
+    bt = ntab[band][:, [0, 1, 2, 3, 6, 10, 11, 12]].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "oht_cfrp_4_fftcc_nr1_r16.npz"),
+                        columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence".split(",")), table=ntab[sel, :9], rows=sel,
+                        band_columns=np.array("x,y,u,v,ZNCC,exx,eyy,exy".split(",")), band=bt,
+                        band_check=(bt[:, 1] >= 390) & (bt[:, 1] < 540))
+
+    # DVC table with strains (examples/dvc/Torus_def_sift_icgn1_r16.csv; strain radius 30, min 5 neighbours,
+    # examples/test_dvc_strain.cpp:48-54)
+    tt = np.genfromtxt(os.path.join(REF, "dvc", "Torus_def_sift_icgn1_r16.csv"), delimiter=",", skip_header=1)
+    box = (tt[:, 0] >= 470) & (tt[:, 0] <= 630) & (tt[:, 2] >= 351) & (tt[:, 2] <= 501)
+    tb = tt[box][:, [0, 1, 2, 3, 4, 5, 9, 22, 23, 24, 25, 26, 27]].astype(np.float32)
+    inner = (tb[:, 0] >= 500) & (tb[:, 0] <= 600) & (tb[:, 2] >= 381) & (tb[:, 2] <= 471)
+    np.savez_compressed(os.path.join(OUT, "torus_strain_crop.npz"),
+                        columns=np.array("x,y,z,u,v,w,ZNCC,exx,eyy,ezz,exy,eyz,ezx".split(",")), table=tb, check=inner)
 
     def load(p):
         d = np.fromfile(p, dtype=np.int32, count=3)

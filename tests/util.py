@@ -81,3 +81,36 @@ def compare_3d(a, b, label="", tol_disp=1e-4, tol_zncc=1e-5, max_iter_mismatch_f
 
 def oht_cfrp_iclm_golden():
     return np.load(os.path.join(GOLDEN, "oht_cfrp_4_fftcc_iclm1_r16.npz"))
+
+
+def oht_cfrp_nr_golden():
+    return np.load(os.path.join(GOLDEN, "oht_cfrp_4_fftcc_nr1_r16.npz"))
+
+
+def torus_strain_crop():
+    return np.load(os.path.join(GOLDEN, "torus_strain_crop.npz"))
+
+
+def strain_band_queue():
+    """POI2D queue of the 96-row band of the shipped NR2D1 + Strain table, golden strains, and the mask of rows whose
+    20-px neighbourhood lies inside the band."""
+    g = oht_cfrp_nr_golden()
+    b = g["band"]
+    q = np.zeros((b.shape[0], 25), np.float32)
+    q[:, 0:2] = b[:, 0:2]
+    q[:, 2] = b[:, 2]
+    q[:, 8] = b[:, 3]
+    q[:, 16] = b[:, 4]
+    return q, b[:, 5:8], g["band_check"]
+
+
+def torus_queue():
+    g = torus_strain_crop()
+    t = g["table"]
+    q = np.zeros((t.shape[0], 31), np.float32)
+    q[:, 0:3] = t[:, 0:3]
+    q[:, 3] = t[:, 3]
+    q[:, 7] = t[:, 4]
+    q[:, 11] = t[:, 5]
+    q[:, 18] = t[:, 6]
+    return q, t[:, 7:13], g["check"]
