@@ -379,6 +379,9 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
     e2e_value = n_total / (e2e_ms * 1e-3)
+    e2e_sorted = sorted(1e3 * t for t in e2e_times)
+    e2e_spread = {"min": e2e_sorted[0], "median": e2e_sorted[len(e2e_sorted) // 2], "max": e2e_sorted[-1],
+                  "argmax_step": int(np.argmax(e2e_times))}
     if world == 1:
         h2d, d2h = img_bytes + 2 * poi_bytes, 2 * poi_bytes
     else:
@@ -489,7 +492,8 @@ def run_ours(args):
                        "l2": "flushed between timed steps (256 MiB write); timing = sum of per-step CUDA-event intervals",
                        "wall_s_timed_region_incl_flush": wall},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+                    "ms_per_step_spread_rank0": e2e_spread},
             "e2e_u8_images": e2e_u8,
             "gpu_launches": int(launches),
             "roofline": roofline,

@@ -309,13 +309,95 @@ namespace opencorr
 			in.read((char*)**vol_mat, sizeof(float) * size);
 			if (!in) throw std::string("Failed to read bin file: " + file_path);
 		}
+		// multi-page TIFF, one page per z slice (src/oc_image.cpp:112-150 reads it with cv::imreadmulti(IMREAD_GRAYSCALE)).
+		// Baseline subset read here without OpenCV: classic TIFF (not BigTIFF), grayscale, 8 or 16 bits per sample
+		// (16-bit is scaled to 8 bits like IMREAD_GRAYSCALE), strips, uncompressed or PackBits.
+		inline void loadTiff(std::string file_path)
+		{
+			std::ifstream in(file_path, std::ios::in | std::ios::binary);
+			if (!in.is_open()) throw std::string("Fail to load multi-page tiff: " + file_path);
+			std::vector<unsigned char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+			if (buf.size() < 8) throw std::string("Not a TIFF file: " + file_path);
+			const bool le = buf[0] == 'I' && buf[1] == 'I';
+			if (!le && !(buf[0] == 'M' && buf[1] == 'M')) throw std::string("Not a TIFF file: " + file_path);
+			auto rd16 = [&](size_t o) -> uint32_t {
+				if (o + 2 > buf.size()) throw std::string("Truncated TIFF: " + file_path);
+				return le ? (uint32_t)buf[o] | ((uint32_t)buf[o + 1] << 8) : (uint32_t)buf[o + 1] | ((uint32_t)buf[o] << 8);
+			};
+			auto rd32 = [&](size_t o) -> uint32_t {
+				if (o + 4 > buf.size()) throw std::string("Truncated TIFF: " + file_path);
+				return le ? (uint32_t)buf[o] | ((uint32_t)buf[o + 1] << 8) | ((uint32_t)buf[o + 2] << 16) | ((uint32_t)buf[o + 3] << 24)
+						  : (uint32_t)buf[o + 3] | ((uint32_t)buf[o + 2] << 8) | ((uint32_t)buf[o + 1] << 16) | ((uint32_t)buf[o] << 24);
+			};
+			if (rd16(2) != 42) throw std::string("Unsupported TIFF flavour (BigTIFF?): " + file_path);
+			struct Page { uint32_t w = 0, h = 0, bits = 8, comp = 1, photo = 1, spp = 1, rps = 0xffffffffu; std::vector<uint32_t> off, cnt; };
+			std::vector<Page> pages;
+			uint32_t ifd = rd32(4);
+			while (ifd != 0) {
+				Page pg;
+				const uint32_t n = rd16(ifd);
+				for (uint32_t e = 0; e < n; e++) {
+					const size_t o = (size_t)ifd + 2 + 12 * (size_t)e;
+					const uint32_t tag = rd16(o), type = rd16(o + 2), count = rd32(o + 4);
+					const uint32_t tsize = type == 3 ? 2 : (type == 4 ? 4 : 1);
+					const size_t vo = (size_t)count * tsize <= 4 ? o + 8 : rd32(o + 8);
+					auto val = [&](uint32_t i) -> uint32_t { return type == 3 ? rd16(vo + 2 * (size_t)i) : (type == 4 ? rd32(vo + 4 * (size_t)i) : buf.at(vo + i)); };
+					switch (tag) {
+					case 256: pg.w = val(0); break;
+					case 257: pg.h = val(0); break;
+					case 258: pg.bits = val(0); break;
+					case 259: pg.comp = val(0); break;
+					case 262: pg.photo = val(0); break;
+					case 277: pg.spp = val(0); break;
+					case 278: pg.rps = val(0); break;
+					case 273: for (uint32_t i = 0; i < count; i++) pg.off.push_back(val(i)); break;
+					case 279: for (uint32_t i = 0; i < count; i++) pg.cnt.push_back(val(i)); break;
+					default: break;
+					}
+				}
+				if (pg.spp != 1 || (pg.bits != 8 && pg.bits != 16) || (pg.comp != 1 && pg.comp != 32773) || pg.off.empty() || pg.off.size() != pg.cnt.size())
+					throw std::string("Unsupported TIFF page (need grayscale, 8/16 bit, uncompressed or PackBits strips): " + file_path);
+				pages.push_back(pg);
+				ifd = rd32((size_t)ifd + 2 + 12 * (size_t)n);
+			}
+			if (pages.empty()) throw std::string("Fail to load multi-page tiff: " + file_path);
+			allocate((int)pages[0].w, (int)pages[0].h, (int)pages.size());
+			std::vector<unsigned char> raw;
+			for (size_t z = 0; z < pages.size(); z++) {
+				const Page& pg = pages[z];
+				if ((int)pg.w != dim_x || (int)pg.h != dim_y) throw std::string("TIFF pages differ in size: " + file_path);
+				const size_t bps = pg.bits / 8, want = (size_t)pg.w * pg.h * bps;
+				raw.clear();
+				for (size_t k = 0; k < pg.off.size(); k++) {
+					if ((size_t)pg.off[k] + pg.cnt[k] > buf.size()) throw std::string("Truncated TIFF: " + file_path);
+					const unsigned char* p = &buf[pg.off[k]];
+					if (pg.comp == 1) raw.insert(raw.end(), p, p + pg.cnt[k]);
+					else { // PackBits
+						size_t i = 0;
+						while (i < pg.cnt[k]) {
+							const int c = (signed char)p[i++];
+							if (c >= 0) { for (int t = 0; t <= c && i < pg.cnt[k]; t++) raw.push_back(p[i++]); }
+							else if (c != -128 && i < pg.cnt[k]) { raw.insert(raw.end(), (size_t)(1 - c), p[i]); i++; }
+						}
+					}
+				}
+				if (raw.size() < want) throw std::string("Truncated TIFF page: " + file_path);
+				float* dst = vol_mat[z][0];
+				for (size_t i = 0; i < (size_t)pg.w * pg.h; i++) {
+					uint32_t v = bps == 1 ? raw[i] : (le ? (uint32_t)raw[2 * i + 1] : (uint32_t)raw[2 * i]); // 16 -> 8 bit: the high byte
+					if (pg.photo == 0) v = 255 - v; // WhiteIsZero
+					dst[i] = (float)v;
+				}
+			}
+		}
 		inline void load(std::string file_path)
 		{
 			this->file_path = file_path;
 			size_t dot_pos = file_path.find_last_of(".");
 			std::string ext = file_path.substr(dot_pos + 1);
 			if (ext == "bin" || ext == "BIN") loadBin(file_path);
-			else throw std::string("Only .bin volumes are supported by this build (multi-page TIFF needs OpenCV): " + file_path);
+			else if (ext == "tif" || ext == "TIF" || ext == "tiff" || ext == "TIFF") loadTiff(file_path);
+			else throw std::string("Not binary file or multi-page tiff: " + file_path);
 		}
 		inline void release()
 		{

@@ -106,15 +106,23 @@ def test_reference_2d_nr_example_runs_unchanged(tmp_path):
     assert ok.sum() > 0.9 * len(gold)
     assert np.abs(mine[ok][:, 2:4] - gold[ok][:, 2:4]).max() < 1e-4
     assert np.abs(mine[ok, 6] - gold[ok, 6]).max() < 1e-5
-    # strains of the band the fixture holds: fitted from this run's own u, v (within 1e-4 px of the table's), so
-    # they agree with the shipped strains to ~1e-4 px / (20 px * sqrt(n)) -- well below 2e-5
+    # Strain ran on this table's own u, v, ZNCC: recompute it with the oracle from the printed values
+    from oracle import oracle
+    q = np.zeros((tab.shape[0], 25), np.float32)
+    q[:, 0:2], q[:, 2], q[:, 8], q[:, 16] = tab[:, 0:2], tab[:, 2], tab[:, 3], tab[:, 6]
+    oracle.strain(q, 20.0, 5, 0.9, 1, exact=True)
+    # (a ZNCC printed as 0.90000000 may have been just below the threshold: allow a handful of such POIs and their
+    # neighbours to differ)
+    assert ((q[:, 20] == 0) != (tab[:, 10] == 0)).sum() <= 5
+    assert np.percentile(np.abs(q[:, 20:23] - tab[:, 10:13]).max(1), 99) < 2e-7   # 8 printed decimals of u, v
+    # and against the shipped strains, where the neighbourhood is the same as in the shipped run (the shipped table
+    # predates the -4 code, so next to non-converged POIs the neighbour sets differ): the bulk agrees
     band, check = g["band"], g["band_check"]
     idx = {(int(x), int(y)): i for i, (x, y) in enumerate(tab[:, 0:2])}
     sel = np.array([idx[(int(x), int(y))] for x, y in band[:, 0:2]])
     mb = tab[sel]
     conv = check & (band[:, 4] >= 0.9) & (mb[:, 6] >= 0.9)
-    # POIs next to non-converged neighbours (the shipped table predates the -4 code) see a different neighbour set
-    assert np.percentile(np.abs(mb[conv][:, 10:13] - band[conv][:, 5:8]).max(1), 90) < 2e-5
+    assert np.percentile(np.abs(mb[conv][:, 10:13] - band[conv][:, 5:8]).max(1), 50) < 2e-5
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "test_2d_dic_strain")), reason="example binary not built")
@@ -137,3 +145,50 @@ def test_reference_2d_strain_example_runs_unchanged(tmp_path):
     good = check & (q[:, 16] >= 0.9)
     assert np.abs(tab[good][:, 10:13] - gold[good]).max() < 5e-7
     assert (data / "oht_cfrp_4_eyy.csv").exists()
+
+
+def _write_tiff_stack(path, vol):
+    """Minimal little-endian multi-page TIFF: 8-bit grayscale, uncompressed, one strip per page."""
+    import struct
+    nz, ny, nx = vol.shape
+    out = bytearray(b"II*\x00\x00\x00\x00\x00")
+    prev_next_field = 4
+    for z in range(nz):
+        data_off = len(out)
+        out += vol[z].astype(np.uint8).tobytes()
+        if len(out) % 2:
+            out += b"\x00"
+        ifd_off = len(out)
+        struct.pack_into("<I", out, prev_next_field, ifd_off)
+        tags = [(256, 4, 1, nx), (257, 4, 1, ny), (258, 3, 1, 8), (259, 3, 1, 1), (262, 3, 1, 1), (273, 4, 1, data_off),
+                (277, 3, 1, 1), (278, 4, 1, ny), (279, 4, 1, nx * ny)]
+        out += struct.pack("<H", len(tags))
+        for tag, typ, cnt, val in tags:
+            out += struct.pack("<HHI", tag, typ, cnt) + (struct.pack("<HH", val, 0) if typ == 3 else struct.pack("<I", val))
+        prev_next_field = len(out)
+        out += struct.pack("<I", 0)
+    with open(path, "wb") as f:
+        f.write(out)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "test_dvc_strain")), reason="example binary not built")
+def test_reference_dvc_strain_example_runs_unchanged(tmp_path):
+    """examples/test_dvc_strain.cpp: Image3D(.tif) for the dimensions, loadTable3D -> Strain -> saveTable3D."""
+    data = tmp_path / "d:" / "dic_tests" / "dvc"
+    data.mkdir(parents=True)
+    _write_tiff_stack(data / "Torus_def.tif", (np.arange(4 * 6 * 8) % 251).reshape(4, 6, 8))
+    q, gold, check = util.torus_queue()
+    with open(data / "Torus_def_sift_icgn1_r16.csv", "w") as f:
+        f.write(",".join("x,y,z,u,v,w,u0,v0,w0,ZNCC,iteration,convergence,feature,ux,uy,uz,vx,vy,vz,wx,wy,wz,exx,eyy,ezz,exy,eyz,ezx,"
+                         "subset_rx,subset_ry,subset_rz".split(",")) + ",\n")
+        for p in q:
+            f.write("%g,%g,%g,%.8f,%.8f,%.8f,0,0,0,%.8f,5,0.0001,0," % (p[0], p[1], p[2], p[3], p[7], p[11], p[18])
+                    + "0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,16,16,16,\n")
+    out = subprocess.run([os.path.join(BIN, "test_dvc_strain")], cwd=tmp_path, stdin=subprocess.DEVNULL,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    _, tab = _read_table(data / "Torus_def_sift_icgn1_r16.csv")
+    assert tab.shape[0] == q.shape[0] and np.array_equal(tab[:, 0:3], q[:, 0:3])
+    good = check & (q[:, 18] >= 0.9)
+    assert np.abs(tab[good][:, 22:28] - gold[good]).max() < 5e-6
+    assert (data / "Torus_def_strain_r30_time.csv").exists()

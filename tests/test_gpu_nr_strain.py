@@ -194,7 +194,7 @@ def test_strain3d_random(engine):
         s.compute(a)
         oracle.strain(b, radius, k, 0.9, approx, exact=True)
         assert np.array_equal(a[:, 22:28] == 0, b[:, 22:28] == 0)
-        assert (b[:, 22] != 0).sum() > 1000
+        assert (b[:, 22] != 0).sum() > (1000 if radius > 20 else 50)
         assert np.abs(a[:, 22:28] - b[:, 22:28]).max() < 2e-6
 
 
