@@ -323,16 +323,24 @@ def run_ours(args):
     poi_bytes = q0.nbytes
     eng.use_own_stream()
 
+    phases = []  # per-step host-side phase times (ms): set_images, POI buffer reset, FFTCC call, ICGN call
+
     def step_e2e():
         if world == 1:
             # exactly what a caller of the reference API does: setImages, FFTCC compute, prepare, ICGN compute
             if kind == "2d":
+                t = [time.perf_counter()]
                 eng._ck(eng._lib.ocb_set_images_2d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[1], ref.shape[0], 0))
+                t.append(time.perf_counter())
                 h_q.copy_(h_q0)
                 qn = h_q.numpy()
+                t.append(time.perf_counter())
                 eng.fftcc2d(qn, r, r)
+                t.append(time.perf_counter())
                 eng.icgn2d_prepare()
                 (eng.icgn2d1 if cfg["order"] == 1 else eng.icgn2d2)(qn, r, r, cfg["conv"], cfg["stop"])
+                t.append(time.perf_counter())
+                phases.append([1e3 * (b - a) for a, b in zip(t[:-1], t[1:])])
             else:
                 eng._ck(eng._lib.ocb_set_images_3d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[2], ref.shape[1], ref.shape[0]))
                 h_q.copy_(h_q0)
@@ -382,6 +390,10 @@ def run_ours(args):
     e2e_sorted = sorted(1e3 * t for t in e2e_times)
     e2e_spread = {"min": e2e_sorted[0], "median": e2e_sorted[len(e2e_sorted) // 2], "max": e2e_sorted[-1],
                   "argmax_step": int(np.argmax(e2e_times))}
+    if phases:
+        ph = phases[-len(e2e_times):]
+        e2e_spread["phases_ms_of_slowest_step[set_images,poi_reset,fftcc,icgn]"] = ph[int(np.argmax(e2e_times))]
+        e2e_spread["phases_ms_median"] = [float(np.median([p[i] for p in ph])) for i in range(4)]
     if world == 1:
         h2d, d2h = img_bytes + 2 * poi_bytes, 2 * poi_bytes
     else:
