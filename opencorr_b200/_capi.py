@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libopencorr_b200.so")
+LIB_PATH = os.environ.get("OCB_LIB_PATH") or os.path.join(_HERE, "lib", "libopencorr_b200.so")  # override: A/B builds
 
 OCB_OK = 0
 OCB_ERR_CUDA = -1

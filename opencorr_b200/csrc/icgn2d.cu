@@ -33,6 +33,10 @@
 
 namespace ocb {
 
+#ifndef ICGN2D_UNROLL
+#define ICGN2D_UNROLL 3
+#endif
+constexpr int ICGN2D_ROW_UNROLL = ICGN2D_UNROLL; // rows of the fast sampling loop in flight per lane
 constexpr int ICGN2D_TILE_MARGIN = 1; // slack (pixels) around subset+support in the target tile
 // TMA tile loads need the innermost coordinate 16-byte aligned (x multiple of 4 floats; measured: an
 // unaligned x raises 'illegal instruction'), so tile origins are rounded down to a multiple of 4 and
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					}
 				}
 				const float* tbase = T - (ty0 + 1) * TW - (tx0 + 1);
-#pragma unroll 3
+#pragma unroll ICGN2D_ROW_UNROLL
 				for (int r = 0; r < sh; r++) {
 					float X, Y;
 					if constexpr (NP == 6) {
@@ -725,6 +729,10 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 		if (warps > best_warps) { best_warps = warps; best_wpb = wpb; }
 	}
 	if (best_wpb == 0) return -1;
+	if (const char* cap = getenv("OCB_ICGN2D_MAX_WARPS")) { // tuning knob: cap the resident warps per SM
+		const int c = atoi(cap);
+		if (c >= 1 && c < best_warps) { best_wpb = 1; best_warps = c; }
+	}
 	const size_t smem = per_warp * best_wpb;
 	CUtensorMap tm_ref, tm_tar;
 	memset(&tm_ref, 0, sizeof(tm_ref));
