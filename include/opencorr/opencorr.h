@@ -843,6 +843,222 @@ namespace opencorr
 		}
 	};
 
+	// ---------------------------------------------------------------- EpipolarSearch
+	// Camera parameters, reference src/oc_calibration.h:25-45
+	union CameraIntrinsics
+	{
+		struct
+		{
+			float fx, fy, fs;
+			float cx, cy;
+			float k1, k2, k3, k4, k5, k6;
+			float p1, p2;
+		};
+		float cam_i[13];
+	};
+
+	union CameraExtrinsics
+	{
+		struct
+		{
+			float tx, ty, tz;
+			float rx, ry, rz;
+		};
+		float cam_e[6];
+	};
+
+	// The part of Calibration (reference src/oc_calibration.h:47-98, src/oc_calibration.cpp:21-88) that EpipolarSearch reads:
+	// intrinsic / rotation / translation / projection matrices, row-major plain arrays instead of Eigen types.
+	// Lens-distortion correction (prepare(height, width), undistort) belongs to the stereo-reconstruction module, which is
+	// out of scope here.
+	class Calibration
+	{
+	public:
+		CameraIntrinsics intrinsics;
+		CameraExtrinsics extrinsics;
+		float intrinsic_matrix[3][3];
+		float rotation_matrix[3][3];
+		float translation_vector[3];
+		float projection_matrix[3][4];
+
+		Calibration()
+		{
+			std::fill(std::begin(intrinsics.cam_i), std::end(intrinsics.cam_i), 0.f);
+			std::fill(std::begin(extrinsics.cam_e), std::end(extrinsics.cam_e), 0.f);
+		}
+		Calibration(CameraIntrinsics& intrinsics, CameraExtrinsics& extrinsics) { updateCalibration(intrinsics, extrinsics); }
+		~Calibration() {}
+
+		void updateIntrinsicMatrix() // src/oc_calibration.cpp:36-48
+		{
+			const float k[3][3] = { { intrinsics.fx, intrinsics.fs, intrinsics.cx }, { 0.f, intrinsics.fy, intrinsics.cy }, { 0.f, 0.f, 1.f } };
+			std::memcpy(intrinsic_matrix, k, sizeof(k));
+			if (intrinsics.fx == 1.f && intrinsics.fy == 1.f && intrinsics.fs == 0.f && intrinsics.cx == 0.f && intrinsics.cy == 0.f)
+				throw std::string("Null intrinsics matrix");
+		}
+		void updateRotationMatrix() // src/oc_calibration.cpp:50-60 (Eigen::AngleAxisf::toRotationMatrix)
+		{
+			const float rx = extrinsics.rx, ry = extrinsics.ry, rz = extrinsics.rz;
+			const float theta = std::sqrt(rx * rx + ry * ry + rz * rz);
+			float x = rx, y = ry, z = rz;
+			if (theta > 0.f) { x /= theta; y /= theta; z /= theta; }
+			const float c = std::cos(theta), s = std::sin(theta), t = 1.f - c;
+			const float r[3][3] = { { t * x * x + c, t * x * y - s * z, t * x * z + s * y },
+				{ t * x * y + s * z, t * y * y + c, t * y * z - s * x },
+				{ t * x * z - s * y, t * y * z + s * x, t * z * z + c } };
+			std::memcpy(rotation_matrix, r, sizeof(r));
+		}
+		void updateTranslationVector()
+		{
+			translation_vector[0] = extrinsics.tx;
+			translation_vector[1] = extrinsics.ty;
+			translation_vector[2] = extrinsics.tz;
+		}
+		void updateProjectionMatrix() // K [R | t], src/oc_calibration.cpp:69-77
+		{
+			for (int i = 0; i < 3; i++)
+				for (int j = 0; j < 4; j++) {
+					float v = 0.f;
+					for (int k = 0; k < 3; k++) v += intrinsic_matrix[i][k] * (j < 3 ? rotation_matrix[k][j] : translation_vector[k]);
+					projection_matrix[i][j] = v;
+				}
+		}
+		void updateMatrices()
+		{
+			updateIntrinsicMatrix();
+			updateRotationMatrix();
+			updateTranslationVector();
+			updateProjectionMatrix();
+		}
+		void updateCalibration(CameraIntrinsics& intrinsics, CameraExtrinsics& extrinsics)
+		{
+			this->intrinsics = intrinsics;
+			this->extrinsics = extrinsics;
+			updateMatrices();
+		}
+		void clear()
+		{
+			std::fill(std::begin(intrinsics.cam_i), std::end(intrinsics.cam_i), 0.f);
+			std::fill(std::begin(extrinsics.cam_e), std::end(extrinsics.cam_e), 0.f);
+		}
+	};
+
+	// EpipolarSearch, reference src/oc_epipolar_search.h:30-63 / .cpp:21-205.  compute(queue) runs the candidate sweep of ALL
+	// POIs as one GPU batch (ocb_epipolar_search2d) instead of one POI at a time.
+	class EpipolarSearch : public DIC
+	{
+	protected:
+		int search_radius = 0;
+		int search_step = 1;
+		Calibration view1_cam;
+		Calibration view2_cam;
+		float fundamental_matrix[9]; // row-major
+		Point2D parallax;
+		float parallax_x[3] = { 0.f, 0.f, 0.f }, parallax_y[3] = { 0.f, 0.f, 0.f };
+
+		static void inverse3(const float m[3][3], float inv[3][3])
+		{
+			const double a = m[0][0], b = m[0][1], c = m[0][2], d = m[1][0], e = m[1][1], f = m[1][2], g = m[2][0], h = m[2][1], i = m[2][2];
+			const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+			const double r[3][3] = { { e * i - f * h, c * h - b * i, b * f - c * e }, { f * g - d * i, a * i - c * g, c * d - a * f }, { d * h - e * g, b * g - a * h, a * e - b * d } };
+			for (int p = 0; p < 3; p++)
+				for (int q = 0; q < 3; q++) inv[p][q] = (float)(r[p][q] / det);
+		}
+		static void matmul3(const float a[3][3], const float b[3][3], float c[3][3])
+		{
+			for (int i = 0; i < 3; i++)
+				for (int j = 0; j < 3; j++) c[i][j] = a[i][0] * b[0][j] + a[i][1] * b[1][j] + a[i][2] * b[2][j];
+		}
+
+	public:
+		std::unique_ptr<ICGN2D1> icgn1;
+
+		EpipolarSearch(Calibration& view1_cam, Calibration& view2_cam, int thread_number)
+		{
+			this->view1_cam = view1_cam;
+			this->view2_cam = view2_cam;
+			this->thread_number = thread_number;
+			std::fill(std::begin(fundamental_matrix), std::end(fundamental_matrix), 0.f);
+		}
+		~EpipolarSearch() { destoryICGN(); }
+
+		int getSearchRadius() const { return search_radius; }
+		int getSearchStep() const { return search_step; }
+		void setSearch(int search_radius, int search_step)
+		{
+			if (search_radius < search_step) throw std::string("Search radius is less than search step");
+			this->search_radius = search_radius;
+			this->search_step = search_step;
+		}
+		void createICGN(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition)
+		{
+			icgn1 = std::make_unique<ICGN2D1>(subset_radius_x, subset_radius_y, conv_criterion, stop_condition, thread_number);
+			icgn_conv = conv_criterion;
+			icgn_stop = stop_condition;
+		}
+		void prepareICGN()
+		{
+			icgn1->setImages(*ref_img, *tar_img);
+			icgn1->prepare();
+		}
+		void destoryICGN()
+		{
+			if (icgn1 != nullptr) icgn1.reset();
+		}
+		void setParallax(Point2D parallax)
+		{
+			this->parallax = parallax;
+			parallax_x[0] = 0; parallax_x[1] = 0; parallax_x[2] = parallax.x;
+			parallax_y[0] = 0; parallax_y[1] = 0; parallax_y[2] = parallax.y;
+		}
+		void setParallax(float coefficient_x[3], float coefficient_y[3])
+		{
+			for (int i = 0; i < 3; i++) { parallax_x[i] = coefficient_x[i]; parallax_y[i] = coefficient_y[i]; }
+		}
+		void updateCameras(Calibration& view1_cam, Calibration& view2_cam)
+		{
+			this->view1_cam = view1_cam;
+			this->view2_cam = view2_cam;
+		}
+		void updateFundementalMatrix() // src/oc_epipolar_search.cpp:110-126
+		{
+			float k2_inv[3][3], k2_inv_t[3][3], k1_inv[3][3], e[3][3], tmp[3][3], f[3][3];
+			inverse3(view2_cam.intrinsic_matrix, k2_inv);
+			for (int i = 0; i < 3; i++)
+				for (int j = 0; j < 3; j++) k2_inv_t[i][j] = k2_inv[j][i];
+			const float* t = view2_cam.translation_vector;
+			const float t_anti[3][3] = { { 0.f, -t[2], t[1] }, { t[2], 0.f, -t[0] }, { -t[1], t[0], 0.f } };
+			matmul3(t_anti, view2_cam.rotation_matrix, e);
+			inverse3(view1_cam.intrinsic_matrix, k1_inv);
+			matmul3(k2_inv_t, e, tmp);
+			matmul3(tmp, k1_inv, f);
+			for (int i = 0; i < 3; i++)
+				for (int j = 0; j < 3; j++) fundamental_matrix[3 * i + j] = f[i][j];
+		}
+		void prepare()
+		{
+			view1_cam.updateMatrices();
+			view2_cam.updateMatrices();
+			updateFundementalMatrix();
+			prepareICGN();
+		}
+		void compute(POI2D* poi) { run(poi, 1); }
+		void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
+
+	private:
+		float icgn_conv = 0.001f, icgn_stop = 10.f;
+		void run(POI2D* p, size_t n)
+		{
+			if (icgn1 == nullptr) throw std::string("opencorr_b200: createICGN() and prepare() must be called before compute()");
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.useImages(ref_img, tar_img);
+			if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+			e.check(ocb_epipolar_search2d(e.context(), p, n, fundamental_matrix, parallax_x, parallax_y, search_radius, search_step, icgn1->subset_radius_x,
+				icgn1->subset_radius_y, icgn_conv, icgn_stop));
+		}
+	};
+
 	class ICGN3D1 : public DVC
 	{
 	private:

@@ -133,6 +133,18 @@ int ocb_nr2d_prepare(ocb_ctx* ctx);
 int ocb_nr2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, float stop);
 int ocb_nr2d1_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop);
 
+/* ---- EpipolarSearch: EpipolarSearch::compute(std::vector<POI2D>&) src/oc_epipolar_search.cpp:197-205
+ *      (per POI :133-195) as one batch: every POI spawns its candidates along the epipolar line of the secondary view
+ *      (centre + every search_step pixels in x below search_radius, both directions), ICGN2D1(rx, ry, conv, stop) registers
+ *      all of them, the candidate with the highest ZNCC replaces the POI's deformation and result.
+ *      fundamental: the 3x3 fundamental matrix, row-major (updateFundementalMatrix :110-126); parallax_x/_y: the three
+ *      coefficients of setParallax(float[3], float[3]) (setParallax(Point2D p) = {0, 0, p.x}, {0, 0, p.y}) -- host pointers in
+ *      both variants.  Images = primary / secondary view (setImages), after ocb_icgn2d_prepare (prepareICGN :63-67). */
+int ocb_epipolar_search2d(ocb_ctx* ctx, void* poi2d, size_t n, const float* fundamental, const float* parallax_x, const float* parallax_y,
+	int search_radius, int search_step, int rx, int ry, float conv, float stop);
+int ocb_epipolar_search2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, const float* fundamental, const float* parallax_x, const float* parallax_y,
+	int search_radius, int search_step, int rx, int ry, float conv, float stop);
+
 /* ---- Strain post-processing of a POI queue: Strain::prepare + Strain::compute(queue),
  *      src/oc_strain.cpp:100-111,150-156,239-250 (POI2D; per POI :158-237) and :476-487 (POI3D; per POI :373-474).
  *      radius = subregion_radius, min_neighbors = neighbor_number_min (constructor :32-36), zncc_threshold = setZnccThreshold

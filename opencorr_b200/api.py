@@ -170,6 +170,15 @@ class Engine:
         self._ck(self._lib.ocb_iclm2d(self._ctx, int(order), _vp(q), q.shape[0], rx, ry, conv, stop,
                                       float(damping[0]), float(damping[1]), float(damping[2])))
 
+    def epipolar_search2d(self, q, fundamental, parallax_x, parallax_y, search_radius, search_step, rx, ry, conv, stop):
+        """EpipolarSearch::compute(queue) (reference src/oc_epipolar_search.cpp:133-205) as one batch."""
+        _check_queue(q, POI2D_FLOATS)
+        f = np.ascontiguousarray(fundamental, dtype=np.float32).reshape(9)
+        ax = np.ascontiguousarray(parallax_x, dtype=np.float32).reshape(3)
+        ay = np.ascontiguousarray(parallax_y, dtype=np.float32).reshape(3)
+        self._ck(self._lib.ocb_epipolar_search2d(self._ctx, _vp(q), q.shape[0], _vp(f), _vp(ax), _vp(ay), int(search_radius),
+                                                 int(search_step), rx, ry, conv, stop))
+
     def strain(self, q, radius, min_neighbors, zncc_threshold=0.9, approximation=1):
         """Strain::prepare + compute(queue) (reference src/oc_strain.cpp) on a POI2D [n,25] or POI3D [n,31] queue."""
         if q.ndim == 2 and q.shape[1] == POI3D_FLOATS:
@@ -383,6 +392,100 @@ class NR2D1(_DIC):
         return poi_queue
 
     setIteration = set_iteration
+
+
+class Calibration:
+    """The part of the reference's Calibration (src/oc_calibration.h:25-98, .cpp:36-88) EpipolarSearch needs: the
+    intrinsic matrix, the rotation matrix from the rotation vector (rx, ry, rz) and the translation vector, float32."""
+
+    def __init__(self, fx, fy, fs, cx, cy, tx=0.0, ty=0.0, tz=0.0, rx=0.0, ry=0.0, rz=0.0):
+        self.intrinsics = dict(fx=fx, fy=fy, fs=fs, cx=cx, cy=cy)
+        self.extrinsics = dict(tx=tx, ty=ty, tz=tz, rx=rx, ry=ry, rz=rz)
+        self.update_matrices()
+
+    def update_matrices(self):
+        f32 = np.float32
+        i, e = self.intrinsics, self.extrinsics
+        self.intrinsic_matrix = np.array([[i["fx"], i["fs"], i["cx"]], [0, i["fy"], i["cy"]], [0, 0, 1]], f32)
+        v = np.array([e["rx"], e["ry"], e["rz"]], f32)
+        th = f32(np.linalg.norm(v))
+        if th == 0:
+            self.rotation_matrix = np.eye(3, dtype=f32)
+        else:  # Eigen::AngleAxisf::toRotationMatrix, src/oc_calibration.cpp:50-60
+            x, y, z = v / th
+            c, s = f32(np.cos(th)), f32(np.sin(th))
+            t = f32(1) - c
+            self.rotation_matrix = np.array([[t * x * x + c, t * x * y - s * z, t * x * z + s * y],
+                                             [t * x * y + s * z, t * y * y + c, t * y * z - s * x],
+                                             [t * x * z - s * y, t * y * z + s * x, t * z * z + c]], f32)
+        self.translation_vector = np.array([e["tx"], e["ty"], e["tz"]], f32)
+
+    updateMatrices = update_matrices
+
+
+class EpipolarSearch(_DIC):
+    """EpipolarSearch(Calibration& view1_cam, Calibration& view2_cam, int thread_number), reference
+    src/oc_epipolar_search.h:30-63.  set_images(view1, view2); the candidate sweep of all POIs runs as one GPU batch."""
+
+    def __init__(self, view1_cam, view2_cam, thread_number=0, engine=None):
+        super().__init__(0, 0, thread_number, engine)
+        self.view1_cam, self.view2_cam = view1_cam, view2_cam
+        self.search_radius, self.search_step = 0, 1
+        self.parallax_x = np.zeros(3, np.float32)
+        self.parallax_y = np.zeros(3, np.float32)
+        self.fundamental_matrix = None
+        self._icgn = None
+
+    def set_search(self, search_radius, search_step):
+        if search_radius < search_step:
+            raise ValueError("Search radius is less than search step")
+        self.search_radius, self.search_step = int(search_radius), int(search_step)
+
+    def create_icgn(self, subset_radius_x, subset_radius_y, conv_criterion, stop_condition):
+        self._icgn = (int(subset_radius_x), int(subset_radius_y), float(conv_criterion), float(stop_condition))
+
+    def set_parallax(self, *args):
+        """set_parallax((px, py))  or  set_parallax(coefficient_x[3], coefficient_y[3])  (src/oc_epipolar_search.cpp:74-95)."""
+        if len(args) == 1:
+            self.parallax_x = np.array([0, 0, args[0][0]], np.float32)
+            self.parallax_y = np.array([0, 0, args[0][1]], np.float32)
+        else:
+            self.parallax_x = np.asarray(args[0], np.float32).reshape(3)
+            self.parallax_y = np.asarray(args[1], np.float32).reshape(3)
+
+    def update_cameras(self, view1_cam, view2_cam):
+        self.view1_cam, self.view2_cam = view1_cam, view2_cam
+
+    def update_fundamental_matrix(self):
+        """src/oc_epipolar_search.cpp:110-126, float32."""
+        f32 = np.float32
+        c1, c2 = self.view1_cam, self.view2_cam
+        t = c2.translation_vector
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]], f32)
+        e = (tx @ c2.rotation_matrix).astype(f32)
+        k2_inv_t = np.linalg.inv(c2.intrinsic_matrix.astype(np.float64)).T.astype(f32)
+        k1_inv = np.linalg.inv(c1.intrinsic_matrix.astype(np.float64)).astype(f32)
+        self.fundamental_matrix = (k2_inv_t @ e @ k1_inv).astype(f32)
+
+    def prepare(self):
+        self.view1_cam.update_matrices()
+        self.view2_cam.update_matrices()
+        self.update_fundamental_matrix()
+        self.engine.icgn2d_prepare()
+
+    def compute(self, poi_queue):
+        if self._icgn is None or self.fundamental_matrix is None:
+            raise _capi.OpenCorrB200Error(_capi.OCB_ERR_STATE, "EpipolarSearch: create_icgn() and prepare() must be called before compute()")
+        rx, ry, conv, stop = self._icgn
+        self.engine.epipolar_search2d(poi_queue, self.fundamental_matrix, self.parallax_x, self.parallax_y, self.search_radius,
+                                      self.search_step, rx, ry, conv, stop)
+        return poi_queue
+
+    setSearch = set_search
+    createICGN = create_icgn
+    setParallax = set_parallax
+    updateCameras = update_cameras
+    updateFundementalMatrix = update_fundamental_matrix
 
 
 class Strain:

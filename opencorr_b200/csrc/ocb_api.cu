@@ -86,6 +86,8 @@ struct ocb_ctx {
 	size_t d_u8_bytes = 0;
 	float* d_off = nullptr; // centre offsets (2 floats per POI)
 	size_t d_off_bytes = 0;
+	float* d_cand = nullptr; // EpipolarSearch candidate queue
+	size_t d_cand_bytes = 0;
 	void* d_strain_ws = nullptr; // Strain: sort keys / compact neighbour arrays / cub scratch
 	size_t d_strain_ws_bytes = 0;
 };
@@ -213,6 +215,7 @@ void ocb_destroy(ocb_ctx* ctx) {
 	cudaFree(ctx->d_poi);
 	cudaFree(ctx->d_off);
 	cudaFree(ctx->d_strain_ws);
+	cudaFree(ctx->d_cand);
 	cudaFree(ctx->d_u8);
 	cudaFree(ctx->d_counter);
 	cudaStreamDestroy(ctx->own_stream);
@@ -628,6 +631,57 @@ int ocb_nr2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, f
 	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
 	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
 	if ((rc = ocb_nr2d1_dev(ctx, ctx->d_poi, n, rx, ry, conv, stop))) return rc;
+	return unstage_pois(ctx, poi2d, bytes);
+}
+
+// ---- EpipolarSearch candidate sweep ----------------------------------------
+int ocb_epipolar_search2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, const float* fundamental, const float* parallax_x, const float* parallax_y,
+	int search_radius, int search_step, int rx, int ry, float conv, float stop) {
+	if (!ctx || (!d_poi2d && n) || !fundamental || !parallax_x || !parallax_y || rx < 1 || ry < 1)
+		return set_error(ctx, OCB_ERR_ARG, "epipolar_search2d: bad arguments");
+	if (search_step < 1 || search_radius < search_step)
+		return set_error(ctx, OCB_ERR_ARG, "epipolar_search2d: search radius is less than search step"); // EpipolarSearch::setSearch, src/oc_epipolar_search.cpp:44-53
+	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "epipolar_search2d: images not set");
+	if (!ctx->prepared2) return set_error(ctx, OCB_ERR_STATE, "epipolar_search2d: prepare() has not been called since setImages()");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	const int slots = ocb::epipolar_slots(search_radius, search_step);
+	// candidates of a block of POIs at a time: at most ~2^22 records (420 MB) in flight
+	size_t block = ((size_t)1 << 22) / (size_t)slots;
+	if (block < 1) block = 1;
+	if (block > n) block = n;
+	const size_t need = block * (size_t)slots * OCB_POI2D_FLOATS * sizeof(float);
+	if (need > ctx->d_cand_bytes) {
+		if (ctx->d_cand) cudaFree(ctx->d_cand);
+		ctx->d_cand = nullptr;
+		ctx->d_cand_bytes = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->d_cand, need));
+		ctx->d_cand_bytes = need;
+	}
+	for (size_t p0 = 0; p0 < n; p0 += block) {
+		const size_t nb = n - p0 < block ? n - p0 : block;
+		ocb::epipolar_candidates_launch((const float*)d_poi2d, p0, nb, fundamental, parallax_x, parallax_y, search_radius, search_step, rx, ry, ctx->img2.w,
+			ctx->img2.h, slots, ctx->d_cand, ctx->sm_count, ctx->stream);
+		OCB_CUDA(ctx, cudaGetLastError());
+		ctx->launches++;
+		int rc = icgn2d_dev(ctx, 6, ctx->d_cand, nb * (size_t)slots, rx, ry, conv, stop);
+		if (rc) return rc;
+		ocb::epipolar_select_launch((float*)d_poi2d, p0, nb, slots, ctx->d_cand, ctx->sm_count, ctx->stream);
+		OCB_CUDA(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	return OCB_OK;
+}
+
+int ocb_epipolar_search2d(ocb_ctx* ctx, void* poi2d, size_t n, const float* fundamental, const float* parallax_x, const float* parallax_y,
+	int search_radius, int search_step, int rx, int ry, float conv, float stop) {
+	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "epipolar_search2d: bad arguments");
+	if (n == 0) return OCB_OK;
+	if (ensure_device(ctx)) return OCB_ERR_CUDA;
+	int rc;
+	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
+	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
+	if ((rc = ocb_epipolar_search2d_dev(ctx, ctx->d_poi, n, fundamental, parallax_x, parallax_y, search_radius, search_step, rx, ry, conv, stop))) return rc;
 	return unstage_pois(ctx, poi2d, bytes);
 }
 

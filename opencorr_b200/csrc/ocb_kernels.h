@@ -38,6 +38,12 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 // nr2d.cu
 int nr2d1_launch(const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count, size_t smem_optin,
 	int* d_counter, cudaStream_t stream, cudaError_t* err);
+// epipolar.cu
+int epipolar_slots(int search_radius, int search_step);
+void epipolar_candidates_launch(const float* d_pois, size_t poi0, size_t n_poi, const float* fundamental, const float* parallax_x,
+	const float* parallax_y, int search_radius, int search_step, int rx, int ry, int w, int h, int slots, float* d_cand, int sm_count,
+	cudaStream_t stream);
+void epipolar_select_launch(float* d_pois, size_t poi0, size_t n_poi, int slots, const float* d_cand, int sm_count, cudaStream_t stream);
 // strain.cu
 size_t strain_workspace_bytes(size_t n);
 int strain_launch(int dim, float* d_pois, size_t n, float radius, int k_min, float zncc_threshold, int approximation, long long only, void* workspace,

@@ -471,6 +471,13 @@ inline void warp3d1_get(const T* W, T* p) { // :416-433
 	p[8] = W[11]; p[9] = W[8]; p[10] = W[9]; p[11] = W[10] - (T)1;
 }
 
+// Pinning aid, OFF by default: the result tables shipped under examples/ were written before the "-4 = not converged"
+// code existed (src/oc_icgn.cpp:329-332 is newer than the tables), so rows that hit the iteration limit keep their
+// ZNCC there -- and EpipolarSearch, which ranks candidates by ZNCC after at most 5 iterations, picked candidates the
+// current source would now discard.  With this flag the 2D IC-GN restatement skips that one rule so that the
+// EpipolarSearch -> ICGN2D2 pipeline can be checked against examples/3d_dic/*_reconstruction_epipolar.csv.
+static bool g_legacy_no_m4 = false;
+
 // Per-thread scratch for 2D IC-GN (the reference's ICGN2D1_/ICGN2D2_, src/oc_icgn.h:30-43,85-98)
 template <class T>
 struct Scratch2D {
@@ -656,7 +663,7 @@ void icgn2d_poi(const Ctx2D& c, float* poi, int rx, int ry, float conv_criterion
 	poi[P2_CONV] = (float)dp_norm_max;
 	poi[P2_RX] = (float)rx;
 	poi[P2_RY] = (float)ry;
-	if (poi[P2_CONV] >= conv_criterion && poi[P2_ITER] >= stop_condition) poi[P2_ZNCC] = -4.f;
+	if (!g_legacy_no_m4 && poi[P2_CONV] >= conv_criterion && poi[P2_ITER] >= stop_condition) poi[P2_ZNCC] = -4.f;
 	if (is_nan(poi[P2_ZNCC]) || is_nan(def[D2_U]) || is_nan(def[D2_V])) {
 		def[D2_U] = poi[P2_U0];
 		def[D2_V] = poi[P2_V0];
@@ -1321,6 +1328,71 @@ void run_strain(float* pois, long n, float radius, int k_min, float zncc_thresho
 			for (int k = 0; k < (D == 2 ? 3 : 6); k++) pois[i * NF + L::STRAIN + k] = out[(size_t)i * (D == 2 ? 3 : 6) + k];
 }
 
+// ----------------------------------------------------------------------------------------------
+// EpipolarSearch::compute(POI2D*), src/oc_epipolar_search.cpp:133-195: candidate POIs are spawned along the
+// epipolar line of the secondary view (centre + every `search_step` pixels in x up to `search_radius`, both
+// directions, kept when the subset stays inside the image), ICGN2D1 runs on each, the candidate with the highest
+// ZNCC wins (std::sort by ZNCC descending; ties -- unspecified there -- go to the earlier candidate here).
+// fundamental: 3x3 row-major (updateFundementalMatrix :110-126); parallax_x/y: the linear parallax model (:74-95).
+// ----------------------------------------------------------------------------------------------
+struct EpiCandidate { float u, v; };
+
+inline void epipolar_candidates(const Ctx2D& c, const float* poi, const float* F, const float* parallax_x, const float* parallax_y,
+	int search_radius, int search_step, int rx, int ry, std::vector<EpiCandidate>& out) {
+	out.clear();
+	const float px = poi[P2_X], py = poi[P2_Y], pu = poi[P2_DEF + D2_U], pv = poi[P2_DEF + D2_V];
+	// :136-137 (int(width / 2) is an integer division)
+	const float par_x = parallax_x[0] * (px - (float)(int)(c.w / 2)) + parallax_x[1] * (py - (float)(int)(c.h / 2)) + parallax_x[2];
+	const float par_y = parallax_y[0] * (px - (float)(int)(c.w / 2)) + parallax_y[1] * (py - (float)(int)(c.h / 2)) + parallax_y[2];
+	const float v1[3] = { px + pu, py + pv, 1.f }; // :140-141
+	float e[3];
+	for (int i = 0; i < 3; i++) e[i] = (F[i * 3] * v1[0] + F[i * 3 + 1] * v1[1]) + F[i * 3 + 2] * v1[2]; // :144
+	const float line_slope = -e[0] / e[1];
+	const float line_intercept = -e[2] / e[1];
+	const int x_view2 = (int)((line_slope * (py + pv + par_y - line_intercept) + px + pu + par_x) / (line_slope * line_slope + 1)); // :147
+	const int y_view2 = (int)(line_slope * x_view2 + line_intercept);
+	out.push_back({ (float)x_view2 - px, (float)y_view2 - py }); // :151-155 (centre: no border test)
+	for (int i = search_step; i < search_radius; i += search_step) { // :159-182
+		for (int sgn = 1; sgn >= -1; sgn -= 2) {
+			const int x_trial = x_view2 + sgn * i;
+			const int y_trial = (int)(line_slope * x_trial + line_intercept);
+			if (x_trial - rx > 0 && x_trial + rx < c.w - 1 && y_trial - ry > 0 && y_trial + ry < c.h - 1)
+				out.push_back({ (float)x_trial - px, (float)y_trial - py });
+		}
+	}
+}
+
+template <class T>
+void run_epipolar(const Ctx2D& c, float* pois, long n, const float* F, const float* parallax_x, const float* parallax_y, int search_radius,
+	int search_step, int rx, int ry, float conv, float stop) {
+#pragma omp parallel num_threads(c.threads)
+	{
+		Scratch2D<T> s;
+		std::vector<EpiCandidate> cand;
+		float q[P2_N], best[P2_N];
+#pragma omp for schedule(dynamic, 4)
+		for (long i = 0; i < n; i++) {
+			float* poi = pois + i * P2_N;
+			epipolar_candidates(c, poi, F, parallax_x, parallax_y, search_radius, search_step, rx, ry, cand);
+			bool have = false;
+			for (const EpiCandidate& k : cand) {
+				for (int j = 0; j < P2_N; j++) q[j] = 0.f; // POI2D current_poi(poi->x, poi->y): everything else cleared (:152)
+				q[P2_X] = poi[P2_X];
+				q[P2_Y] = poi[P2_Y];
+				q[P2_DEF + D2_U] = k.u;
+				q[P2_DEF + D2_V] = k.v;
+				icgn2d_poi<T, 6>(c, q, rx, ry, conv, stop, s);
+				if (!have || q[P2_ZNCC] > best[P2_ZNCC]) {
+					for (int j = 0; j < P2_N; j++) best[j] = q[j];
+					have = true;
+				}
+			}
+			for (int j = 0; j < 12; j++) poi[P2_DEF + j] = best[P2_DEF + j]; // poi->deformation = ... (:193)
+			for (int j = P2_U0; j <= P2_FEAT; j++) poi[j] = best[j];          // poi->result = ... (:194)
+		}
+	}
+}
+
 } // namespace
 
 // ----------------------------------------------------------------------------------------------
@@ -1457,6 +1529,15 @@ int oco_icgn3d1(void* h, float* pois, long n, int rx, int ry, int rz, float conv
 	if (exact) run_icgn3d1<double>(*c, pois, n, rx, ry, rz, conv, stop); else run_icgn3d1<float>(*c, pois, n, rx, ry, rz, conv, stop);
 	return 0;
 }
+// EpipolarSearch::compute(queue), src/oc_epipolar_search.cpp:197-205 (needs oco_prepare2d, like prepareICGN :63-67)
+int oco_epipolar_search(void* h, float* pois, long n, const float* fundamental, const float* parallax_x, const float* parallax_y, int search_radius,
+	int search_step, int rx, int ry, float conv, float stop, int exact) {
+	Ctx2D* c = (Ctx2D*)h;
+	if (!c->prepared || search_step < 1) return -1;
+	if (exact) run_epipolar<double>(*c, pois, n, fundamental, parallax_x, parallax_y, search_radius, search_step, rx, ry, conv, stop);
+	else run_epipolar<float>(*c, pois, n, fundamental, parallax_x, parallax_y, search_radius, search_step, rx, ry, conv, stop);
+	return 0;
+}
 // Strain::prepare + Strain::compute(queue) on POI2D (dim 2) / POI3D (dim 3) records, src/oc_strain.cpp:100-111,239-250,476-487.
 // approximation: 1 Cauchy, 2 Green (setApproximation); zncc_threshold default 0.9 (:38).
 int oco_strain(float* pois, long n, int dim, float radius, int min_neighbors, float zncc_threshold, int approximation, int threads, int exact) {
@@ -1471,6 +1552,7 @@ int oco_strain(float* pois, long n, int dim, float radius, int min_neighbors, fl
 	}
 	return 0;
 }
+void oco_set_legacy_no_minus4(int on) { g_legacy_no_m4 = on != 0; }
 int oco_max_threads(void) { return omp_get_num_procs(); }
 
 } // extern "C"

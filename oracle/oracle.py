@@ -66,6 +66,9 @@ def lib():
         L.oco_icgn3d1.restype = ctypes.c_int
         L.oco_icgn3d1.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   ctypes.c_float, ctypes.c_float, ctypes.c_int]
+        L.oco_epipolar_search.restype = ctypes.c_int
+        L.oco_epipolar_search.argtypes = [ctypes.c_void_p, _f32p, ctypes.c_long, _f32p, _f32p, _f32p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int]
         L.oco_strain.restype = ctypes.c_int
         L.oco_strain.argtypes = [_f32p, ctypes.c_long, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float,
                                  ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -80,6 +83,11 @@ def _p(a):
 
 def _c32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def set_legacy_no_minus4(on):
+    """Pinning aid: drop the '-4 = not converged' rule of 2D IC-GN (the shipped tables predate it); OFF by default."""
+    lib().oco_set_legacy_no_minus4(int(bool(on)))
 
 
 def max_threads():
@@ -175,6 +183,18 @@ class Oracle2D:
             self.prepare()
         d = _c32(damping).reshape(3)
         rc = lib().oco_iclm2d(self._h, order, _p(pois), pois.shape[0], rx, ry, conv, stop, _p(d), int(exact))
+        assert rc == 0
+        return pois
+
+    def epipolar_search(self, pois, fundamental, parallax_x, parallax_y, search_radius, search_step, rx, ry, conv, stop, exact=False):
+        """EpipolarSearch::compute(queue), reference src/oc_epipolar_search.cpp:133-205."""
+        assert pois.dtype == np.float32 and pois.flags.c_contiguous and pois.shape[1] == 25
+        if not self._prepared:
+            self.prepare()
+        f = _c32(fundamental).reshape(9)
+        ax, ay = _c32(parallax_x).reshape(3), _c32(parallax_y).reshape(3)
+        rc = lib().oco_epipolar_search(self._h, _p(pois), pois.shape[0], _p(f), _p(ax), _p(ay), search_radius, search_step,
+                                       rx, ry, conv, stop, int(exact))
         assert rc == 0
         return pois
 

@@ -14,6 +14,13 @@ Outputs
                                     their whole 20-px neighbourhood inside the band
   torus_strain_crop.npz             a box of the shipped DVC table examples/dvc/Torus_def_sift_icgn1_r16.csv
                                     (x,y,z,u,v,w,ZNCC + 6 strains) for the 3D Strain test, same idea
+  step18_epipolar_crop.npz          stereo pair examples/3d_dic/"Step18 00,00-0005_{0,1}.tif" (2448x2048, 8-bit) cut down to what the
+                                    60 POIs x = 1170..1215, y = 1000..1025 of test_3d_reconstruction_epipolar.cpp touch
+                                    (view 1: the subsets; view 2: the +-150 px candidate sweep along the epipolar lines), the
+                                    fundamental matrix of that example's calibration (float32, as updateFundementalMatrix
+                                    forms it) and the shipped rows (x, y, ZNCC, r2_x, r2_y) of those POIs.  The test pastes the
+                                    crops into zero images of the full size; make_golden checks that the oracle's results on
+                                    the pasted images equal those on the full images bit for bit.
   al_foam4_crop.npz                 z-slices [18,118) of the DVC example pair as uint8 (values are
                                     integral, 52..202) + the shipped CPU and GPU result rows of the
                                     196 POIs with z in {60,65,70,75}.  The 15-tap prefilter and the
@@ -27,6 +34,73 @@ import numpy as np
 
 REF = "/root/reference/examples"
 OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def step18_fundamental():
+    """EpipolarSearch::updateFundementalMatrix (src/oc_epipolar_search.cpp:110-126) for the calibration hard-coded in
+    examples/test_3d_reconstruction_epipolar.cpp:46-88, in float32."""
+    f32 = np.float32
+
+    def rot(rx, ry, rz):  # Calibration::updateRotationMatrix, src/oc_calibration.cpp:50-60 (Eigen AngleAxis)
+        v = np.array([rx, ry, rz], f32)
+        th = f32(np.linalg.norm(v))
+        x, y, z = v / th
+        c, s = f32(np.cos(th)), f32(np.sin(th))
+        t = f32(1) - c
+        return np.array([[t * x * x + c, t * x * y - s * z, t * x * z + s * y], [t * x * y + s * z, t * y * y + c, t * y * z - s * x],
+                         [t * x * z - s * y, t * y * z + s * x, t * z * z + c]], f32)
+
+    k1 = np.array([[10664.80664, 0, 1176.03418], [0, 10643.88965, 914.7337036], [0, 0, 1]], f32)
+    k2 = np.array([[10749.53223, 0, 1034.707886], [0, 10726.52441, 1062.162842], [0, 0, 1]], f32)
+    t2 = np.array([250.881488962793, -1.15469183120196, 37.4849858174401], f32)
+    r2 = rot(0.01450813, -0.39152833, 0.01064092)
+    tx = np.array([[0, -t2[2], t2[1]], [t2[2], 0, -t2[0]], [-t2[1], t2[0], 0]], f32)
+    e = (tx @ r2).astype(f32)
+    return (np.linalg.inv(k2.astype(np.float64)).T.astype(f32) @ e @ np.linalg.inv(k1.astype(np.float64)).astype(f32)).astype(f32)
+
+
+def make_epipolar_fixture():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle2D
+
+    def load_tif(name):  # uncompressed 8-bit single-strip TIFF, pixel data at offset 8
+        b = open(os.path.join(REF, "3d_dic", name), "rb").read()
+        return np.frombuffer(b[8:8 + 2448 * 2048], np.uint8).reshape(2048, 2448).astype(np.float32)
+
+    v1, v2 = load_tif("Step18 00,00-0005_0.tif"), load_tif("Step18 00,00-0005_1.tif")
+    fm = step18_fundamental()
+    tab = np.genfromtxt(os.path.join(REF, "3d_dic", "Step18 00,00-0005_1_reconstruction_epipolar.csv"), delimiter=",", skip_header=1)
+    blk = tab.reshape(313, 313, 8)[150:156, 150:160].reshape(-1, 8)
+
+    def run(a, b, legacy):
+        orc.set_legacy_no_minus4(legacy)
+        q = np.zeros((len(blk), 25), np.float32)
+        q[:, 0:2] = blk[:, 0:2]
+        o = Oracle2D(a, b)
+        o.epipolar_search(q, fm, [0, 0, -30], [0, 0, -40], 150, 4, 20, 20, 0.05, 5)
+        c = q.copy()
+        o.icgn2d2(q, 9, 9, 0.001, 10)
+        orc.set_legacy_no_minus4(0)
+        return c, q
+
+    c_full, q_full = run(v1, v2, 1)
+    x, y = blk[:, 0], blk[:, 1]
+    a0 = (int(y.min()) - 28, int(y.max()) + 29, int(x.min()) - 28, int(x.max()) + 29)
+    cx, cy = c_full[:, 0] + c_full[:, 2], c_full[:, 1] + c_full[:, 8]
+    b0 = (int(cy.min()) - 70, int(cy.max()) + 70, int(cx.min()) - 340, int(cx.max()) + 340)
+    m1, m2 = np.zeros_like(v1), np.zeros_like(v2)
+    m1[a0[0]:a0[1], a0[2]:a0[3]] = v1[a0[0]:a0[1], a0[2]:a0[3]]
+    m2[b0[0]:b0[1], b0[2]:b0[3]] = v2[b0[0]:b0[1], b0[2]:b0[3]]
+    for legacy in (1, 0):
+        cf, qf = run(v1, v2, legacy)
+        cm, qm = run(m1, m2, legacy)
+        assert np.array_equal(cf, cm) and np.array_equal(qf, qm), "crop changes the result"
+    np.savez_compressed(os.path.join(OUT, "step18_epipolar_crop.npz"), shape=np.array(v1.shape),
+                        view1=v1[a0[0]:a0[1], a0[2]:a0[3]].astype(np.uint8), view1_origin=np.array([a0[0], a0[2]]),
+                        view2=v2[b0[0]:b0[1], b0[2]:b0[3]].astype(np.uint8), view2_origin=np.array([b0[0], b0[2]]),
+                        fundamental=fm, columns=np.array("x,y,r1r2 ZNCC,r2_x,r2_y".split(",")), table=blk[:, :5])
 
 
 def main():
@@ -62,6 +136,8 @@ def main():
     inner = (tb[:, 0] >= 500) & (tb[:, 0] <= 600) & (tb[:, 2] >= 381) & (tb[:, 2] <= 471)
     np.savez_compressed(os.path.join(OUT, "torus_strain_crop.npz"),
                         columns=np.array("x,y,z,u,v,w,ZNCC,exx,eyy,ezz,exy,eyz,ezx".split(",")), table=tb, check=inner)
+
+    make_epipolar_fixture()
 
     def load(p):
         d = np.fromfile(p, dtype=np.int32, count=3)

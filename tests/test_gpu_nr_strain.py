@@ -206,3 +206,74 @@ def test_strain_empty_and_tiny_queues(engine):
     q[:, 16] = 1.0
     s.compute(q)                      # 3 POIs < 5 neighbours: nothing is fitted
     assert np.all(q[:, 20:23] == 0)
+
+
+# ------------------------------------------------------------------------------------------------ EpipolarSearch
+def _step18_calibrations():
+    """examples/test_3d_reconstruction_epipolar.cpp:46-88"""
+    c1 = ob.Calibration(10664.80664, 10643.88965, 0.0, 1176.03418, 914.7337036)
+    c2 = ob.Calibration(10749.53223, 10726.52441, 0.0, 1034.707886, 1062.162842, tx=250.881488962793, ty=-1.15469183120196,
+                        tz=37.4849858174401, rx=0.01450813, ry=-0.39152833, rz=0.01064092)
+    return c1, c2
+
+
+def test_epipolar_search_golden_crop(engine):
+    v1, v2, fm, tab = util.step18_epipolar_fixture()
+    p = util.STEP18_EPIPOLAR
+    es = ob.EpipolarSearch(*_step18_calibrations(), engine=engine)
+    es.set_images(v1, v2)
+    es.set_parallax((-30, -40))
+    es.set_search(p["search_radius"], p["search_step"])
+    es.create_icgn(p["rx"], p["ry"], p["conv"], p["stop"])
+    es.prepare()
+    assert np.abs(es.fundamental_matrix - fm).max() <= 1e-6 * np.abs(fm).max()
+    es.fundamental_matrix = fm.copy()   # the fixture's float32 matrix, so candidate positions are identical by construction
+    q = ob.make_poi2d(tab[:, 0:2])
+    cpu = q.copy()
+    es.compute(q)
+    Oracle2D(v1, v2).epipolar_search(cpu, fm, p["parallax_x"], p["parallax_y"], p["search_radius"], p["search_step"], p["rx"], p["ry"],
+                                     p["conv"], p["stop"])
+    assert np.array_equal(q[:, 14:16], cpu[:, 14:16])      # the same candidate wins (its integer offset is kept in u0, v0)
+    same_it = q[:, 17] == cpu[:, 17]
+    assert same_it.mean() > 0.9
+    assert np.abs(q[same_it][:, [2, 8]] - cpu[same_it][:, [2, 8]]).max() < 1e-4
+    assert np.abs(q[same_it, 16] - cpu[same_it, 16]).max() < 1e-5
+    # refine like the example does and compare with the shipped table
+    icgn2 = ob.ICGN2D2(9, 9, 0.001, 10, engine=engine)
+    icgn2.set_images(v1, v2)
+    icgn2.prepare()
+    icgn2.compute(q)
+    assert np.abs(q[:, 0] + q[:, 2] - tab[:, 3]).max() < 3e-4
+    assert np.abs(q[:, 1] + q[:, 8] - tab[:, 4]).max() < 3e-4
+    conv = q[:, 16] != -4
+    assert conv.mean() > 0.9
+    assert np.abs(q[conv, 16] - tab[conv, 2]).max() < 1e-5
+
+
+def test_epipolar_search_synthetic_borders_and_errors(engine):
+    """A pure translation between the views; POIs near the border lose candidates to the border test, POIs whose every
+    candidate fails keep the best sentinel code."""
+    ref, tar = synth.speckle_pair_2d(512, 512)
+    # epipolar lines y' = y (rectified pair): F = [[0,0,0],[0,0,-1],[0,1,0]]
+    fm = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)
+    xy = np.array([[x, y] for y in (40, 200, 256, 470) for x in (30, 100, 256, 400, 490)], np.float32)
+    q = ob.make_poi2d(xy)
+    cpu = q.copy()
+    args = dict(search_radius=24, search_step=3, rx=12, ry=10, conv=0.05, stop=5)
+    engine.set_images_2d(ref, tar)
+    engine.icgn2d_prepare()
+    engine.epipolar_search2d(q, fm, [0.001, 0, 1.5], [0, 0.002, 0.5], **args)
+    Oracle2D(ref, tar).epipolar_search(cpu, fm, [0.001, 0, 1.5], [0, 0.002, 0.5], args["search_radius"], args["search_step"], args["rx"],
+                                       args["ry"], args["conv"], args["stop"])
+    assert np.array_equal(q[:, 14:16], cpu[:, 14:16])
+    assert np.array_equal(q[:, 16] < 0, cpu[:, 16] < 0)
+    neg = q[:, 16] < 0
+    assert np.array_equal(q[neg, 16], cpu[neg, 16])
+    ok = ~neg & (q[:, 17] == cpu[:, 17])
+    assert ok.sum() >= 10
+    assert np.abs(q[ok][:, [2, 8]] - cpu[ok][:, [2, 8]]).max() < 1e-4
+    assert np.abs(q[ok, 16] - cpu[ok, 16]).max() < 1e-5
+    untouched = [0, 1, 20, 21, 22, 23, 24]
+    assert np.array_equal(q[:, untouched], cpu[:, untouched])
+    with pytest.raises(ob.OpenCorrB200Error):
+        engine.epipolar_search2d(q, fm, [0, 0, 0], [0, 0, 0], search_radius=2, search_step=4, rx=12, ry=10, conv=0.05, stop=5)

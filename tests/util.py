@@ -114,3 +114,21 @@ def torus_queue():
     q[:, 11] = t[:, 5]
     q[:, 18] = t[:, 6]
     return q, t[:, 7:13], g["check"]
+
+
+def step18_epipolar_fixture():
+    """Stereo pair of the reference's test_3d_reconstruction_epipolar.cpp cut down to what 60 POIs touch (pasted into
+    zero images of the full 2448x2048 size), the example's fundamental matrix, and the shipped rows x,y,ZNCC,r2_x,r2_y."""
+    g = np.load(os.path.join(GOLDEN, "step18_epipolar_crop.npz"))
+    h, w = (int(v) for v in g["shape"])
+    views = []
+    for k in ("view1", "view2"):
+        img = np.zeros((h, w), np.float32)
+        a, o = g[k], g[k + "_origin"]
+        img[o[0]:o[0] + a.shape[0], o[1]:o[1] + a.shape[1]] = a
+        views.append(img)
+    return views[0], views[1], g["fundamental"], g["table"]
+
+
+# parameters of examples/test_3d_reconstruction_epipolar.cpp:137-150
+STEP18_EPIPOLAR = dict(parallax_x=[0, 0, -30], parallax_y=[0, 0, -40], search_radius=150, search_step=4, rx=20, ry=20, conv=0.05, stop=5)
