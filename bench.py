@@ -23,6 +23,7 @@ inside the e2e leg.
 because the reference cannot be compiled without Eigen/FFTW/OpenCV -- DESIGN.md) on the same config.
 """
 import argparse
+import gc
 import json
 import math
 import os
@@ -318,6 +319,7 @@ def run_ours(args):
     h_tar = torch.from_numpy(tar).pin_memory()
     h_q0 = torch.from_numpy(q0).pin_memory()
     h_q = torch.empty_like(h_q0).pin_memory()
+    h_q0_np = h_q0.numpy()
     n_total = world * n
     h_all = torch.empty((n_total, floats), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
     img_bytes = ref.nbytes + tar.nbytes
@@ -333,8 +335,9 @@ def run_ours(args):
                 t = [time.perf_counter()]
                 eng._ck(eng._lib.ocb_set_images_2d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[1], ref.shape[0], 0))
                 t.append(time.perf_counter())
-                h_q.copy_(h_q0)
                 qn = h_q.numpy()
+                np.copyto(qn, h_q0_np)  # plain memcpy: torch's copy_ fans 5 MB out over an OpenMP pool of ~127 threads,
+                #                         and one straggler thread on a shared host stalls the step for 60-80 ms
                 t.append(time.perf_counter())
                 eng.fftcc2d(qn, r, r)
                 t.append(time.perf_counter())
@@ -344,8 +347,9 @@ def run_ours(args):
                 phases.append([1e3 * (b - a) for a, b in zip(t[:-1], t[1:])])
             else:
                 eng._ck(eng._lib.ocb_set_images_3d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[2], ref.shape[1], ref.shape[0]))
-                h_q.copy_(h_q0)
                 qn = h_q.numpy()
+                np.copyto(qn, h_q0_np)  # plain memcpy: torch's copy_ fans 5 MB out over an OpenMP pool of ~127 threads,
+                #                         and one straggler thread on a shared host stalls the step for 60-80 ms
                 eng.fftcc3d(qn, r, r, r)
                 eng.icgn3d_prepare()
                 eng.icgn3d1(qn, r, r, r, cfg["conv"], cfg["stop"])
@@ -381,6 +385,10 @@ def run_ours(args):
     for _ in range(n_w):
         step_e2e()
     barrier()
+    # a generation-2 pass of Python's cyclic GC over the ~1e6 objects torch leaves on the heap takes 60-80 ms and used
+    # to land in one of the timed steps; collect now and keep the collector off while timing (as timeit does)
+    gc.collect()
+    gc.disable()
     e2e_times = []
     for _ in range(args.steps):
         barrier()
@@ -388,6 +396,7 @@ def run_ours(args):
         step_e2e()
         torch.cuda.synchronize(dev)
         e2e_times.append(time.perf_counter() - t0)
+    gc.enable()
     e2e_ms = torch.tensor([1e3 * sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
@@ -415,15 +424,17 @@ def run_ours(args):
         def step_e2e_u8():
             if kind == "2d":
                 eng._ck(eng._lib.ocb_set_images_2d_u8(eng._ctx, h8_ref.data_ptr(), h8_tar.data_ptr(), ref.shape[1], ref.shape[0]))
-                h_q.copy_(h_q0)
                 qn = h_q.numpy()
+                np.copyto(qn, h_q0_np)  # plain memcpy: torch's copy_ fans 5 MB out over an OpenMP pool of ~127 threads,
+                #                         and one straggler thread on a shared host stalls the step for 60-80 ms
                 eng.fftcc2d(qn, r, r)
                 eng.icgn2d_prepare()
                 (eng.icgn2d1 if cfg["order"] == 1 else eng.icgn2d2)(qn, r, r, cfg["conv"], cfg["stop"])
             else:
                 eng._ck(eng._lib.ocb_set_images_3d_u8(eng._ctx, h8_ref.data_ptr(), h8_tar.data_ptr(), ref.shape[2], ref.shape[1], ref.shape[0]))
-                h_q.copy_(h_q0)
                 qn = h_q.numpy()
+                np.copyto(qn, h_q0_np)  # plain memcpy: torch's copy_ fans 5 MB out over an OpenMP pool of ~127 threads,
+                #                         and one straggler thread on a shared host stalls the step for 60-80 ms
                 eng.fftcc3d(qn, r, r, r)
                 eng.icgn3d_prepare()
                 eng.icgn3d1(qn, r, r, r, cfg["conv"], cfg["stop"])
@@ -431,12 +442,15 @@ def run_ours(args):
         for _ in range(max(3, args.warmup)):
             step_e2e_u8()
         ts = []
+        gc.collect()
+        gc.disable()
         for _ in range(args.steps):
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             step_e2e_u8()
             torch.cuda.synchronize(dev)
             ts.append(time.perf_counter() - t0)
+        gc.enable()
         u8_ms = 1e3 * sum(ts) / len(ts)
         same = bool(np.array_equal(h_q.numpy()[:, :floats], res)) if False else None
         e2e_u8 = {"value": n / (u8_ms * 1e-3), "unit": UNIT, "ms_per_step": u8_ms,
