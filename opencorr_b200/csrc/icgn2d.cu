@@ -29,10 +29,18 @@
 
 #include "ocb_kernels.h"
 #include "ocb_tma.cuh"
+#include "ocb_f32x2.cuh"
 #include "ocb_tile2d.cuh"
 
 namespace ocb {
 
+#ifndef ICGN2D_PACKED
+// 1: fast row loop in packed f32x2 arithmetic (FFMA2/FMUL2/FADD2).  Measured on B200 (tools/ab_icgn2d.sh, config B/C/E):
+// 65 instead of 80 issue slots per sample, but ICGN2D1 gets 10 % SLOWER (0.95 vs 0.865 ms) and ICGN2D2 2 % faster: the
+// kernel is bound by dependent-issue latency at 11 warps/SM, and the packed ops lengthen the dependency chains
+// (Horner weights, the 4-row accumulation) more than they relieve the issue port.  Kept for reference, off.
+#define ICGN2D_PACKED 0
+#endif
 #ifndef ICGN2D_UNROLL
 #define ICGN2D_UNROLL 3
 #endif
@@ -485,6 +493,52 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					}
 				}
 				const float* tbase = T - (ty0 + 1) * TW - (tx0 + 1);
+#if ICGN2D_PACKED
+				// Packed-pair arithmetic (fma/mul/add.rn.f32x2 -> FFMA2/FMUL2/FADD2, ocb_f32x2.cuh): the x and y parts of the
+				// position, the weights {w0,w1},{w2,w3} of each axis, the column pairs of the 4x4 block and the two
+				// gradient channels each go through ONE instruction per pair -- ~55 instead of ~80 issue slots per sample.
+				const float2 pc2 = make_float2(pcx, pcy);
+				const float2 s0 = make_float2(xs0, ys0), s1 = make_float2(xs1, ys1), s2 = make_float2(xs2, ys2);
+				float2 G2[DEG + 1]; // {sum gx d y^Q, sum gy d y^Q}
+#pragma unroll
+				for (int qq = 0; qq <= DEG; qq++) G2[qq] = make_float2(0.f, 0.f);
+#pragma unroll ICGN2D_ROW_UNROLL
+				for (int r = 0; r < sh; r++) {
+					const float2 yl2 = bcast2(yl);
+					float2 XY;
+					if constexpr (NP == 6) XY = fadd2(pc2, ffma2(s1, yl2, s0));
+					else XY = fadd2(pc2, ffma2(ffma2(s2, yl2, s1), yl2, s0));
+					const float xf = floorf(XY.x), yf = floorf(XY.y);
+					const float2 fr = fsub2(XY, make_float2(xf, yf));
+					float2 wx01, wx23, wy01, wy23;
+					bicubic_weights2(fr.x, wx01, wx23);
+					bicubic_weights2(fr.y, wy01, wy23);
+					const float* q = tbase + (int)yf * TW + (int)xf;
+					// {q0 w0 + q2 w2, q1 w1 + q3 w3} per block row, weighted by wy and summed over the rows in both halves
+					float2 T2 = fmul2(ffma2(make_float2(q[2], q[3]), wx23, fmul2(make_float2(q[0], q[1]), wx01)), bcast2(wy01.x));
+					T2 = ffma2(ffma2(make_float2(q[TW + 2], q[TW + 3]), wx23, fmul2(make_float2(q[TW], q[TW + 1]), wx01)), bcast2(wy01.y), T2);
+					T2 = ffma2(ffma2(make_float2(q[2 * TW + 2], q[2 * TW + 3]), wx23, fmul2(make_float2(q[2 * TW], q[2 * TW + 1]), wx01)), bcast2(wy23.x), T2);
+					T2 = ffma2(ffma2(make_float2(q[3 * TW + 2], q[3 * TW + 3]), wx23, fmul2(make_float2(q[3 * TW], q[3 * TW + 1]), wx01)), bcast2(wy23.y), T2);
+					const float t = T2.x + T2.y;
+					tmin = fminf(tmin, t);
+					const float R = pc[0];
+					const float d = lane_on ? t - R : 0.f;
+					d1 += d;
+					d2 = fmaf(d, d, d2);
+					rd = fmaf(R, d, rd);
+					float2 gd = fmul2(make_float2(pc[1], pc[2]), bcast2(d));
+					G2[0] = fadd2(G2[0], gd);
+#pragma unroll
+					for (int qq = 1; qq <= DEG; qq++) {
+						gd = fmul2(gd, yl2);
+						G2[qq] = fadd2(G2[qq], gd);
+					}
+					pc += 3 * sw;
+					yl += 1.f;
+				}
+#pragma unroll
+				for (int qq = 0; qq <= DEG; qq++) { G[0][qq] = G2[qq].x; G[1][qq] = G2[qq].y; }
+#else
 #pragma unroll ICGN2D_ROW_UNROLL
 				for (int r = 0; r < sh; r++) {
 					float X, Y;
@@ -525,6 +579,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					pc += 3 * sw;
 					yl += 1.f;
 				}
+#endif
 				if (!LM && tmin < neg_limit) invalid = true;
 			} else {
 				for (int r = 0; r < sh; r++) {
