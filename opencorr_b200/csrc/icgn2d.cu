@@ -59,10 +59,13 @@ __host__ __device__ inline int icgn2d_tile_floats(int rx, int ry) {
 	const int a = icgn2d_ref_w(rx) * icgn2d_ref_h(ry), b = icgn2d_tar_w(rx) * icgn2d_tar_h(ry);
 	return round_up32(a > b ? a : b);
 }
-// lm: the Levenberg-Marquardt variant keeps the undamped Hessian (<= 78 floats) at the end of the slab
-__host__ __device__ inline int icgn2d_warp_floats(int rx, int ry, bool lm) {
+// lm: the Levenberg-Marquardt variant keeps the undamped Hessian (<= 78 floats) behind the constants;
+// wpp > 1 (warps per POI): a reduction area follows -- wpp x 96 floats of setup partials, 2 x wpp x 32 floats of
+// per-iteration partials (double-buffered by iteration parity)
+constexpr int ICGN2D_RED_SETUP = 96, ICGN2D_RED_ITER = 32;
+__host__ __device__ inline int icgn2d_slab_floats(int rx, int ry, bool lm, int wpp) {
 	const int n = (2 * rx + 1) * (2 * ry + 1);
-	return 32 + icgn2d_tile_floats(rx, ry) + round_up32(3 * n) + (lm ? 96 : 0);
+	return 32 + icgn2d_tile_floats(rx, ry) + round_up32(3 * n) + (lm ? 96 : 0) + (wpp > 1 ? wpp * (ICGN2D_RED_SETUP + 2 * ICGN2D_RED_ITER) : 0);
 }
 
 // Shape functions: sd = g_a * phi_i, phi = [1, x, y, x^2/2, xy, y^2/2] (first 3 for NP == 6);
@@ -155,8 +158,15 @@ __device__ __forceinline__ void right_divide_2x6(float* rows, float* M) {
 // LM: inverse-compositional Levenberg-Marquardt siblings ICLM2D1 / ICLM2D2 (reference src/oc_iclm.cpp:150-358,
 // :502-730): the Hessian is damped with lambda*I and re-factorised every iteration, a step is accepted only
 // when ZNSSD decreased, and out-of-range samples are NOT rejected (the interpolant's -1 is used as a value).
-template <int NP, int RC, bool LM>
-__global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
+// WPP: warps per POI.  One CTA = WPP warps = one POI at a time; the subset rows are split between the warps, which
+// share the POI's slab and meet at a CTA barrier once per pass (partial sums through the slab).  Everything after the
+// sums (statistics, solve, warp update) is computed redundantly by every warp from the same totals, so the warps
+// never diverge in control flow.  With the slab unchanged this doubles the resident warps per SM (r=16: 22 instead
+// of 11), which is what the latency-bound row loops need.
+// (the second launch bound keeps the register file from limiting residency below what the slab allows:
+//  <= 96 registers for the 6-parameter kernels, <= 144 for the 12-parameter ones)
+template <int NP, int RC, bool LM, int WPP>
+__global__ void __launch_bounds__(32 * WPP, NP == 6 ? 20 / WPP : 7) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
 	float conv_criterion, float stop_condition, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_ref,
 	const __grid_constant__ CUtensorMap tm_tar, int use_tma, const float* __restrict__ center_offsets, float lm_lambda, float lm_alpha,
 	float lm_beta) {
@@ -168,22 +178,31 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 	constexpr int NM = (D2 + 1) * (D2 + 2) / 2; // monomials x^P y^Q with P+Q <= 2*DEG: 6 or 15
 	const int rx = RC ? RC : rx_arg, ry = RC ? RC : ry_arg;
 	const int lane = threadIdx.x & 31;
-	const int warp = threadIdx.x >> 5;
+	const int sub = WPP > 1 ? (int)(threadIdx.x >> 5) : 0; // this warp's share of the POI
 	const int sw = 2 * rx + 1, sh = 2 * ry + 1, N = sw * sh;
+	const int rows_per = (sh + WPP - 1) / WPP;
+	const int r_lo = sub * rows_per, r_hi = (r_lo + rows_per) < sh ? (r_lo + rows_per) : sh; // rows [r_lo, r_hi) belong to this warp
 	const int ncol = sw < 32 ? sw : 32;        // columns handled by the row-mapped main loops
 	const int rem = sw - ncol;                  // columns 32.. handled by the tail loops
 	const int ntail = rem * sh;
 	const int RW = icgn2d_ref_w(rx), RH = icgn2d_ref_h(ry);
 	const int TW = icgn2d_tar_w(rx), TH = icgn2d_tar_h(ry);
-	float* slab = smem + (size_t)warp * icgn2d_warp_floats(rx, ry, LM);
+	float* slab = smem;
 	uint64_t* bar = (uint64_t*)slab;
+	int* s_poi = (int*)(slab + 8);              // WPP > 1: the POI index fetched by thread 0
 	float* T = slab + 32;
 	float* sC = T + icgn2d_tile_floats(rx, ry); // per-sample constants, interleaved {R, gx, gy} (12-byte lane stride: conflict-free)
 	float* sH = sC + round_up32(3 * N);         // LM only: the undamped Hessian, packed lower triangle
+	float* sRedS = sH + (LM ? 96 : 0);          // WPP > 1: setup partials [WPP][ICGN2D_RED_SETUP]
+	float* sRedI = sRedS + WPP * ICGN2D_RED_SETUP; // WPP > 1: iteration partials [2][WPP][ICGN2D_RED_ITER]
 	uint32_t bar_phase = 0;
+	auto gsync = [&]() { // all warps of this POI
+		if constexpr (WPP > 1) __syncthreads();
+		else __syncwarp();
+	};
 	if (use_tma) {
-		if (lane == 0) mbar_init(bar, 1);
-		__syncwarp();
+		if (threadIdx.x == 0) mbar_init(bar, 1);
+		gsync();
 	}
 	const float* __restrict__ ref = img.ref;
 	const float* __restrict__ tar = img.tar;
@@ -194,8 +213,15 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 
 	while (true) {
 		int poi = 0;
-		if (lane == 0) poi = atomicAdd(work_counter, 1);
-		poi = __shfl_sync(0xffffffffu, poi, 0);
+		if constexpr (WPP > 1) {
+			gsync(); // every warp is done with the previous POI (slab, s_poi)
+			if (threadIdx.x == 0) *s_poi = atomicAdd(work_counter, 1);
+			gsync();
+			poi = *s_poi;
+		} else {
+			if (lane == 0) poi = atomicAdd(work_counter, 1);
+			poi = __shfl_sync(0xffffffffu, poi, 0);
+		}
 		if (poi >= n_poi) break;
 		float* P = pois + (size_t)poi * P2_N;
 		const float rec = lane < P2_N ? P[lane] : 0.f;
@@ -207,10 +233,10 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		// guard, reference src/oc_icgn.cpp:160-167 / :701-708 (NaN coordinates are rejected too)
 		if (py - ry < 0 || px - rx < 0 || py + ry > h - 1 || px + rx > w - 1 || fabsf(u_in) >= w || fabsf(v_in) >= h
 			|| zncc_in < 0 || is_nan_f(u_in) || is_nan_f(v_in) || is_nan_f(px) || is_nan_f(py)) {
-			if (lane == 0) P[P2_ZNCC] = zncc_in >= 0 ? -3.f : zncc_in;
+			if (threadIdx.x == 0) P[P2_ZNCC] = zncc_in >= 0 ? -3.f : zncc_in;
 			continue;
 		}
-		__syncwarp();
+		gsync(); // every warp has read the record before thread 0 may write results / TMA may overwrite the slab
 		// compute(POI2D*, Point2D& center_offset), src/oc_icgn.cpp:353-547 / :910-1126: local coordinates are
 		// (integer - offset) and the target subset is centred at poi + offset; (0, 0) for the plain overload
 		float ox = 0.f, oy = 0.f;
@@ -225,7 +251,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		const int x0 = (int)px - rx, y0 = (int)py - ry; // Subset2D::fill upper-left, src/oc_subset.cpp:41-42
 		const int rox = floor4(x0 - 2), ex = (x0 - 2) - rox; // 16-byte aligned tile origin, column offset 0..3
 		if (use_tma) {
-			if (lane == 0) {
+			if (threadIdx.x == 0) {
 				fence_proxy_async(); // earlier generic-proxy accesses to T are ordered before the async-proxy write
 				mbar_expect_tx(bar, (uint32_t)(RW * RH * sizeof(float)));
 				tma_load_2d(T, &tm_ref, rox, y0 - 2, bar);
@@ -233,8 +259,8 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			mbar_wait(bar, bar_phase);
 			bar_phase ^= 1;
 		} else {
-			stage_tile(T, ref, w, h, rox, y0 - 2, RW, RH, 0.f, lane);
-			__syncwarp();
+			if (sub == 0) stage_tile(T, ref, w, h, rox, y0 - 2, RW, RH, 0.f, lane);
+			gsync();
 		}
 		const float c0 = T[(ry + 2) * RW + rx + 2 + ex]; // pilot value: the centre pixel
 
@@ -254,7 +280,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		{
 			const int xg = x0 + lane;
 			const bool gx_ok = lane_on && xg >= 2 && xg < w - 2; // gradient maps are zero on a 2-pixel border (src/oc_gradient.cpp:42,46)
-			for (int r = 0; r < sh; r++) {
+			for (int r = r_lo; r < r_hi; r++) {
 				const int yg = y0 + r;
 				const bool gy_ok = yg >= 2 && yg < h - 2;
 				const float yl = (float)(r - ry) - oy;
@@ -318,7 +344,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				}
 		}
 		// tail columns (>= 32): lanes run over (row, column) pairs, general x and y
-		for (int idx = lane; idx < ntail; idx += 32) {
+		for (int idx = sub * 32 + lane; idx < ntail; idx += 32 * WPP) {
 			const int r = idx / rem, c = 32 + (idx - r * rem);
 			const int xg = x0 + c, yg = y0 + r;
 			const float xl = (float)(c - rx) - ox, yl = (float)(r - ry) - oy;
@@ -364,6 +390,48 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		for (int a = 0; a < 2; a++)
 #pragma unroll
 			for (int i = 0; i < NPHI; i++) { Sg[a][i] = warp_sum(Sg[a][i]); SRg[a][i] = warp_sum(SRg[a][i]); }
+		if constexpr (WPP > 1) {
+			// partial sums of the warps meet here; every warp then adds them in the same order
+			static_assert(2 + 3 * NM + 4 * NPHI <= ICGN2D_RED_SETUP, "setup partials do not fit");
+			if (lane == 0) {
+				float* o = sRedS + sub * ICGN2D_RED_SETUP;
+				o[0] = r1;
+				o[1] = r2;
+#pragma unroll
+				for (int a = 0; a < 3; a++)
+#pragma unroll
+					for (int m = 0; m < NM; m++) o[2 + a * NM + m] = M[a][m];
+#pragma unroll
+				for (int a = 0; a < 2; a++)
+#pragma unroll
+					for (int i = 0; i < NPHI; i++) { o[2 + 3 * NM + a * NPHI + i] = Sg[a][i]; o[2 + 3 * NM + 2 * NPHI + a * NPHI + i] = SRg[a][i]; }
+			}
+			gsync(); // also: every warp is done with the reference tile
+			r1 = 0.f;
+			r2 = 0.f;
+#pragma unroll
+			for (int a = 0; a < 3; a++)
+#pragma unroll
+				for (int m = 0; m < NM; m++) M[a][m] = 0.f;
+#pragma unroll
+			for (int a = 0; a < 2; a++)
+#pragma unroll
+				for (int i = 0; i < NPHI; i++) { Sg[a][i] = 0.f; SRg[a][i] = 0.f; }
+#pragma unroll
+			for (int ww = 0; ww < WPP; ww++) {
+				const float* o = sRedS + ww * ICGN2D_RED_SETUP;
+				r1 += o[0];
+				r2 += o[1];
+#pragma unroll
+				for (int a = 0; a < 3; a++)
+#pragma unroll
+					for (int m = 0; m < NM; m++) M[a][m] += o[2 + a * NM + m];
+#pragma unroll
+				for (int a = 0; a < 2; a++)
+#pragma unroll
+					for (int i = 0; i < NPHI; i++) { Sg[a][i] += o[2 + 3 * NM + a * NPHI + i]; SRg[a][i] += o[2 + 3 * NM + 2 * NPHI + a * NPHI + i]; }
+			}
+		}
 		// reference subset statistics (Subset2D::zeroMeanNorm, src/oc_subset.cpp:46-53), relative to c0
 		const float rbar = r1 * inv_n;              // mean(R) - c0
 		const float f2 = r2 - r1 * rbar;            // sum f^2, f = R - mean(R)
@@ -386,22 +454,23 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					}
 			}
 		if constexpr (LM) {
-			if (lane == 0) {
+			if (threadIdx.x == 0) {
 #pragma unroll
 				for (int k = 0; k < NH; k++) sH[k] = H[k];
 			}
-			__syncwarp();
+			gsync();
 		} else {
 			cholesky_packed<NP>(H);
 		}
 		float lm_cur = 0.f, znssd0 = 4.f; // src/oc_iclm.cpp:234-235
 
 		// ---------------- stage the target tile over the reference tile ----------------
-		__syncwarp();
+		// (WPP > 1: the barrier of the setup reduction already ordered every warp's last read of the reference tile)
+		if constexpr (WPP == 1) __syncwarp();
 		const int tx0 = floor4((int)floorf(pcx + u_in) - rx - 1 - ICGN2D_TILE_MARGIN);
 		const int ty0 = (int)floorf(pcy + v_in) - ry - 1 - ICGN2D_TILE_MARGIN;
 		if (use_tma) {
-			if (lane == 0) {
+			if (threadIdx.x == 0) {
 				fence_proxy_async();
 				mbar_expect_tx(bar, (uint32_t)(TW * TH * sizeof(float)));
 				tma_load_2d(T, &tm_tar, tx0, ty0, bar);
@@ -409,8 +478,8 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			mbar_wait(bar, bar_phase);
 			bar_phase ^= 1;
 		} else {
-			stage_tile(T, tar, w, h, tx0, ty0, TW, TH, 0.f, lane);
-			__syncwarp();
+			if (sub == 0) stage_tile(T, tar, w, h, tx0, ty0, TW, TH, 0.f, lane);
+			gsync();
 		}
 		// a sample is "fast" when it is valid (src/oc_cubic_bspline.cpp:137-142) AND its support is in the tile
 		const float xlo = fmaxf(1.f, (float)(tx0 + 1)), xhi = fminf((float)(w - 2), (float)(tx0 + TW - 2));
@@ -476,8 +545,8 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 			if (iter_fast) {
 				// branch-free row loop: no per-sample validity tests (min(t) is tested after the loop)
 				float tmin = 0.f;
-				float yl = (float)(-ry) - oy;
-				const float* pc = sC + 3 * lane_c;
+				float yl = (float)(r_lo - ry) - oy;
+				const float* pc = sC + 3 * (r_lo * sw + lane_c);
 				float xs0, xs1, xs2, ys0, ys1, ys2;
 				{
 					const float xl = (float)(lane_c - rx) - ox;
@@ -503,7 +572,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 #pragma unroll
 				for (int qq = 0; qq <= DEG; qq++) G2[qq] = make_float2(0.f, 0.f);
 #pragma unroll ICGN2D_ROW_UNROLL
-				for (int r = 0; r < sh; r++) {
+				for (int r = r_lo; r < r_hi; r++) {
 					const float2 yl2 = bcast2(yl);
 					float2 XY;
 					if constexpr (NP == 6) XY = fadd2(pc2, ffma2(s1, yl2, s0));
@@ -540,7 +609,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 				for (int qq = 0; qq <= DEG; qq++) { G[0][qq] = G2[qq].x; G[1][qq] = G2[qq].y; }
 #else
 #pragma unroll ICGN2D_ROW_UNROLL
-				for (int r = 0; r < sh; r++) {
+				for (int r = r_lo; r < r_hi; r++) {
 					float X, Y;
 					if constexpr (NP == 6) {
 						X = pcx + fmaf(xs1, yl, xs0);
@@ -582,7 +651,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 #endif
 				if (!LM && tmin < neg_limit) invalid = true;
 			} else {
-				for (int r = 0; r < sh; r++) {
+				for (int r = r_lo; r < r_hi; r++) {
 					const float yl = (float)(r - ry) - oy;
 					float X, Y;
 					if constexpr (NP == 6) {
@@ -631,7 +700,7 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 #pragma unroll
 					for (int i = 0; i < NPHI; i++) SD[a * NPHI + i] = phi_c(i) * xp[phi_p(i)] * G[a][phi_q(i)];
 			}
-			for (int idx = lane; idx < ntail; idx += 32) {
+			for (int idx = sub * 32 + lane; idx < ntail; idx += 32 * WPP) {
 				const int r = idx / rem, c = 32 + (idx - r * rem);
 				const float xl = (float)(c - rx) - ox, yl = (float)(r - ry) - oy;
 				float X, Y;
@@ -665,15 +734,46 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 					}
 				}
 			}
-			if (__any_sync(0xffffffffu, invalid)) { // src/oc_icgn.cpp:251-255
-				left_image = true;
-				break;
-			}
+			bool any_invalid = __any_sync(0xffffffffu, invalid);
 			d1 = warp_sum(d1);
 			d2 = warp_sum(d2);
 			rd = warp_sum(rd);
 #pragma unroll
 			for (int k = 0; k < NP; k++) SD[k] = warp_sum(SD[k]);
+			if constexpr (WPP > 1) {
+				static_assert(4 + NP <= ICGN2D_RED_ITER, "iteration partials do not fit");
+				float* o = sRedI + ((iteration & 1) * WPP + sub) * ICGN2D_RED_ITER; // double-buffered: one barrier per iteration
+				if (lane == 0) {
+					o[0] = d1;
+					o[1] = d2;
+					o[2] = rd;
+					o[3] = any_invalid ? 1.f : 0.f;
+#pragma unroll
+					for (int k = 0; k < NP; k++) o[4 + k] = SD[k];
+				}
+				gsync();
+				d1 = 0.f;
+				d2 = 0.f;
+				rd = 0.f;
+				float inv_flag = 0.f;
+#pragma unroll
+				for (int k = 0; k < NP; k++) SD[k] = 0.f;
+#pragma unroll
+				for (int ww = 0; ww < WPP; ww++) {
+					const float* q = sRedI + ((iteration & 1) * WPP + ww) * ICGN2D_RED_ITER;
+					d1 += q[0];
+					d2 += q[1];
+					rd += q[2];
+					inv_flag += q[3];
+#pragma unroll
+					for (int k = 0; k < NP; k++) SD[k] += q[4 + k];
+				}
+				any_invalid = inv_flag > 0.f;
+			}
+			if (any_invalid) { // src/oc_icgn.cpp:251-255
+				left_image = true;
+				break;
+			}
 			// warped-target statistics: g = t - mean(t) = f + (d - dbar); sum f d = sum R'd - rbar * sum d
 			const float dbar = d1 * inv_n;
 			const float fd = (rd - c0 * d1) - rbar * d1; // rd holds sum R d with the raw R
@@ -730,12 +830,12 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 		} while ((float)iteration < stop_condition && dp_norm >= conv_criterion);
 
 		if (left_image) {
-			if (lane == 0) P[P2_ZNCC] = -3.f;
+			if (threadIdx.x == 0) P[P2_ZNCC] = -3.f;
 			__syncwarp();
 			continue;
 		}
 		// ---------------- results, src/oc_icgn.cpp:310-340 / :859-897 ----------------
-		if (lane == 0) {
+		if (threadIdx.x == 0) {
 			float u, v;
 			if constexpr (NP == 6) {
 				u = A[2]; v = A[5];
@@ -770,44 +870,56 @@ __global__ void __launch_bounds__(128) icgn2d_kernel(Image2D img, float* __restr
 // host-side launch ---------------------------------------------------------------------------
 // Returns 0, -1 when one warp's slab does not fit in shared memory, -2 on a CUDA error.
 // d_counter: one int of device memory owned by the context (work queue head).
+typedef void (*Icgn2dKernel)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int, const float*, float, float, float);
+
+template <int WPP>
+static Icgn2dKernel icgn2d_pick(int np, int rx, int ry, bool lm) {
+	if (lm) return (np == 6) ? icgn2d_kernel<6, 0, true, WPP> : icgn2d_kernel<12, 0, true, WPP>;
+	if (np == 6) return (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16, false, WPP> : icgn2d_kernel<6, 0, false, WPP>;
+	return (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20, false, WPP> : icgn2d_kernel<12, 0, false, WPP>;
+}
+
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
 	size_t smem_optin, int* d_counter, const float* d_center_offsets, const float* lm_damping, cudaStream_t stream, cudaError_t* err) {
 	const bool lm = lm_damping != nullptr;
-	const size_t per_warp = (size_t)icgn2d_warp_floats(rx, ry, lm) * sizeof(float);
-	int best_wpb = 0, best_warps = 0;
-	for (int wpb = 4; wpb >= 1; wpb >>= 1) {
-		size_t need = per_warp * wpb;
-		if (need > smem_optin) continue;
-		int blocks = (int)((228 * 1024) / (need + 1024));
-		if (blocks > 32) blocks = 32;
-		int warps = blocks * wpb;
-		if (warps > best_warps) { best_warps = warps; best_wpb = wpb; }
+	// Warps per POI.  Measured on B200 (tools/ab_icgn2d.sh): with the GPU full, one warp per POI wins (config B 0.853 vs
+	// 0.906 ms, C 2.22 vs 2.43 ms, E 8.38 vs 8.87 ms) -- the second warp doubles the resident warps but also the per-POI
+	// fixed work and adds a barrier per pass; with fewer POIs than resident slots, two warps per POI shorten the tail
+	// (config A, 200 POIs: 24.6 vs 32.5 us).  So: 2 only when the queue cannot fill the machine.
+	auto slots = [&](int wpp_) {
+		const size_t b = (size_t)icgn2d_slab_floats(rx, ry, lm, wpp_) * sizeof(float);
+		if (b > smem_optin) return 0;
+		int k = (int)((228 * 1024) / (b + 1024));
+		return k > 32 ? 32 : k;
+	};
+	int wpp = ((long long)n < (long long)sm_count * slots(1) && (2 * ry + 1) >= 8 && slots(2) > 0) ? 2 : 1;
+	if (const char* e = getenv("OCB_ICGN2D_WPP")) { // tuning knob
+		const int v = atoi(e);
+		if (v == 1 || (v == 2 && slots(2) > 0)) wpp = v;
 	}
-	if (best_wpb == 0) return -1;
+	size_t smem = (size_t)icgn2d_slab_floats(rx, ry, lm, wpp) * sizeof(float);
+	if (smem > smem_optin) return -1;
+	int blocks_per_sm = slots(wpp);
+	if (blocks_per_sm < 1) blocks_per_sm = 1;
 	if (const char* cap = getenv("OCB_ICGN2D_MAX_WARPS")) { // tuning knob: cap the resident warps per SM
-		const int c = atoi(cap);
-		if (c >= 1 && c < best_warps) { best_wpb = 1; best_warps = c; }
+		const int c = atoi(cap) / wpp;
+		if (c >= 1 && c < blocks_per_sm) blocks_per_sm = c;
 	}
-	const size_t smem = per_warp * best_wpb;
 	CUtensorMap tm_ref, tm_tar;
 	memset(&tm_ref, 0, sizeof(tm_ref));
 	memset(&tm_tar, 0, sizeof(tm_tar));
 	const int dims[2] = { img.w, img.h };
 	const int box_ref[2] = { icgn2d_ref_w(rx), icgn2d_ref_h(ry) }, box_tar[2] = { icgn2d_tar_w(rx), icgn2d_tar_h(ry) };
 	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm_ref, img.ref, 2, dims, box_ref) && tma_make_map(&tm_tar, img.tar, 2, dims, box_tar);
-	void (*kern)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int, const float*, float, float, float);
-	if (lm) kern = (np == 6) ? icgn2d_kernel<6, 0, true> : icgn2d_kernel<12, 0, true>;
-	else if (np == 6) kern = (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16, false> : icgn2d_kernel<6, 0, false>;
-	else kern = (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20, false> : icgn2d_kernel<12, 0, false>;
+	Icgn2dKernel kern = wpp == 2 ? icgn2d_pick<2>(np, rx, ry, lm) : icgn2d_pick<1>(np, rx, ry, lm);
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
 	*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
 	if (*err != cudaSuccess) return -2;
-	long long blocks_needed = ((long long)n + best_wpb - 1) / best_wpb;
-	long long resident = (long long)sm_count * (best_warps / best_wpb);
-	int grid = (int)(blocks_needed < resident ? blocks_needed : resident); // persistent: one wave
+	long long resident = (long long)sm_count * blocks_per_sm;
+	int grid = (int)((long long)n < resident ? (long long)n : resident); // persistent: one wave, one POI per CTA at a time
 	if (grid < 1) grid = 1;
-	kern<<<grid, best_wpb * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, d_counter, tm_ref, tm_tar, use_tma, d_center_offsets,
+	kern<<<grid, wpp * 32, smem, stream>>>(img, d_pois, (int)n, rx, ry, conv, stop, d_counter, tm_ref, tm_tar, use_tma, d_center_offsets,
 		lm ? lm_damping[0] : 0.f, lm ? lm_damping[1] : 0.f, lm ? lm_damping[2] : 0.f);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;

@@ -429,3 +429,36 @@ def test_iclm2d1_golden_table(engine):
     d = np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max(1)
     assert np.percentile(d, 98) < 1e-4 and d.max() < 1.5e-3
     assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 1e-5
+
+
+@pytest.mark.parametrize("wpp", ["1", "2"])
+@pytest.mark.parametrize("order", [1, 2])
+def test_icgn2d_warps_per_poi_variants(engine, cfg_a, monkeypatch, wpp, order):
+    """The launch picks one or two warps per POI from the queue length (icgn2d.cu icgn2d_launch); both code paths must
+    meet the same parity bar, also with sentinels, an odd row split and the LM variant."""
+    monkeypatch.setenv("OCB_ICGN2D_WPP", wpp)
+    ref, tar, xy, _ = cfg_a
+    o = Oracle2D(ref, tar)
+    for rx, ry in ((15, 15), (16, 13)):
+        q = ob.make_poi2d(np.vstack([xy, [[3, 3], [ref.shape[1] - 2, 50]]]).astype(np.float32))
+        o.fftcc2d(q, rx, ry)
+        a, b = q.copy(), q.copy()
+        cls = ob.ICGN2D1 if order == 1 else ob.ICGN2D2
+        ic = cls(rx, ry, 0.001, 10, engine=engine)
+        ic.set_images(ref, tar)
+        ic.prepare()
+        ic.compute(a)
+        (o.icgn2d1 if order == 1 else o.icgn2d2)(b, rx, ry, 0.001, 10)
+        util.compare_2d(a, b, "wpp=%s order=%d r=(%d,%d)" % (wpp, order, rx, ry), order=order)
+        assert a[-1, 16] == -3 and a[-2, 16] == -3
+    lm = ob.ICLM2D1(16, 16, 0.001, 10, engine=engine)
+    lm.set_images(ref, tar)
+    lm.prepare()
+    q = ob.make_poi2d(xy)
+    o.fftcc2d(q, 16, 16)
+    a, b = q.copy(), q.copy()
+    lm.compute(a)
+    o.iclm2d(1, b, 16, 16, 0.001, 10)
+    same = a[:, 17] == b[:, 17]
+    assert same.mean() > 0.97
+    assert np.abs(a[same][:, [2, 8]] - b[same][:, [2, 8]]).max() < 1e-4
