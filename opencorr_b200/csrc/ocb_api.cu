@@ -384,6 +384,13 @@ int ocb_fftcc2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry) {
 		ctx->launches++;
 		return OCB_OK;
 	}
+	if (rx == ry && ocb::fftcc2d_reg_supported(rx) && !getenv("OCB_FFTCC2D_GENERIC")) { // thread-per-row register FFTs, N = 2^a 3^b 5^c <= 64
+		cudaError_t errr;
+		if (ocb::fftcc2d_reg_launch(ctx->img2, (float*)d_poi2d, n, rx, ctx->sm_count, ctx->stream, &errr))
+			return set_error(ctx, OCB_ERR_CUDA, "fftcc2d launch failed: %s", cudaGetErrorString(errr));
+		ctx->launches++;
+		return OCB_OK;
+	}
 	ocb::FftAxis ax, ay;
 	if (!ocb::fft_plan_axis(2 * rx, &ax) || !ocb::fft_plan_axis(2 * ry, &ay))
 		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc2d: window size %dx%d has a prime factor > 31", 2 * rx, 2 * ry);

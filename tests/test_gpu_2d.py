@@ -40,6 +40,43 @@ def test_fftcc2d_matches_oracle(engine, cfg_a, r):
     assert np.array_equal(q_gpu[:, untouched], q_cpu[:, untouched])
 
 
+@pytest.mark.parametrize("r", [4, 5, 8, 9, 10, 12, 18, 24, 25, 27, 30, 32])
+def test_fftcc2d_register_kernels_all_sizes(engine, r):
+    """Every window size served by fftcc2d_reg.cu (thread-per-row register FFTs), with a POI count that does not fill
+    the last CTA, border POIs (left untouched) and a non-zero incoming guess."""
+    ref, tar = synth.speckle_pair_2d(400, 360)
+    xy = synth.grid_2d(70, 70, 9, 7, 29, 31)[:59]
+    xy = np.vstack([xy, [[2, 2], [399, 100], [200, 358]]]).astype(np.float32)
+    q_gpu = ob.make_poi2d(xy)
+    q_gpu[::4, 2] = 1.0
+    q_gpu[::5, 8] = -1.6
+    q_cpu = q_gpu.copy()
+    f = ob.FFTCC2D(r, r, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q_gpu)
+    Oracle2D(ref, tar).fftcc2d(q_cpu, r, r)
+    assert np.array_equal(q_gpu[:, [2, 8, 14, 15]], q_cpu[:, [2, 8, 14, 15]])
+    assert np.abs(q_gpu[:, 16] - q_cpu[:, 16]).max() < 1e-5
+    untouched = np.delete(np.arange(25), [2, 8, 14, 15, 16])
+    assert np.array_equal(q_gpu[:, untouched], q_cpu[:, untouched])
+    assert np.all(q_gpu[-3:, 16] == 0)
+
+
+def test_fftcc2d_generic_kernel_still_matches(engine, cfg_a, monkeypatch):
+    """The Stockham-over-shared-memory kernel stays the fallback (non-square windows, other prime factors)."""
+    monkeypatch.setenv("OCB_FFTCC2D_GENERIC", "1")
+    ref, tar, xy, _ = cfg_a
+    for r in (16, 20, 7):
+        q_gpu = ob.make_poi2d(xy)
+        q_cpu = q_gpu.copy()
+        f = ob.FFTCC2D(r, r, engine=engine)
+        f.set_images(ref, tar)
+        f.compute(q_gpu)
+        Oracle2D(ref, tar).fftcc2d(q_cpu, r, r)
+        assert np.array_equal(q_gpu[:, [2, 8, 14, 15]], q_cpu[:, [2, 8, 14, 15]])
+        assert np.abs(q_gpu[:, 16] - q_cpu[:, 16]).max() < 1e-5
+
+
 def test_fftcc2d_nonsquare_window_and_initial_guess(engine, cfg_a):
     ref, tar, xy, _ = cfg_a
     q_gpu = ob.make_poi2d(xy)
