@@ -546,7 +546,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="B", choices=["A", "B", "C", "D", "E"])
+    ap.add_argument("--config", default="B", choices=["A", "B", "C", "D", "E", "F"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="POIs per step for --impl reference (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -443,6 +443,24 @@ int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int r
 		ctx->launches++;
 		return OCB_OK;
 	}
+	if (rx == ry && ry == rz && ocb::fftcc3d_reg_supported(rx) && !getenv("OCB_FFTCC3D_GENERIC")) { // register FFT codelets, N = 2^a 3^b 5^c <= 64
+		int gridr = ocb::fftcc3d_reg_grid(rx, ctx->sm_count);
+		if ((size_t)gridr > n) gridr = (int)n;
+		const size_t needr = (size_t)gridr * 2 * 8 * rx * ry * rz; // two scratch volumes of (2r)^3 complex per CTA
+		if (needr > ctx->fft_scratch_elems) {
+			OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+			cudaFree(ctx->fft_scratch);
+			ctx->fft_scratch = nullptr;
+			ctx->fft_scratch_elems = 0;
+			OCB_CUDA(ctx, cudaMalloc(&ctx->fft_scratch, needr * sizeof(float2)));
+			ctx->fft_scratch_elems = needr;
+		}
+		cudaError_t errr;
+		if (ocb::fftcc3d_reg_launch(ctx->img3, (float*)d_poi3d, n, rx, ctx->fft_scratch, gridr, ctx->stream, &errr))
+			return set_error(ctx, OCB_ERR_CUDA, "fftcc3d launch failed: %s", cudaGetErrorString(errr));
+		ctx->launches++;
+		return OCB_OK;
+	}
 	ocb::FftAxis ax, ay, az;
 	if (!ocb::fft_plan_axis(2 * rx, &ax) || !ocb::fft_plan_axis(2 * ry, &ay) || !ocb::fft_plan_axis(2 * rz, &az))
 		return set_error(ctx, OCB_ERR_UNSUPPORTED, "fftcc3d: window size has a prime factor > 31");

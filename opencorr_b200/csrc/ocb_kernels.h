@@ -57,6 +57,10 @@ int fftcc2d_w32_launch(const Image2D& img, float* d_pois, size_t n, int sm_count
 // fftcc2d_reg.cu (square windows of 2^a 3^b 5^c <= 64 points, one thread per row, register FFT codelets)
 bool fftcc2d_reg_supported(int r);
 int fftcc2d_reg_launch(const Image2D& img, float* d_pois, size_t n, int r, int sm_count, cudaStream_t stream, cudaError_t* err);
+// fftcc3d_reg.cu (cubic windows of 2^a 3^b 5^c <= 64 points, one thread per 1D transform, register FFT codelets)
+bool fftcc3d_reg_supported(int r);
+int fftcc3d_reg_grid(int r, int sm_count);
+int fftcc3d_reg_launch(const Image3D& img, float* d_pois, size_t n_poi, int r, float2* scratch, int grid, cudaStream_t stream, cudaError_t* err);
 size_t fftcc3d_smem_bytes(int rx, int ry, int rz);
 int fftcc3d_grid(int rx, int ry, int rz, int sm_count);
 int fftcc3d_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, int rz, const FftAxis& ax, const FftAxis& ay,

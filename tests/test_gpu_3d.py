@@ -52,6 +52,44 @@ def test_fftcc3d_matches_oracle(engine, vol, r):
     assert (q_cpu[:, 18] > 0.3).all()
 
 
+@pytest.mark.parametrize("r", [4, 5, 6, 9, 10, 12, 18, 20])
+def test_fftcc3d_register_kernels(engine, r):
+    """The cubic windows served by fftcc3d_reg.cu (one thread per 1D transform, register codelets); r = 8, 15 and 30 are
+    covered by the tests above / the golden DVC table.  Includes a POI too close to the border (left untouched) and a
+    non-zero incoming guess."""
+    ref, tar = synth.speckle_pair_3d(96, 88, 80)
+    c = np.array([[48, 44, 40], [50, 41, 38], [44, 46, 42], [3, 44, 40]], np.float32)
+    if r > 12:
+        c = c[[0, 3]]
+    q_gpu = ob.make_poi3d(c)
+    q_gpu[0, 3] = 1.0
+    q_gpu[0, 11] = -1.4
+    q_cpu = q_gpu.copy()
+    f = ob.FFTCC3D(r, r, r, engine=engine)
+    f.set_images(ref, tar)
+    f.compute(q_gpu)
+    o = Oracle3D(ref, tar)
+    o.fftcc3d(q_cpu, r, r, r, exact=True)
+    assert np.array_equal(q_gpu[:, [3, 7, 11, 15, 16, 17]], q_cpu[:, [3, 7, 11, 15, 16, 17]])
+    assert np.abs(q_gpu[:, 18] - q_cpu[:, 18]).max() < 1e-5
+    assert q_gpu[-1, 18] == 0 and np.all(q_gpu[-1, 3:15] == 0)
+
+
+def test_fftcc3d_generic_kernel_still_matches(engine, vol, monkeypatch):
+    """The Stockham kernel stays the fallback (non-cubic windows, other prime factors)."""
+    monkeypatch.setenv("OCB_FFTCC3D_GENERIC", "1")
+    ref, tar, xyz = vol
+    for r in (8, 7):
+        q_gpu = ob.make_poi3d(xyz)
+        q_cpu = q_gpu.copy()
+        f = ob.FFTCC3D(r, r, r, engine=engine)
+        f.set_images(ref, tar)
+        f.compute(q_gpu)
+        Oracle3D(ref, tar).fftcc3d(q_cpu, r, r, r, exact=True)
+        assert np.array_equal(q_gpu[:, [3, 7, 11, 15, 16, 17]], q_cpu[:, [3, 7, 11, 15, 16, 17]])
+        assert np.abs(q_gpu[:, 18] - q_cpu[:, 18]).max() < 1e-5
+
+
 def test_fftcc3d_out_of_volume_pois_are_left_untouched(engine, vol):
     ref, tar, _ = vol
     xyz = np.array([[5, 30, 30], [30, 5, 30], [30, 30, 5], [70, 30, 30], [36, 32, 40]], np.float32)
