@@ -37,17 +37,29 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into one shared library."""
+    """Compile every CUDA source for sm_100a into one shared library (objects in parallel, then one link)."""
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cu, _ = sources()
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + cu
+    nvcc = [_nvcc()]
     # the image's CXX points at a gcc without OpenMP specs; nvcc only needs a host g++
-    env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    subprocess.check_call(cmd, env=env)
+        nvcc += ["-ccbin", "/usr/bin/g++"]
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        subprocess.check_call(nvcc + compile_flags + ["-c", "-o", obj, src])
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(cu), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, cu))
+    subprocess.check_call(nvcc + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + objs)
+    shutil.rmtree(obj_dir, ignore_errors=True)
     return LIB_PATH
 
 
