@@ -24,8 +24,7 @@
 
 namespace ocb {
 
-constexpr int ICGN3D_THREADS = 256;
-constexpr int ICGN3D_WARPS = ICGN3D_THREADS / 32;
+constexpr int ICGN3D_MAX_WARPS = 16; // CTAs run 8 warps (two CTAs per SM) or, when only one slab-carrying CTA fits, 16
 
 // ---- ICGN3D1::prepareRef: Gradient3D4::getGradientX/Y/Z, src/oc_gradient.cpp:143-231 ----------
 // Output is packed {ref, gx, gy, gz} per voxel so that IC-GN fetches a sample's constants with one 16-byte load.
@@ -85,7 +84,7 @@ constexpr int NITER = 3 + NP3;            // d1, d2, rd, SD[12]
 constexpr int ICGN3D_TILE_MARGIN = 1;
 
 struct Icgn3dShared {
-	float part[ICGN3D_WARPS][NSETUP]; // per-warp partial sums
+	float part[ICGN3D_MAX_WARPS][NSETUP]; // per-warp partial sums
 	float tot[NSETUP];
 	float L[NH3];   // packed Cholesky factor (diag = 1/L_ii)
 	float S[NP3], SF[NP3];
@@ -168,9 +167,11 @@ __host__ __device__ inline int icgn3d_tile_y(int ry) { return 2 * ry + 1 + 3 + 2
 __host__ __device__ inline int icgn3d_tile_z(int slab_k) { return slab_k + 3 + 2 * ICGN3D_TILE_MARGIN; }
 
 // RC > 0: radius known at compile time (rx == ry == rz == RC): tile pitches become immediates.
-template <int RC>
-__global__ void __launch_bounds__(ICGN3D_THREADS, 2) icgn3d1_kernel(Image3D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg, int rz_arg,
+// THREADS: 256 (two CTAs per SM) or 512 (large radii: the slab leaves room for one CTA only, which then brings 16 warps)
+template <int RC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg, int rz_arg,
 	float conv_criterion, float stop_condition, int slab_k, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_coef, int use_tma) {
+	constexpr int ICGN3D_THREADS = THREADS, ICGN3D_WARPS = THREADS / 32;
 	extern __shared__ __align__(128) float dsmem[];
 	__shared__ Icgn3dShared sh;
 	uint64_t* bar = (uint64_t*)dsmem;
@@ -489,7 +490,9 @@ int icgn3d1_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, 
 	const int box[3] = { icgn3d_tile_x(rx), icgn3d_tile_y(ry), icgn3d_tile_z(slab_k) };
 	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm, img.coef, 3, dims, box);
 	void (*kern)(Image3D, float*, int, int, int, int, float, float, int, int*, const CUtensorMap, int);
-	kern = (rx == 16 && ry == 16 && rz == 16) ? icgn3d1_kernel<16> : icgn3d1_kernel<0>;
+	const int threads = ctas == 1 ? 512 : 256;
+	if (ctas == 1) kern = icgn3d1_kernel<0, 512>;
+	else kern = (rx == 16 && ry == 16 && rz == 16) ? icgn3d1_kernel<16, 256> : icgn3d1_kernel<0, 256>;
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
 	*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
@@ -497,7 +500,7 @@ int icgn3d1_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, 
 	long long grid = (long long)sm_count * ctas;
 	if (grid > (long long)n) grid = (long long)n;
 	if (grid < 1) grid = 1;
-	kern<<<(int)grid, ICGN3D_THREADS, smem, stream>>>(img, d_pois, (int)n, rx, ry, rz, conv, stop, slab_k, d_counter, tm, use_tma);
+	kern<<<(int)grid, threads, smem, stream>>>(img, d_pois, (int)n, rx, ry, rz, conv, stop, slab_k, d_counter, tm, use_tma);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;
 }
