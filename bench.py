@@ -461,17 +461,21 @@ def run_ours(args):
     icgn_avg_ms = sum(icgn_ms) / len(icgn_ms)
     bytes_per_launch = icgn_bytes_per_poi(kind, r) * n
     achieved = bytes_per_launch / (icgn_avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_pipes = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.config, {}).get("icgn_dram_bytes_per_launch")
+            rec = json.load(open(tp)).get(args.config, {})
+            traffic = rec.get("icgn_dram_bytes_per_launch")
+            if "ncu_issue_slots_busy_pct" in rec:  # the resources that actually bind, from the committed ncu capture
+                ncu_pipes = {"issue_slots_busy_pct": rec["ncu_issue_slots_busy_pct"], "fma_pipe_busy_pct": rec["ncu_fma_pipe_busy_pct"],
+                             "shared_mem_pipe_busy_pct": rec["ncu_mem_pipes_busy_pct"], "source": rec.get("ncu_source")}
         except Exception:
-            traffic = None
+            traffic, ncu_pipes = None, None
     roofline = {"bound": "hbm", "kernel": "icgn%s" % ("2d%d" % cfg["order"] if kind == "2d" else "3d1"), "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_poi": icgn_bytes_per_poi(kind, r), "kernel_ms": icgn_avg_ms,
-                "kernel_share_of_step": icgn_avg_ms / (sum(step_ms) / len(step_ms)),
+                "kernel_share_of_step": icgn_avg_ms / (sum(step_ms) / len(step_ms)), "binding_resources_ncu": ncu_pipes,
                 "note": "kernel is FP32-issue/shared-memory bound once tiles are on chip (DESIGN.md); the HBM fraction is reported as north_star asks"}
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only) ----------------
