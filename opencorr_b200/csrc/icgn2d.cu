@@ -41,6 +41,9 @@ namespace ocb {
 // (Horner weights, the 4-row accumulation) more than they relieve the issue port.  Kept for reference, off.
 #define ICGN2D_PACKED 0
 #endif
+#ifndef ICGN2D_MINB
+#define ICGN2D_MINB 16 // resident one-warp CTAs the 6-parameter kernels' register budget is sized for (16 -> 128 registers; measured best of 11/16/20)
+#endif
 #ifndef ICGN2D_UNROLL
 #define ICGN2D_UNROLL 3
 #endif
@@ -166,7 +169,7 @@ __device__ __forceinline__ void right_divide_2x6(float* rows, float* M) {
 // (the second launch bound keeps the register file from limiting residency below what the slab allows:
 //  <= 96 registers for the 6-parameter kernels, <= 144 for the 12-parameter ones)
 template <int NP, int RC, bool LM, int WPP>
-__global__ void __launch_bounds__(32 * WPP, NP == 6 ? 20 / WPP : 7) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
+__global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
 	float conv_criterion, float stop_condition, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_ref,
 	const __grid_constant__ CUtensorMap tm_tar, int use_tma, const float* __restrict__ center_offsets, float lm_lambda, float lm_alpha,
 	float lm_beta) {
