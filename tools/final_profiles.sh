@@ -14,3 +14,7 @@ g=lambda k: float(r[h.index(k)].replace(',',''))
 print(json.dumps({'kernel':'icgn2d_kernel<6,16,false,1> config B','dram_bytes_read':g('dram__bytes_read.sum'),'dram_bytes_write':g('dram__bytes_write.sum'),'unit':r[h.index('dram__bytes_read.sum')] and rows[1][h.index('dram__bytes_read.sum')]}))
 " > gpurun_out/traffic_raw.json
 cat gpurun_out/pytest_gpu.txt
+# the reference's own 2D example (compiled unchanged against the shim) on its shipped image pair: its timing file next to the shipped one
+rm -rf /tmp/ex && mkdir -p "/tmp/ex/d:/dic_tests/2d_dic" && cp tests/golden/oht_cfrp_0.bmp tests/golden/oht_cfrp_4.bmp "/tmp/ex/d:/dic_tests/2d_dic/"
+(cd /tmp/ex && for i in 1 2; do $OLDPWD/examples/bin/test_2d_dic_fftcc_icgn1 < /dev/null > /tmp/ex/out.txt 2>&1; done; cat /tmp/ex/out.txt | head -5)
+cp "/tmp/ex/d:/dic_tests/2d_dic/oht_cfrp_4_fftcc_icgn1_r16_time.csv" gpurun_out/r1_example_2d_dic_fftcc_icgn1_time.csv
