@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- POIs/sec of the FFT-CC -> IC-GN hot path (BASELINE.json metric) on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config B|C|D|A|E] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config B|C|D|A|E|F] [--impl ours|reference]
   N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one pass of the hot path (FFT-CC initial guess + IC-GN to convergence, prepare() included)
@@ -15,7 +15,9 @@ inside the e2e leg.
            (sum over ranks of POIs / max-over-ranks device time, CUDA events, L2 flushed between steps)
   e2e    : same metric through the host-buffer C-ABI calls (pinned host memory): image H2D (+ NCCL
            broadcast), prepare, POI H2D, kernels, (gather,) POI D2H inside the timed region
-  roofline: dominant kernel (IC-GN) algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS hbm_gbs
+  e2e_u8_images: the e2e step with the pair handed over as 8-bit arrays (what the image files hold), N=1 only
+  roofline: dominant kernel (IC-GN) algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS hbm_gbs; `traffic` and
+           `binding_resources_ncu` (issue-slot / FMA / shared-memory pipe utilisation) come from the committed ncu capture
   cpu_baseline: the oracle port of the reference (oracle/, g++ -O3 -fopenmp, nproc-1 threads like
            the reference examples) timed on this box's host cores on the same workload
 
