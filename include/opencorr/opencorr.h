@@ -131,6 +131,17 @@ namespace opencorr
 		float r[7];
 	};
 
+	union DisplacementVector3D
+	{
+		struct { float u, v, w; };
+		float p[3];
+	};
+	union Result2DS
+	{
+		struct { float r1r2_zncc, r1t1_zncc, r1t2_zncc, r2_x, r2_y, t1_x, t1_y, t2_x, t2_y; };
+		float r[9];
+	};
+
 	class POI2D : public Point2D
 	{
 	public:
@@ -173,6 +184,31 @@ namespace opencorr
 			subset_radius.z = 0.f;
 		}
 	};
+	// stereo / 3D DIC record (src/oc_poi.h:140-186)
+	class POI2DS : public Point2D
+	{
+	public:
+		DisplacementVector3D deformation;
+		Result2DS result;
+		Point3D ref_coor, tar_coor;
+		StrainVector3D strain;
+		Point2D subset_radius;
+		inline POI2DS(int x, int y) : Point2D(x, y) { clear(); }
+		inline POI2DS(float x, float y) : Point2D(x, y) { clear(); }
+		inline POI2DS(Point2D location) : Point2D(location) { clear(); }
+		inline ~POI2DS() {}
+		inline void clear()
+		{
+			std::fill(std::begin(deformation.p), std::end(deformation.p), 0.f);
+			std::fill(std::begin(result.r), std::end(result.r), 0.f);
+			ref_coor = Point3D();
+			tar_coor = Point3D();
+			std::fill(std::begin(strain.e), std::end(strain.e), 0.f);
+			subset_radius.x = 0.f;
+			subset_radius.y = 0.f;
+		}
+	};
+	static_assert(sizeof(POI2DS) == OCB_POI2DS_FLOATS * sizeof(float), "POI2DS must be the 112-byte record of the C ABI");
 	static_assert(sizeof(POI2D) == OCB_POI2D_FLOATS * sizeof(float), "POI2D must be the 100-byte record of the C ABI");
 	static_assert(sizeof(POI3D) == OCB_POI3D_FLOATS * sizeof(float), "POI3D must be the 124-byte record of the C ABI");
 	static_assert(sizeof(Point2D) == 2 * sizeof(float), "Point2D must be two packed floats (centre-offset queues cross the C ABI verbatim)");
@@ -190,6 +226,94 @@ namespace opencorr
 		inline int rows() const { return n_rows; }
 		inline int cols() const { return n_cols; }
 	};
+
+	namespace b200
+	{
+		// Baseline TIFF reader (no OpenCV here): classic TIFF (not BigTIFF), grayscale, 8 or 16 bits per sample (16-bit is scaled
+		// to 8 bits like cv::IMREAD_GRAYSCALE), strips, uncompressed or PackBits, any number of pages.  Returns one 8-bit
+		// plane per page, all of the first page's size.
+		inline std::vector<std::vector<unsigned char>> readTiffPages(const std::string& file_path, int& width, int& height)
+		{
+			std::ifstream in(file_path, std::ios::in | std::ios::binary);
+			if (!in.is_open()) throw std::string("Fail to load tiff: " + file_path);
+			std::vector<unsigned char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+			if (buf.size() < 8) throw std::string("Not a TIFF file: " + file_path);
+			const bool le = buf[0] == 'I' && buf[1] == 'I';
+			if (!le && !(buf[0] == 'M' && buf[1] == 'M')) throw std::string("Not a TIFF file: " + file_path);
+			auto rd16 = [&](size_t o) -> uint32_t {
+				if (o + 2 > buf.size()) throw std::string("Truncated TIFF: " + file_path);
+				return le ? (uint32_t)buf[o] | ((uint32_t)buf[o + 1] << 8) : (uint32_t)buf[o + 1] | ((uint32_t)buf[o] << 8);
+			};
+			auto rd32 = [&](size_t o) -> uint32_t {
+				if (o + 4 > buf.size()) throw std::string("Truncated TIFF: " + file_path);
+				return le ? (uint32_t)buf[o] | ((uint32_t)buf[o + 1] << 8) | ((uint32_t)buf[o + 2] << 16) | ((uint32_t)buf[o + 3] << 24)
+						  : (uint32_t)buf[o + 3] | ((uint32_t)buf[o + 2] << 8) | ((uint32_t)buf[o + 1] << 16) | ((uint32_t)buf[o] << 24);
+			};
+			if (rd16(2) != 42) throw std::string("Unsupported TIFF flavour (BigTIFF?): " + file_path);
+			struct Page { uint32_t w = 0, h = 0, bits = 8, comp = 1, photo = 1, spp = 1, rps = 0xffffffffu; std::vector<uint32_t> off, cnt; };
+			std::vector<Page> pages;
+			uint32_t ifd = rd32(4);
+			while (ifd != 0) {
+				Page pg;
+				const uint32_t n = rd16(ifd);
+				for (uint32_t e = 0; e < n; e++) {
+					const size_t o = (size_t)ifd + 2 + 12 * (size_t)e;
+					const uint32_t tag = rd16(o), type = rd16(o + 2), count = rd32(o + 4);
+					const uint32_t tsize = type == 3 ? 2 : (type == 4 ? 4 : 1);
+					const size_t vo = (size_t)count * tsize <= 4 ? o + 8 : rd32(o + 8);
+					auto val = [&](uint32_t i) -> uint32_t { return type == 3 ? rd16(vo + 2 * (size_t)i) : (type == 4 ? rd32(vo + 4 * (size_t)i) : buf.at(vo + i)); };
+					switch (tag) {
+					case 256: pg.w = val(0); break;
+					case 257: pg.h = val(0); break;
+					case 258: pg.bits = val(0); break;
+					case 259: pg.comp = val(0); break;
+					case 262: pg.photo = val(0); break;
+					case 277: pg.spp = val(0); break;
+					case 278: pg.rps = val(0); break;
+					case 273: for (uint32_t i = 0; i < count; i++) pg.off.push_back(val(i)); break;
+					case 279: for (uint32_t i = 0; i < count; i++) pg.cnt.push_back(val(i)); break;
+					default: break;
+					}
+				}
+				if (pg.spp != 1 || (pg.bits != 8 && pg.bits != 16) || (pg.comp != 1 && pg.comp != 32773) || pg.off.empty() || pg.off.size() != pg.cnt.size())
+					throw std::string("Unsupported TIFF page (need grayscale, 8/16 bit, uncompressed or PackBits strips): " + file_path);
+				pages.push_back(pg);
+				ifd = rd32((size_t)ifd + 2 + 12 * (size_t)n);
+			}
+			if (pages.empty()) throw std::string("Fail to load tiff: " + file_path);
+			width = (int)pages[0].w;
+			height = (int)pages[0].h;
+			std::vector<std::vector<unsigned char>> out(pages.size());
+			std::vector<unsigned char> raw;
+			for (size_t z = 0; z < pages.size(); z++) {
+				const Page& pg = pages[z];
+				if ((int)pg.w != width || (int)pg.h != height) throw std::string("TIFF pages differ in size: " + file_path);
+				const size_t bps = pg.bits / 8, want = (size_t)pg.w * pg.h * bps;
+				raw.clear();
+				for (size_t k = 0; k < pg.off.size(); k++) {
+					if ((size_t)pg.off[k] + pg.cnt[k] > buf.size()) throw std::string("Truncated TIFF: " + file_path);
+					const unsigned char* p = &buf[pg.off[k]];
+					if (pg.comp == 1) raw.insert(raw.end(), p, p + pg.cnt[k]);
+					else { // PackBits
+						size_t i = 0;
+						while (i < pg.cnt[k]) {
+							const int c = (signed char)p[i++];
+							if (c >= 0) { for (int t = 0; t <= c && i < pg.cnt[k]; t++) raw.push_back(p[i++]); }
+							else if (c != -128 && i < pg.cnt[k]) { raw.insert(raw.end(), (size_t)(1 - c), p[i]); i++; }
+						}
+					}
+				}
+				if (raw.size() < want) throw std::string("Truncated TIFF page: " + file_path);
+				out[z].resize((size_t)pg.w * pg.h);
+				for (size_t i = 0; i < (size_t)pg.w * pg.h; i++) {
+					uint32_t v = bps == 1 ? raw[i] : (le ? (uint32_t)raw[2 * i + 1] : (uint32_t)raw[2 * i]); // 16 -> 8 bit: the high byte
+					if (pg.photo == 0) v = 255 - v; // WhiteIsZero
+					out[z][i] = (unsigned char)v;
+				}
+			}
+			return out;
+		}
+	} // namespace b200
 
 	class Image2D
 	{
@@ -263,6 +387,12 @@ namespace opencorr
 				width = vals[0]; height = vals[1]; size = (unsigned int)(width * height);
 				eg_mat.resize(height, width);
 				for (size_t i = 0; i < (size_t)width * height; i++) eg_mat.data[i] = (float)buf[pos + i];
+			} else if (buf.size() > 8 && ((buf[0] == 'I' && buf[1] == 'I') || (buf[0] == 'M' && buf[1] == 'M'))) {
+				int w = 0, h = 0;
+				const std::vector<std::vector<unsigned char>> pages = b200::readTiffPages(file_path, w, h); // first page
+				width = w; height = h; size = (unsigned int)(w * h);
+				eg_mat.resize(h, w);
+				for (size_t i = 0; i < (size_t)w * h; i++) eg_mat.data[i] = (float)pages[0][i];
 			} else {
 				throw std::string("Fail to load file: " + file_path);
 			}
@@ -309,85 +439,15 @@ namespace opencorr
 			in.read((char*)**vol_mat, sizeof(float) * size);
 			if (!in) throw std::string("Failed to read bin file: " + file_path);
 		}
-		// multi-page TIFF, one page per z slice (src/oc_image.cpp:112-150 reads it with cv::imreadmulti(IMREAD_GRAYSCALE)).
-		// Baseline subset read here without OpenCV: classic TIFF (not BigTIFF), grayscale, 8 or 16 bits per sample
-		// (16-bit is scaled to 8 bits like IMREAD_GRAYSCALE), strips, uncompressed or PackBits.
+		// multi-page TIFF, one page per z slice (src/oc_image.cpp:112-150 reads it with cv::imreadmulti(IMREAD_GRAYSCALE))
 		inline void loadTiff(std::string file_path)
 		{
-			std::ifstream in(file_path, std::ios::in | std::ios::binary);
-			if (!in.is_open()) throw std::string("Fail to load multi-page tiff: " + file_path);
-			std::vector<unsigned char> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-			if (buf.size() < 8) throw std::string("Not a TIFF file: " + file_path);
-			const bool le = buf[0] == 'I' && buf[1] == 'I';
-			if (!le && !(buf[0] == 'M' && buf[1] == 'M')) throw std::string("Not a TIFF file: " + file_path);
-			auto rd16 = [&](size_t o) -> uint32_t {
-				if (o + 2 > buf.size()) throw std::string("Truncated TIFF: " + file_path);
-				return le ? (uint32_t)buf[o] | ((uint32_t)buf[o + 1] << 8) : (uint32_t)buf[o + 1] | ((uint32_t)buf[o] << 8);
-			};
-			auto rd32 = [&](size_t o) -> uint32_t {
-				if (o + 4 > buf.size()) throw std::string("Truncated TIFF: " + file_path);
-				return le ? (uint32_t)buf[o] | ((uint32_t)buf[o + 1] << 8) | ((uint32_t)buf[o + 2] << 16) | ((uint32_t)buf[o + 3] << 24)
-						  : (uint32_t)buf[o + 3] | ((uint32_t)buf[o + 2] << 8) | ((uint32_t)buf[o + 1] << 16) | ((uint32_t)buf[o] << 24);
-			};
-			if (rd16(2) != 42) throw std::string("Unsupported TIFF flavour (BigTIFF?): " + file_path);
-			struct Page { uint32_t w = 0, h = 0, bits = 8, comp = 1, photo = 1, spp = 1, rps = 0xffffffffu; std::vector<uint32_t> off, cnt; };
-			std::vector<Page> pages;
-			uint32_t ifd = rd32(4);
-			while (ifd != 0) {
-				Page pg;
-				const uint32_t n = rd16(ifd);
-				for (uint32_t e = 0; e < n; e++) {
-					const size_t o = (size_t)ifd + 2 + 12 * (size_t)e;
-					const uint32_t tag = rd16(o), type = rd16(o + 2), count = rd32(o + 4);
-					const uint32_t tsize = type == 3 ? 2 : (type == 4 ? 4 : 1);
-					const size_t vo = (size_t)count * tsize <= 4 ? o + 8 : rd32(o + 8);
-					auto val = [&](uint32_t i) -> uint32_t { return type == 3 ? rd16(vo + 2 * (size_t)i) : (type == 4 ? rd32(vo + 4 * (size_t)i) : buf.at(vo + i)); };
-					switch (tag) {
-					case 256: pg.w = val(0); break;
-					case 257: pg.h = val(0); break;
-					case 258: pg.bits = val(0); break;
-					case 259: pg.comp = val(0); break;
-					case 262: pg.photo = val(0); break;
-					case 277: pg.spp = val(0); break;
-					case 278: pg.rps = val(0); break;
-					case 273: for (uint32_t i = 0; i < count; i++) pg.off.push_back(val(i)); break;
-					case 279: for (uint32_t i = 0; i < count; i++) pg.cnt.push_back(val(i)); break;
-					default: break;
-					}
-				}
-				if (pg.spp != 1 || (pg.bits != 8 && pg.bits != 16) || (pg.comp != 1 && pg.comp != 32773) || pg.off.empty() || pg.off.size() != pg.cnt.size())
-					throw std::string("Unsupported TIFF page (need grayscale, 8/16 bit, uncompressed or PackBits strips): " + file_path);
-				pages.push_back(pg);
-				ifd = rd32((size_t)ifd + 2 + 12 * (size_t)n);
-			}
-			if (pages.empty()) throw std::string("Fail to load multi-page tiff: " + file_path);
-			allocate((int)pages[0].w, (int)pages[0].h, (int)pages.size());
-			std::vector<unsigned char> raw;
+			int w = 0, h = 0;
+			const std::vector<std::vector<unsigned char>> pages = b200::readTiffPages(file_path, w, h);
+			allocate(w, h, (int)pages.size());
 			for (size_t z = 0; z < pages.size(); z++) {
-				const Page& pg = pages[z];
-				if ((int)pg.w != dim_x || (int)pg.h != dim_y) throw std::string("TIFF pages differ in size: " + file_path);
-				const size_t bps = pg.bits / 8, want = (size_t)pg.w * pg.h * bps;
-				raw.clear();
-				for (size_t k = 0; k < pg.off.size(); k++) {
-					if ((size_t)pg.off[k] + pg.cnt[k] > buf.size()) throw std::string("Truncated TIFF: " + file_path);
-					const unsigned char* p = &buf[pg.off[k]];
-					if (pg.comp == 1) raw.insert(raw.end(), p, p + pg.cnt[k]);
-					else { // PackBits
-						size_t i = 0;
-						while (i < pg.cnt[k]) {
-							const int c = (signed char)p[i++];
-							if (c >= 0) { for (int t = 0; t <= c && i < pg.cnt[k]; t++) raw.push_back(p[i++]); }
-							else if (c != -128 && i < pg.cnt[k]) { raw.insert(raw.end(), (size_t)(1 - c), p[i]); i++; }
-						}
-					}
-				}
-				if (raw.size() < want) throw std::string("Truncated TIFF page: " + file_path);
 				float* dst = vol_mat[z][0];
-				for (size_t i = 0; i < (size_t)pg.w * pg.h; i++) {
-					uint32_t v = bps == 1 ? raw[i] : (le ? (uint32_t)raw[2 * i + 1] : (uint32_t)raw[2 * i]); // 16 -> 8 bit: the high byte
-					if (pg.photo == 0) v = 255 - v; // WhiteIsZero
-					dst[i] = (float)v;
-				}
+				for (size_t i = 0; i < (size_t)w * h; i++) dst[i] = (float)pages[z][i];
 			}
 		}
 		inline void load(std::string file_path)
@@ -752,7 +812,7 @@ namespace opencorr
 
 	// Strain (reference src/oc_strain.h:33-70, src/oc_strain.cpp): least-squares plane fit of the displacement field
 	// over each POI's neighbourhood.  prepare() builds kd-trees in the reference; here the spatial binning is part of
-	// the GPU call, so prepare() is empty.  The stereo (POI2DS) overloads are out of scope.
+	// the GPU call, so prepare() is empty.  
 	class Strain
 	{
 	protected:
@@ -784,6 +844,7 @@ namespace opencorr
 		void setApproximation(int approximation) { this->approximation = approximation; }
 
 		void prepare(std::vector<POI2D>&) {}
+		void prepare(std::vector<POI2DS>&) {}
 		void prepare(std::vector<POI3D>&) {}
 
 		void compute(std::vector<POI2D>& poi_queue)
@@ -791,6 +852,12 @@ namespace opencorr
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
 			e.check(ocb_strain2d(e.context(), poi_queue.data(), poi_queue.size(), subregion_radius, neighbor_number_min, zncc_threshold, approximation));
+		}
+		void compute(std::vector<POI2DS>& poi_queue) // src/oc_strain.cpp:362-371 (per POI :252-360)
+		{
+			b200::Engine& e = b200::Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.check(ocb_strain2ds(e.context(), poi_queue.data(), poi_queue.size(), subregion_radius, neighbor_number_min, zncc_threshold, approximation));
 		}
 		void compute(std::vector<POI3D>& poi_queue)
 		{
@@ -1246,6 +1313,43 @@ namespace opencorr
 				poi_queue.push_back(poi);
 			}
 			return poi_queue;
+		}
+		// src/oc_io.cpp:506-584
+		std::vector<POI2DS> loadTable2DS()
+		{
+			std::vector<POI2DS> poi_queue;
+			for (const std::vector<float>& k : b200::readTable(file_path, delimiter, 28)) {
+				POI2DS poi(k[0], k[1]);
+				for (int i = 0; i < 3; i++) poi.deformation.p[i] = k[2 + i];
+				for (int i = 0; i < 9; i++) poi.result.r[i] = k[5 + i];
+				poi.ref_coor.x = k[14]; poi.ref_coor.y = k[15]; poi.ref_coor.z = k[16];
+				poi.tar_coor.x = k[17]; poi.tar_coor.y = k[18]; poi.tar_coor.z = k[19];
+				for (int i = 0; i < 6; i++) poi.strain.e[i] = k[20 + i];
+				poi.subset_radius.x = k[26];
+				poi.subset_radius.y = k[27];
+				poi_queue.push_back(poi);
+			}
+			return poi_queue;
+		}
+		// src/oc_io.cpp:586-670
+		void saveTable2DS(std::vector<POI2DS>& poi_queue)
+		{
+			b200::TableWriter t(delimiter);
+			const char* head[] = { "x", "y", "u", "v", "w", "r1r2 ZNCC", "r1t1 ZNCC", "r1t2 ZNCC", "r2_x", "r2_y", "t1_x", "t1_y", "t2_x", "t2_y", "ref_x", "ref_y",
+				"ref_z", "tar_x", "tar_y", "tar_z", "exx", "eyy", "ezz", "exy", "eyz", "ezx", "subset_rx", "subset_ry" };
+			for (const char* h : head) t.text(h);
+			t.endRow();
+			for (auto iter = poi_queue.begin(); iter != poi_queue.end(); iter++) {
+				t.num(iter->x); t.num(iter->y);
+				for (int i = 0; i < 3; i++) t.num(iter->deformation.p[i]);
+				for (int i = 0; i < 9; i++) t.num(iter->result.r[i]);
+				t.num(iter->ref_coor.x); t.num(iter->ref_coor.y); t.num(iter->ref_coor.z);
+				t.num(iter->tar_coor.x); t.num(iter->tar_coor.y); t.num(iter->tar_coor.z);
+				for (int i = 0; i < 6; i++) t.num(iter->strain.e[i]);
+				t.num(iter->subset_radius.x); t.num(iter->subset_radius.y);
+				t.endRow();
+			}
+			t.save(file_path);
 		}
 		// src/oc_io.cpp:318-373
 		void saveTable2D(std::vector<POI2D>& poi_queue)

@@ -46,6 +46,7 @@ extern "C" {
 
 #define OCB_POI2D_FLOATS 25
 #define OCB_POI3D_FLOATS 31
+#define OCB_POI2DS_FLOATS 28 /* stereo-DIC record, src/oc_poi.h:140-186 */
 
 typedef struct ocb_ctx ocb_ctx;
 
@@ -156,6 +157,11 @@ int ocb_strain3d(ocb_ctx* ctx, void* poi3d, size_t n, float radius, int min_neig
 /* Strain::compute(POI2D* poi, queue) / (POI3D* poi, queue) for the queue member `index`: fitted whatever its own ZNCC. */
 int ocb_strain2d_single(ocb_ctx* ctx, void* poi2d, size_t n, size_t index, float radius, int min_neighbors, float zncc_threshold, int approximation);
 int ocb_strain3d_single(ocb_ctx* ctx, void* poi3d, size_t n, size_t index, float radius, int min_neighbors, float zncc_threshold, int approximation);
+/* Stereo-DIC queues (POI2DS records, OCB_POI2DS_FLOATS floats: x y | u v w | r1r2 r1t1 r1t2 ZNCC r2_x r2_y t1_x t1_y t2_x t2_y |
+ * ref_coor | tar_coor | e[6] | subset_radius, src/oc_poi.h:140-186): Strain::compute(std::vector<POI2DS>&) src/oc_strain.cpp:362-371
+ * (per POI :252-360) -- neighbours searched in the image plane, plane fit over ref_coor and u, v, w, all three ZNCCs tested. */
+int ocb_strain2ds(ocb_ctx* ctx, void* poi2ds, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
+int ocb_strain2ds_dev(ocb_ctx* ctx, void* d_poi2ds, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
 int ocb_strain2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
 int ocb_strain3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
 

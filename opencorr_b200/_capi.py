@@ -56,6 +56,8 @@ SIGNATURES = {
     "ocb_epipolar_search2d_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f]),
     "ocb_strain2d": (_i, [_vp, _vp, _sz, _f, _i, _f, _i]),
     "ocb_strain3d": (_i, [_vp, _vp, _sz, _f, _i, _f, _i]),
+    "ocb_strain2ds": (_i, [_vp, _vp, _sz, _f, _i, _f, _i]),
+    "ocb_strain2ds_dev": (_i, [_vp, _vp, _sz, _f, _i, _f, _i]),
     "ocb_strain2d_single": (_i, [_vp, _vp, _sz, _sz, _f, _i, _f, _i]),
     "ocb_strain3d_single": (_i, [_vp, _vp, _sz, _sz, _f, _i, _f, _i]),
     "ocb_strain2d_dev": (_i, [_vp, _vp, _sz, _f, _i, _f, _i]),

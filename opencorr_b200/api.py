@@ -181,7 +181,10 @@ class Engine:
 
     def strain(self, q, radius, min_neighbors, zncc_threshold=0.9, approximation=1):
         """Strain::prepare + compute(queue) (reference src/oc_strain.cpp) on a POI2D [n,25] or POI3D [n,31] queue."""
-        if q.ndim == 2 and q.shape[1] == POI3D_FLOATS:
+        if q.ndim == 2 and q.shape[1] == 28:  # POI2DS records (stereo DIC)
+            _check_queue(q, 28)
+            fn = self._lib.ocb_strain2ds
+        elif q.ndim == 2 and q.shape[1] == POI3D_FLOATS:
             _check_queue(q, POI3D_FLOATS)
             fn = self._lib.ocb_strain3d
         else:

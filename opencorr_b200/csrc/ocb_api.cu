@@ -738,7 +738,7 @@ static int strain_host(ocb_ctx* ctx, int dim, void* poi, size_t n, float radius,
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	int rc;
-	const size_t bytes = n * (dim == 2 ? OCB_POI2D_FLOATS : OCB_POI3D_FLOATS) * sizeof(float);
+	const size_t bytes = n * (dim == 2 ? OCB_POI2D_FLOATS : (dim == 3 ? OCB_POI3D_FLOATS : OCB_POI2DS_FLOATS)) * sizeof(float);
 	if ((rc = stage_pois(ctx, poi, bytes))) return rc;
 	if ((rc = strain_dev(ctx, dim, ctx->d_poi, n, radius, min_neighbors, zncc_threshold, approximation, only))) return rc;
 	return unstage_pois(ctx, poi, bytes);
@@ -749,6 +749,12 @@ int ocb_strain2d(ocb_ctx* ctx, void* poi2d, size_t n, float radius, int min_neig
 }
 int ocb_strain3d(ocb_ctx* ctx, void* poi3d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation) {
 	return strain_host(ctx, 3, poi3d, n, radius, min_neighbors, zncc_threshold, approximation);
+}
+int ocb_strain2ds(ocb_ctx* ctx, void* poi2ds, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_host(ctx, 23, poi2ds, n, radius, min_neighbors, zncc_threshold, approximation);
+}
+int ocb_strain2ds_dev(ocb_ctx* ctx, void* d_poi2ds, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation) {
+	return strain_dev(ctx, 23, d_poi2ds, n, radius, min_neighbors, zncc_threshold, approximation);
 }
 int ocb_strain2d_single(ocb_ctx* ctx, void* poi2d, size_t n, size_t index, float radius, int min_neighbors, float zncc_threshold, int approximation) {
 	return strain_host(ctx, 2, poi2d, n, radius, min_neighbors, zncc_threshold, approximation, (long long)index);

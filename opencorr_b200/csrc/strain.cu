@@ -28,9 +28,15 @@ namespace ocb {
 
 namespace {
 
-template <int D> struct SL;
-template <> struct SL<2> { enum { NF = P2_N, ZNCC = P2_ZNCC, STRAIN = P2_STRAIN, U = P2_DEF + D2_U, V = P2_DEF + D2_V, W = P2_DEF + D2_V, NE = 3 }; };
-template <> struct SL<3> { enum { NF = P3_N, ZNCC = P3_ZNCC, STRAIN = P3_STRAIN, U = P3_DEF + 0, V = P3_DEF + 4, W = P3_DEF + 8, NE = 6 }; };
+// MODE 2: POI2D, 3: POI3D, 23: POI2DS (stereo DIC, src/oc_strain.cpp:252-371: neighbours are searched in the image plane
+// of the primary view, the plane fit runs over the reconstructed 3D coordinates ref_coor and u, v, w; a POI counts when
+// r1r2, r1t1 and r1t2 ZNCC all pass the threshold).  SD = search dimensions, FD = fit dimensions, FC = offset of the
+// fit coordinates in the record, Z0 / NZ = the ZNCC fields that must pass.
+// POI2DS record (src/oc_poi.h:140-186), 28 floats: x y | u v w | r1r2 r1t1 r1t2 r2_x r2_y t1_x t1_y t2_x t2_y | ref_coor | tar_coor | e[6] | subset_radius
+template <int MODE> struct SL;
+template <> struct SL<2> { enum { NF = P2_N, SD = 2, FD = 2, FC = 0, Z0 = P2_ZNCC, NZ = 1, STRAIN = P2_STRAIN, U = P2_DEF + D2_U, V = P2_DEF + D2_V, W = P2_DEF + D2_V }; };
+template <> struct SL<3> { enum { NF = P3_N, SD = 3, FD = 3, FC = 0, Z0 = P3_ZNCC, NZ = 1, STRAIN = P3_STRAIN, U = P3_DEF + 0, V = P3_DEF + 4, W = P3_DEF + 8 }; };
+template <> struct SL<23> { enum { NF = 28, SD = 2, FD = 3, FC = 14, Z0 = 5, NZ = 3, STRAIN = 20, U = 2, V = 3, W = 4 }; };
 
 struct StrainGrid {
 	float lo[3];
@@ -51,9 +57,10 @@ inline float ordered_to_float(unsigned int o) {
 }
 
 // bbox[0..2] = min (ordered encoding), bbox[3..5] = max
-template <int D>
+template <int MODE>
 __global__ void strain_bbox_kernel(const float* __restrict__ pois, int n, unsigned int* __restrict__ bbox) {
-	typedef SL<D> L;
+	typedef SL<MODE> L;
+	constexpr int D = L::SD;
 	unsigned int mn[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu }, mx[3] = { 0u, 0u, 0u };
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const float* p = pois + (size_t)i * L::NF;
@@ -95,9 +102,10 @@ __device__ __forceinline__ void strain_cell(const StrainGrid& g, const float* p,
 	}
 }
 
-template <int D>
+template <int MODE>
 __global__ void strain_keys_kernel(const float* __restrict__ pois, int n, StrainGrid g, unsigned int* __restrict__ keys, int* __restrict__ vals) {
-	typedef SL<D> L;
+	typedef SL<MODE> L;
+	constexpr int D = L::SD;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const float* p = pois + (size_t)i * L::NF;
 		bool fin = true;
@@ -114,15 +122,20 @@ __global__ void strain_keys_kernel(const float* __restrict__ pois, int n, Strain
 	}
 }
 
-// sorted, compact copies: pos = {x, y, z|0, fit flag (ZNCC >= threshold)}, disp = {u, v, w|0, 0}
-template <int D>
+// sorted, compact copies: pos = {x, y, z|0, fit flag (every ZNCC >= threshold)}, disp = {u, v, w|0, 0},
+// fpos = the fit coordinates when they are not the search coordinates (POI2DS: ref_coor)
+template <int MODE>
 __global__ void strain_gather_kernel(const float* __restrict__ pois, int n, const int* __restrict__ order, float zncc_threshold,
-	float4* __restrict__ pos, float4* __restrict__ disp) {
-	typedef SL<D> L;
+	float4* __restrict__ pos, float4* __restrict__ disp, float4* __restrict__ fpos) {
+	typedef SL<MODE> L;
 	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
 		const float* p = pois + (size_t)order[s] * L::NF;
-		pos[s] = make_float4(p[0], p[1], D == 3 ? p[2] : 0.f, p[L::ZNCC] >= zncc_threshold ? 1.f : 0.f);
-		disp[s] = make_float4(p[L::U], p[L::V], D == 3 ? p[L::W] : 0.f, 0.f);
+		bool good = true;
+#pragma unroll
+		for (int k = 0; k < L::NZ; k++) good = good && (p[L::Z0 + k] >= zncc_threshold);
+		pos[s] = make_float4(p[0], p[1], L::SD == 3 ? p[2] : 0.f, good ? 1.f : 0.f);
+		disp[s] = make_float4(p[L::U], p[L::V], L::FD == 3 ? p[L::W] : 0.f, 0.f);
+		if (L::FC != 0) fpos[s] = make_float4(p[L::FC], p[L::FC + 1], p[L::FC + 2], 0.f);
 	}
 }
 
@@ -240,12 +253,13 @@ __device__ void solve_normal(const FitSums<D>& s, double x[D][D + 1]) {
 		}
 }
 
-template <int D>
+template <int MODE>
 __global__ void __launch_bounds__(256) strain_kernel(float* __restrict__ pois, int n_valid, StrainGrid g, const unsigned int* __restrict__ keys,
-	const int* __restrict__ order, const float4* __restrict__ pos, const float4* __restrict__ disp, float radius, int k_min, int approximation,
-	int only) {
-	typedef SL<D> L;
-	constexpr int C = D + 1;
+	const int* __restrict__ order, const float4* __restrict__ pos, const float4* __restrict__ disp, const float4* __restrict__ fpos, float radius,
+	int k_min, int approximation, int only) {
+	typedef SL<MODE> L;
+	constexpr int D = L::SD, FD = L::FD; // search / fit dimensions
+	constexpr int C = FD + 1;
 	constexpr int ROWS = D == 2 ? 3 : 9;
 	const int lane = threadIdx.x & 31;
 	const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -272,7 +286,8 @@ __global__ void __launch_bounds__(256) strain_kernel(float* __restrict__ pois, i
 				run_hi = lower_bound_u32(keys, n_valid, base + cx1 + 1);
 			}
 		}
-		FitSums<D> sums;
+		const float4 fcentre = L::FC != 0 ? __ldg(fpos + s) : centre; // origin of the fit coordinates
+		FitSums<FD> sums;
 		sums.clear();
 		int found = 0;
 #pragma unroll 1
@@ -282,7 +297,7 @@ __global__ void __launch_bounds__(256) strain_kernel(float* __restrict__ pois, i
 				const float4 q = __ldg(pos + j);
 				if (dist2<D>(centre, q) < r2) {
 					found++;
-					if (q.w != 0.f) sums.add(centre, q, __ldg(disp + j));
+					if (q.w != 0.f) sums.add(fcentre, L::FC != 0 ? __ldg(fpos + j) : q, __ldg(disp + j));
 				}
 			}
 		}
@@ -317,16 +332,16 @@ __global__ void __launch_bounds__(256) strain_kernel(float* __restrict__ pois, i
 				prev_i = bi;
 				if (lane == 0) {
 					const float4 q = __ldg(pos + bs);
-					if (q.w != 0.f) sums.add(centre, q, __ldg(disp + bs));
+					if (q.w != 0.f) sums.add(fcentre, L::FC != 0 ? __ldg(fpos + bs) : q, __ldg(disp + bs));
 				}
 			}
 		}
 		sums.reduce();
 		if (lane == 0 && sums.a[0] >= (double)k_min) { // enough neighbours with good ZNCC (:200-201)
-			double x[D][C];
-			solve_normal<D>(sums, x);
+			double x[FD][C];
+			solve_normal<FD>(sums, x);
 			float* e = pois + (size_t)__ldg(order + s) * L::NF + L::STRAIN;
-			if (D == 2) {
+			if (FD == 2) {
 				const float ux = (float)x[0][1], uy = (float)x[0][2], vx = (float)x[1][1], vy = (float)x[1][2];
 				if (approximation == 2) { // Green strain (:229-235)
 					e[0] = ux + 0.5f * (ux * ux + vx * vx);
@@ -340,7 +355,7 @@ __global__ void __launch_bounds__(256) strain_kernel(float* __restrict__ pois, i
 			} else {
 				const float ux = (float)x[0][1], uy = (float)x[0][2], uz = (float)x[0][C - 1];
 				const float vx = (float)x[1][1], vy = (float)x[1][2], vz = (float)x[1][C - 1];
-				const float wx = (float)x[D - 1][1], wy = (float)x[D - 1][2], wz = (float)x[D - 1][C - 1];
+				const float wx = (float)x[FD - 1][1], wy = (float)x[FD - 1][2], wz = (float)x[FD - 1][C - 1];
 				if (approximation == 2) { // :455-463
 					e[0] = ux + 0.5f * (ux * ux + vx * vx + wx * wx);
 					e[1] = vy + 0.5f * (uy * uy + vy * vy + wy * wy);
@@ -366,16 +381,17 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 } // namespace
 
 // Device scratch layout (one grow-only allocation owned by the context):
-//   bbox[8] | keys_in[n] | keys_out[n] | vals_in[n] | vals_out[n] | pos[n] | disp[n] | cub temp
+//   bbox[8] | keys_in[n] | keys_out[n] | vals_in[n] | vals_out[n] | pos[n] | disp[n] | fpos[n] | cub temp
 size_t strain_workspace_bytes(size_t n) {
 	size_t cub_bytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr, (const int*)nullptr, (int*)nullptr,
 		(int)n);
-	return 256 + 4 * align256(n * 4) + 2 * align256(n * 16) + align256(cub_bytes) + 256;
+	return 256 + 4 * align256(n * 4) + 3 * align256(n * 16) + align256(cub_bytes) + 256;
 }
 
 // Returns 0 on success, -2 on a CUDA error.  *launches is incremented by the number of kernels launched.
-int strain_launch(int dim, float* d_pois, size_t n, float radius, int k_min, float zncc_threshold, int approximation, long long only, void* workspace,
+// mode: 2 (POI2D records), 3 (POI3D), 23 (POI2DS)
+int strain_launch(int mode, float* d_pois, size_t n, float radius, int k_min, float zncc_threshold, int approximation, long long only, void* workspace,
 	int sm_count, cudaStream_t stream, cudaError_t* err, long long* launches) {
 	char* ws = (char*)workspace;
 	unsigned int* d_bbox = (unsigned int*)ws; ws += 256;
@@ -385,7 +401,9 @@ int strain_launch(int dim, float* d_pois, size_t n, float radius, int k_min, flo
 	int* vals_out = (int*)ws; ws += align256(n * 4);
 	float4* pos = (float4*)ws; ws += align256(n * 16);
 	float4* disp = (float4*)ws; ws += align256(n * 16);
+	float4* fpos = (float4*)ws; ws += align256(n * 16);
 	void* cub_temp = ws;
+	const int dim = mode == 3 ? 3 : 2; // search dimensions
 	size_t cub_bytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr, (const int*)nullptr, (int*)nullptr,
 		(int)n);
@@ -396,8 +414,9 @@ int strain_launch(int dim, float* d_pois, size_t n, float radius, int k_min, flo
 
 	const unsigned int init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
 	if ((*err = cudaMemcpyAsync(d_bbox, init, sizeof(init), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return -2;
-	if (dim == 2) strain_bbox_kernel<2><<<blocks, threads, 0, stream>>>(d_pois, (int)n, d_bbox);
-	else strain_bbox_kernel<3><<<blocks, threads, 0, stream>>>(d_pois, (int)n, d_bbox);
+	if (mode == 2) strain_bbox_kernel<2><<<blocks, threads, 0, stream>>>(d_pois, (int)n, d_bbox);
+	else if (mode == 3) strain_bbox_kernel<3><<<blocks, threads, 0, stream>>>(d_pois, (int)n, d_bbox);
+	else strain_bbox_kernel<23><<<blocks, threads, 0, stream>>>(d_pois, (int)n, d_bbox);
 	unsigned int hb[6];
 	if ((*err = cudaMemcpyAsync(hb, d_bbox, sizeof(hb), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return -2;
 	if ((*err = cudaStreamSynchronize(stream)) != cudaSuccess) return -2;
@@ -432,14 +451,16 @@ int strain_launch(int dim, float* d_pois, size_t n, float radius, int k_min, flo
 	g.inv_cell *= 0.999f;
 	g.n_cells = (unsigned int)g.nc[0] * (unsigned int)g.nc[1] * (unsigned int)g.nc[2];
 
-	if (dim == 2) strain_keys_kernel<2><<<blocks, threads, 0, stream>>>(d_pois, (int)n, g, keys_in, vals_in);
-	else strain_keys_kernel<3><<<blocks, threads, 0, stream>>>(d_pois, (int)n, g, keys_in, vals_in);
+	if (mode == 2) strain_keys_kernel<2><<<blocks, threads, 0, stream>>>(d_pois, (int)n, g, keys_in, vals_in);
+	else if (mode == 3) strain_keys_kernel<3><<<blocks, threads, 0, stream>>>(d_pois, (int)n, g, keys_in, vals_in);
+	else strain_keys_kernel<23><<<blocks, threads, 0, stream>>>(d_pois, (int)n, g, keys_in, vals_in);
 	int end_bit = 1;
 	while (end_bit < 32 && (g.n_cells >> end_bit) != 0) end_bit++;
 	if ((*err = cub::DeviceRadixSort::SortPairs(cub_temp, cub_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, stream)) != cudaSuccess)
 		return -2;
-	if (dim == 2) strain_gather_kernel<2><<<blocks, threads, 0, stream>>>(d_pois, (int)n, vals_out, zncc_threshold, pos, disp);
-	else strain_gather_kernel<3><<<blocks, threads, 0, stream>>>(d_pois, (int)n, vals_out, zncc_threshold, pos, disp);
+	if (mode == 2) strain_gather_kernel<2><<<blocks, threads, 0, stream>>>(d_pois, (int)n, vals_out, zncc_threshold, pos, disp, fpos);
+	else if (mode == 3) strain_gather_kernel<3><<<blocks, threads, 0, stream>>>(d_pois, (int)n, vals_out, zncc_threshold, pos, disp, fpos);
+	else strain_gather_kernel<23><<<blocks, threads, 0, stream>>>(d_pois, (int)n, vals_out, zncc_threshold, pos, disp, fpos);
 	// POIs with non-finite coordinates carry the sentinel key and sit at the end of the sorted order: the count
 	// of valid ones comes from the keys (binary search on the device side would need another round trip)
 	int n_valid = (int)n;
@@ -458,10 +479,13 @@ int strain_launch(int dim, float* d_pois, size_t n, float radius, int k_min, flo
 		long long warps_needed = n_valid;
 		long long grid = (warps_needed * 32 + threads - 1) / threads;
 		if (grid > (long long)sm_count * 8) grid = (long long)sm_count * 8;
-		if (dim == 2)
-			strain_kernel<2><<<(int)grid, threads, 0, stream>>>(d_pois, n_valid, g, keys_out, vals_out, pos, disp, radius, k_min, approximation, (int)only);
+		if (mode == 2)
+			strain_kernel<2><<<(int)grid, threads, 0, stream>>>(d_pois, n_valid, g, keys_out, vals_out, pos, disp, fpos, radius, k_min, approximation, (int)only);
+		else if (mode == 3)
+			strain_kernel<3><<<(int)grid, threads, 0, stream>>>(d_pois, n_valid, g, keys_out, vals_out, pos, disp, fpos, radius, k_min, approximation, (int)only);
 		else
-			strain_kernel<3><<<(int)grid, threads, 0, stream>>>(d_pois, n_valid, g, keys_out, vals_out, pos, disp, radius, k_min, approximation, (int)only);
+			strain_kernel<23><<<(int)grid, threads, 0, stream>>>(d_pois, n_valid, g, keys_out, vals_out, pos, disp, fpos, radius, k_min, approximation,
+				(int)only);
 		(*launches)++;
 	}
 	*err = cudaGetLastError();

@@ -1151,9 +1151,23 @@ void run_icgn3d1(const Ctx3D& c, float* pois, long n, int rx, int ry, int rz, fl
 // Strain::compute(POI2D*, queue) :158-237, Strain::compute(POI3D*, queue) :373-474, batch :239-250 / :476-487.
 // D = 2: POI2D records (25 floats), strain = {exx, eyy, exy}; D = 3: POI3D (31 floats), {exx, eyy, ezz, exy, eyz, ezx}.
 // ----------------------------------------------------------------------------------------------
-template <int D> struct StrainLayout;
-template <> struct StrainLayout<2> { enum { NF = P2_N, ZNCC = P2_ZNCC, STRAIN = P2_STRAIN, U = P2_DEF + D2_U, V = P2_DEF + D2_V, W = -1 }; };
-template <> struct StrainLayout<3> { enum { NF = P3_N, ZNCC = P3_ZNCC, STRAIN = P3_STRAIN, U = P3_DEF + 0, V = P3_DEF + 4, W = P3_DEF + 8 }; };
+// MODE 2: POI2D, MODE 3: POI3D, MODE 23: POI2DS (stereo DIC: neighbours are searched in the image plane of the primary
+// view, the plane fit runs over the reconstructed 3D coordinates ref_coor and u, v, w; a POI counts when all of
+// r1r2 / r1t1 / r1t2 ZNCC pass the threshold, src/oc_strain.cpp:252-371).  SD = search dimensions, FD = fit dimensions,
+// FC = offset of the fit coordinates in the record, Z0.. = the ZNCC fields that must pass.
+template <int MODE> struct StrainLayout;
+template <> struct StrainLayout<2> { enum { NF = P2_N, SD = 2, FD = 2, FC = 0, NZ = 1, Z0 = P2_ZNCC, STRAIN = P2_STRAIN, U = P2_DEF + D2_U, V = P2_DEF + D2_V, W = -1 }; };
+template <> struct StrainLayout<3> { enum { NF = P3_N, SD = 3, FD = 3, FC = 0, NZ = 1, Z0 = P3_ZNCC, STRAIN = P3_STRAIN, U = P3_DEF + 0, V = P3_DEF + 4, W = P3_DEF + 8 }; };
+// POI2DS record (src/oc_poi.h:140-186): x y | u v w | r1r2 r1t1 r1t2 r2_x r2_y t1_x t1_y t2_x t2_y | ref_coor | tar_coor | e[6] | subset_radius
+enum { PS_N = 28, PS_U = 2, PS_Z = 5, PS_REF = 14, PS_STRAIN = 20 };
+template <> struct StrainLayout<23> { enum { NF = PS_N, SD = 2, FD = 3, FC = PS_REF, NZ = 3, Z0 = PS_Z, STRAIN = PS_STRAIN, U = PS_U, V = PS_U + 1, W = PS_U + 2 }; };
+template <int MODE>
+inline bool strain_good(const float* p, float thr) {
+	typedef StrainLayout<MODE> L;
+	for (int k = 0; k < L::NZ; k++)
+		if (!(p[L::Z0 + k] >= thr)) return false;
+	return true;
+}
 
 // least squares A x = b_k for NB right-hand sides by column-pivoted Householder QR (what Eigen's
 // colPivHouseholderQr().solve does), A is m x C row-major in `a`, b is m x NB row-major; destroys both.
@@ -1213,10 +1227,10 @@ void lsq_qr(std::vector<T>& a, std::vector<T>& b, int m, T x[NB][C]) {
 	}
 }
 
-template <class T, int D>
+template <class T, int MODE>
 void run_strain(float* pois, long n, float radius, int k_min, float zncc_threshold, int approximation, int threads) {
-	typedef StrainLayout<D> L;
-	const int NF = L::NF;
+	typedef StrainLayout<MODE> L;
+	constexpr int NF = L::NF, D = L::SD, FD = L::FD, NE = FD == 2 ? 3 : 6; // D: search dimensions
 	// uniform grid over the POI positions, cell edge = radius
 	float lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
 	for (int d = 0; d < D; d++) { lo[d] = 1e30f; hi[d] = -1e30f; }
@@ -1233,7 +1247,7 @@ void run_strain(float* pois, long n, float radius, int k_min, float zncc_thresho
 		std::vector<long> fill(start.begin(), start.end() - 1);
 		for (long i = 0; i < n; i++) { long c[3]; cell_of(pois + i * NF, c); order[fill[(c[2] * nc[1] + c[1]) * nc[0] + c[0]]++] = i; }
 	}
-	std::vector<float> out((size_t)n * (D == 2 ? 3 : 6));
+	std::vector<float> out((size_t)n * NE);
 	std::vector<char> done(n, 0);
 	const float r2 = radius * radius;
 #pragma omp parallel num_threads(threads)
@@ -1244,7 +1258,7 @@ void run_strain(float* pois, long n, float radius, int k_min, float zncc_thresho
 #pragma omp for schedule(dynamic, 64)
 		for (long i = 0; i < n; i++) {
 			const float* p = pois + i * NF;
-			if (!(p[L::ZNCC] >= zncc_threshold)) continue; // :244-248
+			if (!strain_good<MODE>(p, zncc_threshold)) continue; // :244-248 / :362-368
 			long c[3];
 			cell_of(p, c);
 			fit.clear();
@@ -1260,7 +1274,7 @@ void run_strain(float* pois, long n, float radius, int k_min, float zncc_thresho
 							for (int d = 0; d < D; d++) { float df = p[d] - q[d]; d2 += df * df; }
 							if (d2 < r2) {
 								found++;
-								if (q[L::ZNCC] >= zncc_threshold) fit.push_back(j);
+								if (strain_good<MODE>(q, zncc_threshold)) fit.push_back(j);
 							}
 						}
 					}
@@ -1276,26 +1290,26 @@ void run_strain(float* pois, long n, float radius, int k_min, float zncc_thresho
 				long k = std::min((long)k_min, n);
 				std::partial_sort(cand.begin(), cand.begin() + k, cand.end());
 				for (long t = 0; t < k; t++)
-					if (pois[cand[t].second * NF + L::ZNCC] >= zncc_threshold) fit.push_back(cand[t].second);
+					if (strain_good<MODE>(pois + cand[t].second * NF, zncc_threshold)) fit.push_back(cand[t].second);
 			}
 			std::sort(fit.begin(), fit.end());
 			const int m = (int)fit.size();
 			if (m < k_min) continue; // :200-201
-			constexpr int C = D + 1;
+			constexpr int C = FD + 1;
 			A.resize((size_t)m * C);
-			B.resize((size_t)m * D);
+			B.resize((size_t)m * FD);
 			for (int t = 0; t < m; t++) {
 				const float* q = pois + fit[t] * NF;
 				A[(size_t)t * C] = 1;
-				for (int d = 0; d < D; d++) A[(size_t)t * C + 1 + d] = (T)(q[d] - p[d]);
-				B[(size_t)t * D] = q[L::U];
-				B[(size_t)t * D + 1] = q[L::V];
-				if (D == 3) B[(size_t)t * D + 2] = q[L::W];
+				for (int d = 0; d < FD; d++) A[(size_t)t * C + 1 + d] = (T)(q[L::FC + d] - p[L::FC + d]);
+				B[(size_t)t * FD] = q[L::U];
+				B[(size_t)t * FD + 1] = q[L::V];
+				if (FD == 3) B[(size_t)t * FD + 2] = q[L::W];
 			}
-			T x[D][C];
-			lsq_qr<T, C, D>(A, B, m, x);
-			float* e = &out[(size_t)i * (D == 2 ? 3 : 6)];
-			if (D == 2) {
+			T x[FD][C];
+			lsq_qr<T, C, FD>(A, B, m, x);
+			float* e = &out[(size_t)i * NE];
+			if (FD == 2) {
 				float ux = (float)x[0][1], uy = (float)x[0][2], vx = (float)x[1][1], vy = (float)x[1][2];
 				if (approximation == 2) { // Green strain :229-235
 					e[0] = ux + 0.5f * (ux * ux + vx * vx);
@@ -1307,7 +1321,7 @@ void run_strain(float* pois, long n, float radius, int k_min, float zncc_thresho
 			} else {
 				float ux = (float)x[0][1], uy = (float)x[0][2], uz = (float)x[0][3];
 				float vx = (float)x[1][1], vy = (float)x[1][2], vz = (float)x[1][3];
-				float wx = (float)x[2 % D][1], wy = (float)x[2 % D][2], wz = (float)x[2 % D][3 % C];
+				float wx = (float)x[2 % FD][1], wy = (float)x[2 % FD][2], wz = (float)x[2 % FD][3 % C];
 				if (approximation == 2) { // :455-463
 					e[0] = ux + 0.5f * (ux * ux + vx * vx + wx * wx);
 					e[1] = vy + 0.5f * (uy * uy + vy * vy + wy * wy);
@@ -1325,7 +1339,7 @@ void run_strain(float* pois, long n, float radius, int k_min, float zncc_thresho
 	}
 	for (long i = 0; i < n; i++)
 		if (done[i])
-			for (int k = 0; k < (D == 2 ? 3 : 6); k++) pois[i * NF + L::STRAIN + k] = out[(size_t)i * (D == 2 ? 3 : 6) + k];
+			for (int k = 0; k < NE; k++) pois[i * NF + L::STRAIN + k] = out[(size_t)i * NE + k];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1541,14 +1555,17 @@ int oco_epipolar_search(void* h, float* pois, long n, const float* fundamental, 
 // Strain::prepare + Strain::compute(queue) on POI2D (dim 2) / POI3D (dim 3) records, src/oc_strain.cpp:100-111,239-250,476-487.
 // approximation: 1 Cauchy, 2 Green (setApproximation); zncc_threshold default 0.9 (:38).
 int oco_strain(float* pois, long n, int dim, float radius, int min_neighbors, float zncc_threshold, int approximation, int threads, int exact) {
-	if (dim != 2 && dim != 3) return -1;
+	if (dim != 2 && dim != 3 && dim != 23) return -1; // 23: POI2DS records (28 floats), the stereo-DIC variant
 	if (threads < 1) threads = 1;
 	if (dim == 2) {
 		if (exact) run_strain<double, 2>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
 		else run_strain<float, 2>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
-	} else {
+	} else if (dim == 3) {
 		if (exact) run_strain<double, 3>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
 		else run_strain<float, 3>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
+	} else {
+		if (exact) run_strain<double, 23>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
+		else run_strain<float, 23>(pois, n, radius, min_neighbors, zncc_threshold, approximation, threads);
 	}
 	return 0;
 }

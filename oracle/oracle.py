@@ -95,9 +95,10 @@ def max_threads():
 
 
 def strain(pois, radius, min_neighbors, zncc_threshold=0.9, approximation=1, threads=0, exact=False):
-    """Strain::prepare + Strain::compute(queue) (reference src/oc_strain.cpp) on a POI2D [n,25] / POI3D [n,31] array."""
-    assert pois.dtype == np.float32 and pois.flags.c_contiguous and pois.shape[1] in (25, 31)
-    dim = 2 if pois.shape[1] == 25 else 3
+    """Strain::prepare + Strain::compute(queue) (reference src/oc_strain.cpp) on a POI2D [n,25] / POI3D [n,31] /
+    POI2DS [n,28] array."""
+    assert pois.dtype == np.float32 and pois.flags.c_contiguous and pois.shape[1] in (25, 31, 28)
+    dim = {25: 2, 31: 3, 28: 23}[pois.shape[1]]  # 28 floats: POI2DS records (stereo DIC)
     threads = threads if threads > 0 else max(1, max_threads() - 1)
     rc = lib().oco_strain(_p(pois), pois.shape[0], dim, radius, min_neighbors, zncc_threshold, approximation, threads, int(exact))
     assert rc == 0

@@ -14,6 +14,10 @@ Outputs
                                     their whole 20-px neighbourhood inside the band
   torus_strain_crop.npz             a box of the shipped DVC table examples/dvc/Torus_def_sift_icgn1_r16.csv
                                     (x,y,z,u,v,w,ZNCC + 6 strains) for the 3D Strain test, same idea
+  gt4_stereo_strain_crop.npz        the POIs with 600 <= x <= 1100, 400 <= y <= 800 of the shipped stereo-DIC table
+                                    examples/3d_dic/GT4-0273_0_epipolar_sift_r16.csv (all 26 columns: x, y, u, v, w, three ZNCCs,
+                                    matched positions, ref/tar 3D coordinates, 6 strains) for the POI2DS Strain test; `check` marks
+                                    the POIs whose 20-px neighbourhood lies inside the crop
   step18_epipolar_crop.npz          stereo pair examples/3d_dic/"Step18 00,00-0005_{0,1}.tif" (2448x2048, 8-bit) cut down to what the
                                     60 POIs x = 1170..1215, y = 1000..1025 of test_3d_reconstruction_epipolar.cpp touch
                                     (view 1: the subsets; view 2: the +-150 px candidate sweep along the epipolar lines), the
@@ -138,6 +142,15 @@ def main():
                         columns=np.array("x,y,z,u,v,w,ZNCC,exx,eyy,ezz,exy,eyz,ezx".split(",")), table=tb, check=inner)
 
     make_epipolar_fixture()
+
+    # stereo-DIC table with strains (examples/test_3d_dic_strain.cpp: radius 20, 5 neighbours)
+    gt = np.genfromtxt(os.path.join(REF, "3d_dic", "GT4-0273_0_epipolar_sift_r16.csv"), delimiter=",", skip_header=1)
+    box = (gt[:, 0] >= 600) & (gt[:, 0] <= 1100) & (gt[:, 1] >= 400) & (gt[:, 1] <= 800)
+    gb = gt[box].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "gt4_stereo_strain_crop.npz"), table=gb,
+                        columns=np.array("x,y,u,v,w,r1r2 ZNCC,r1t1 ZNCC,r1t2 ZNCC,r2_x,r2_y,t1_x,t1_y,t2_x,t2_y,ref_x,ref_y,ref_z,tar_x,tar_y,tar_z,"
+                                         "exx,eyy,ezz,exy,eyz,ezx".split(",")),
+                        check=(gb[:, 0] >= 621) & (gb[:, 0] <= 1079) & (gb[:, 1] >= 421) & (gb[:, 1] <= 779))
 
     def load(p):
         d = np.fromfile(p, dtype=np.int32, count=3)

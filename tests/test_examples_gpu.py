@@ -192,3 +192,26 @@ def test_reference_dvc_strain_example_runs_unchanged(tmp_path):
     good = check & (q[:, 18] >= 0.9)
     assert np.abs(tab[good][:, 22:28] - gold[good]).max() < 5e-6
     assert (data / "Torus_def_strain_r30_time.csv").exists()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "test_3d_dic_strain")), reason="example binary not built")
+def test_reference_stereo_strain_example_runs_unchanged(tmp_path):
+    """examples/test_3d_dic_strain.cpp: Image2D(.tif) for the size, loadTable2DS -> Strain(POI2DS) -> saveTable2DS."""
+    data = tmp_path / "d:" / "dic_tests" / "3d_dic"
+    data.mkdir(parents=True)
+    _write_tiff_stack(data / "GT4-0273_0.tif", (np.arange(12 * 16) % 251).reshape(1, 12, 16))
+    q, gold, check = util.gt4_stereo_queue()
+    cols = "x,y,u,v,w,r1r2 ZNCC,r1t1 ZNCC,r1t2 ZNCC,r2_x,r2_y,t1_x,t1_y,t2_x,t2_y,ref_x,ref_y,ref_z,tar_x,tar_y,tar_z,exx,eyy,ezz,exy,eyz,ezx,subset_rx,subset_ry"
+    with open(data / "GT4-0273_0_epipolar_sift_r16.csv", "w") as f:
+        f.write(cols + ",\n")
+        for p in q:
+            f.write(",".join("%.9g" % v for v in p[:20]) + ",0,0,0,0,0,0,16,16,\n")
+    out = subprocess.run([os.path.join(BIN, "test_3d_dic_strain")], cwd=tmp_path, stdin=subprocess.DEVNULL,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    header, tab = _read_table(data / "GT4-0273_0_epipolar_sift_r16.csv")
+    assert header == cols.split(",")
+    assert tab.shape[0] == q.shape[0] and np.array_equal(tab[:, 0:2], q[:, 0:2])
+    good = check & np.all(q[:, 5:8] >= 0.9, axis=1)
+    d = np.abs(tab[good][:, 20:26] - gold[good]).max(1)
+    assert np.median(d) < 2e-5 and d.max() < 1e-3

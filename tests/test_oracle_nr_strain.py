@@ -121,3 +121,19 @@ def test_epipolar_search_golden_crop(legacy):
     conv = q[:, 16] != -4    # current source: a refinement that hits the iteration limit loses its ZNCC to the -4 code
     assert conv.mean() > 0.9 and (legacy == 0 or conv.all())
     assert np.abs(q[conv, 16] - tab[conv, 2]).max() < 2e-6
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_strain_stereo_golden_crop(exact):
+    """Strain on POI2DS records (stereo DIC, reference src/oc_strain.cpp:252-371) vs the strains shipped in
+    examples/3d_dic/GT4-0273_0_epipolar_sift_r16.csv.  The fit is poorly conditioned there (~20 neighbours on a nearly
+    flat patch, 3D coordinates of ~400 mm): the reference's own float32 QR carries ~1e-4 of noise, which bounds the
+    agreement of either flavour with the table."""
+    q, gold, check = util.gt4_stereo_queue()
+    oracle.strain(q, 20.0, 5, 0.9, 1, exact=exact)
+    good = check & np.all(q[:, 5:8] >= 0.9, axis=1)
+    assert good.sum() > 1500
+    d = np.abs(q[good, 20:26] - gold[good]).max(1)
+    assert np.median(d) < (2e-5 if exact else 6e-5) and d.max() < 1e-3, (np.median(d), d.max())
+    bad = ~np.all(q[:, 5:8] >= 0.9, axis=1)
+    assert np.all(q[bad, 20:26] == 0)

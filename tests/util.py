@@ -132,3 +132,12 @@ def step18_epipolar_fixture():
 
 # parameters of examples/test_3d_reconstruction_epipolar.cpp:137-150
 STEP18_EPIPOLAR = dict(parallax_x=[0, 0, -30], parallax_y=[0, 0, -40], search_radius=150, search_step=4, rx=20, ry=20, conv=0.05, stop=5)
+
+
+def gt4_stereo_queue():
+    """POI2DS queue (28 floats per record) of the cropped stereo-DIC table, its shipped strains, and the interior mask."""
+    g = np.load(os.path.join(GOLDEN, "gt4_stereo_strain_crop.npz"))
+    t = g["table"]
+    q = np.zeros((t.shape[0], 28), np.float32)
+    q[:, 0:20] = t[:, 0:20]
+    return q, t[:, 20:26], g["check"]
