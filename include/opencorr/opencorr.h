@@ -510,13 +510,7 @@ namespace opencorr
 				std::lock_guard<std::mutex> g(lock);
 				context();
 			}
-			// upload at setImages() time when the pair is usable; problems surface at compute(), like in the reference
-			template <class Img>
-			void tryUseImages(Img* ref, Img* tar)
-			{
-				std::lock_guard<std::mutex> g(lock);
-				try { useImages(ref, tar); } catch (const std::string&) {}
-			}
+
 			~Engine()
 			{
 				if (ctx) ocb_destroy(ctx);
@@ -558,13 +552,9 @@ namespace opencorr
 		// FFTW plans in the constructors), so that its ~0.2 s start-up is not charged to the first compute() call.
 		DIC() : subset_radius_x(0), subset_radius_y(0), thread_number(1), self_adaptive(false) { b200::Engine::get().warm(); }
 		virtual ~DIC() = default;
-		// (the device copy is made here already when it can be; compute() re-checks the Image objects' generation counters)
-		void setImages(Image2D& ref_img, Image2D& tar_img)
-		{
-			this->ref_img = &ref_img;
-			this->tar_img = &tar_img;
-			b200::Engine::get().tryUseImages(&ref_img, &tar_img);
-		}
+		// (pointers only, like the reference: the device copy is made by the first prepare()/compute() that needs it, so
+		// images filled in after setImages() are seen)
+		void setImages(Image2D& ref_img, Image2D& tar_img) { this->ref_img = &ref_img; this->tar_img = &tar_img; }
 		void setSubset(int radius_x, int radius_y) { subset_radius_x = radius_x; subset_radius_y = radius_y; }
 		void setSelfAdaptive(bool is_self_adaptive) { self_adaptive = is_self_adaptive; }
 		virtual void prepare() = 0;
@@ -582,12 +572,7 @@ namespace opencorr
 
 		DVC() : subset_radius_x(0), subset_radius_y(0), subset_radius_z(0), thread_number(1) { b200::Engine::get().warm(); }
 		virtual ~DVC() = default;
-		void setImages(Image3D& ref_img, Image3D& tar_img)
-		{
-			this->ref_img = &ref_img;
-			this->tar_img = &tar_img;
-			b200::Engine::get().tryUseImages(&ref_img, &tar_img);
-		}
+		void setImages(Image3D& ref_img, Image3D& tar_img) { this->ref_img = &ref_img; this->tar_img = &tar_img; }
 		void setSubset(int radius_x, int radius_y, int radius_z) { subset_radius_x = radius_x; subset_radius_y = radius_y; subset_radius_z = radius_z; }
 		virtual void prepare() = 0;
 		virtual void compute(POI3D* POI) = 0;
