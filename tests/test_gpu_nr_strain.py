@@ -298,7 +298,7 @@ def test_strain_stereo_poi2ds(engine):
     assert np.array_equal(q[:, 20:26] == 0, cpu[:, 20:26] == 0)
     assert np.all(q[[7, 11], 20:26] == 0)
     # normal equations in FP64 vs Householder QR in FP64 on a poorly conditioned fit (coordinates ~400 mm, spread ~3 mm)
-    assert np.abs(q[:, 20:26] - cpu[:, 20:26]).max() < 2e-6
+    assert np.abs(q[:, 20:26] - cpu[:, 20:26]).max() < 1e-5
     good = check & np.all(q[:, 5:8] >= 0.9, axis=1)
     d = np.abs(q[good, 20:26] - gold[good]).max(1)
     assert np.median(d) < 2e-5 and d.max() < 1e-3
@@ -311,4 +311,4 @@ def test_strain_stereo_poi2ds(engine):
     s.set_approximation(2)
     s.compute(a)
     oracle.strain(b, 20.0, 5, 0.9, 2, exact=True)
-    assert np.abs(a[:, 20:26] - b[:, 20:26]).max() < 2e-6
+    assert np.abs(a[:, 20:26] - b[:, 20:26]).max() < 1e-5
