@@ -104,3 +104,62 @@ def test_full_size_dvc(engine):
     o.icgn3d1(qc, r, r, r, cfg["conv"], cfg["stop"], exact=True)
     stats = util.compare_3d(q[sel], qc, "full-size D")
     assert stats["n_compared"] > 0.95 * len(sel)
+
+
+def test_full_size_sibling_rows_config_b(engine):
+    """The section-8(f) operators on the full config-B workload: ICLM2D1 and NR2D1 against the oracle on a sample, Strain
+    against the oracle on all 50 000 POIs, order invariance of each."""
+    from oracle import oracle
+    cfg = synth.CONFIGS["B"]
+    ref, tar = _pair(cfg)
+    r = cfg["r"]
+    xy = synth.grid_2d(*cfg["grid"])
+    n = len(xy)
+    engine.set_images_2d(ref, tar)
+    engine.icgn2d_prepare()
+    engine.nr2d_prepare()
+    q0 = ob.make_poi2d(xy)
+    engine.fftcc2d(q0, r, r)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(n)
+    sel = np.sort(rng.choice(n, 1500, replace=False))
+    o = Oracle2D(ref, tar)
+
+    lm = q0.copy()
+    engine.iclm2d(1, lm, r, r, 0.001, 10)
+    lmp = q0[perm].copy()
+    engine.iclm2d(1, lmp, r, r, 0.001, 10)
+    assert np.array_equal(lmp, lm[perm])
+    c = q0[sel].copy()
+    o.iclm2d(1, c, r, r, 0.001, 10)
+    same = lm[sel, 17] == c[:, 17]
+    assert same.mean() > 0.97
+    assert np.abs(lm[sel][same][:, [2, 8]] - c[same][:, [2, 8]]).max() < 1e-4
+    assert np.abs(lm[sel][same, 16] - c[same, 16]).max() < 1e-5
+
+    nr = q0.copy()
+    engine.nr2d1(nr, r, r, 0.001, 10)
+    nrp = q0[perm].copy()
+    engine.nr2d1(nrp, r, r, 0.001, 10)
+    assert np.array_equal(nrp, nr[perm])
+    c = q0[sel].copy()
+    o.nr2d1(c, r, r, 0.001, 10)
+    same = nr[sel, 17] == c[:, 17]
+    assert same.mean() > 0.97
+    assert np.abs(nr[sel][same][:, [2, 8]] - c[same][:, [2, 8]]).max() < 1e-4
+    assert np.abs(nr[sel][same, 16] - c[same, 16]).max() < 1e-5
+    assert (nr[:, 16] > 0.9).all()
+
+    st = nr.copy()
+    engine.strain(st, 25.0, 5)
+    cs = nr.copy()
+    oracle.strain(cs, 25.0, 5, 0.9, 1, exact=True)
+    assert np.abs(st[:, 20:23] - cs[:, 20:23]).max() < 1e-6
+    assert (st[:, 20] != 0).all()
+    # the fitted gradients recover the synthetic field's: u_x = 1.5e-3, v_y = 2.1e-3, (u_y + v_x) / 2 = -1e-4
+    inner = (xy[:, 0] > 300) & (xy[:, 0] < 1700) & (xy[:, 1] > 300) & (xy[:, 1] < 1700)
+    assert np.abs(st[inner, 20] - 1.5e-3).max() < 6e-4 and np.abs(st[inner, 21] - 2.1e-3).max() < 6e-4
+    assert np.abs(st[inner, 22] + 1e-4).max() < 6e-4
+    stp = nr[perm].copy()
+    engine.strain(stp, 25.0, 5)
+    assert np.abs(stp[:, 20:23] - st[perm][:, 20:23]).max() < 1e-9   # FP64 sums in sorted-cell order: independent of the queue order
