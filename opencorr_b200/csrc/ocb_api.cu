@@ -86,6 +86,10 @@ struct ocb_ctx {
 	size_t d_u8_bytes = 0;
 	float* d_off = nullptr; // centre offsets (2 floats per POI)
 	size_t d_off_bytes = 0;
+	// host-queue calls on large 2D queues are split into chunks whose H2D copy, kernel and D2H copy run on separate
+	// streams, so the PCIe transfers of one chunk overlap the kernel of another
+	cudaStream_t pipe[4] = { nullptr, nullptr, nullptr, nullptr };
+	cudaEvent_t pipe_ready = nullptr;
 	float* d_cand = nullptr; // EpipolarSearch candidate queue
 	size_t d_cand_bytes = 0;
 	void* d_strain_ws = nullptr; // Strain: sort keys / compact neighbour arrays / cub scratch
@@ -149,6 +153,61 @@ static int unstage_pois(ocb_ctx* ctx, void* host, size_t bytes) {
 	OCB_CUDA(ctx, cudaMemcpyAsync(host, ctx->d_poi, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return OCB_OK;
+}
+
+// Host-queue driver for the per-POI independent 2D operators: stage -> dev_call(d_queue, n, first) -> unstage.
+// Queues of >= OCB_PIPE_MIN records are processed in 4 chunks on 4 internal streams (each chunk: H2D, kernel, D2H), which
+// hides most of the POI traffic behind the kernels; results do not depend on the split (the POIs are independent).
+// dev_call launches on ctx->stream with ctx->d_counter, both of which are redirected per chunk.
+static const size_t OCB_PIPE_MIN = 16384;
+template <class F>
+static int run_host_queue_2d(ocb_ctx* ctx, void* host, size_t n, F dev_call) {
+	const size_t rec = OCB_POI2D_FLOATS * sizeof(float);
+	int rc;
+	if (n < OCB_PIPE_MIN || getenv("OCB_NO_PIPELINE")) {
+		if ((rc = stage_pois(ctx, host, n * rec))) return rc;
+		if ((rc = dev_call((float*)ctx->d_poi, n, (size_t)0))) return rc;
+		return unstage_pois(ctx, host, n * rec);
+	}
+	if (n * rec > ctx->d_poi_bytes) {
+		if (ctx->d_poi) cudaFree(ctx->d_poi);
+		ctx->d_poi = nullptr;
+		ctx->d_poi_bytes = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->d_poi, n * rec));
+		ctx->d_poi_bytes = n * rec;
+	}
+	const int K = 4;
+	if (!ctx->pipe_ready) {
+		OCB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ready, cudaEventDisableTiming));
+		for (int i = 0; i < K; i++) OCB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking));
+	}
+	// everything enqueued so far on the caller-visible stream (image uploads, prepare, offsets) comes first
+	OCB_CUDA(ctx, cudaEventRecord(ctx->pipe_ready, ctx->stream));
+	cudaStream_t saved_stream = ctx->stream;
+	int* saved_counter = ctx->d_counter;
+	rc = OCB_OK;
+	for (int c = 0; c < K && rc == OCB_OK; c++) {
+		const size_t a = n * (size_t)c / K, b = n * (size_t)(c + 1) / K;
+		if (b == a) continue;
+		char* h = (char*)host + a * rec;
+		float* d = ctx->d_poi + a * OCB_POI2D_FLOATS;
+		cudaError_t e = cudaStreamWaitEvent(ctx->pipe[c], ctx->pipe_ready, 0);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, (b - a) * rec, cudaMemcpyHostToDevice, ctx->pipe[c]);
+		if (e != cudaSuccess) { rc = set_error(ctx, OCB_ERR_CUDA, "pipelined upload failed: %s", cudaGetErrorString(e)); break; }
+		ctx->stream = ctx->pipe[c];
+		ctx->d_counter = saved_counter + c;
+		rc = dev_call(d, b - a, a);
+		ctx->stream = saved_stream;
+		ctx->d_counter = saved_counter;
+		if (rc != OCB_OK) break;
+		e = cudaMemcpyAsync(h, d, (b - a) * rec, cudaMemcpyDeviceToHost, ctx->pipe[c]);
+		if (e != cudaSuccess) rc = set_error(ctx, OCB_ERR_CUDA, "pipelined download failed: %s", cudaGetErrorString(e));
+	}
+	for (int c = 0; c < K; c++) {
+		cudaError_t e = cudaStreamSynchronize(ctx->pipe[c]);
+		if (e != cudaSuccess && rc == OCB_OK) rc = set_error(ctx, OCB_ERR_CUDA, "pipelined queue failed: %s", cudaGetErrorString(e));
+	}
+	return rc;
 }
 
 extern "C" {
@@ -216,6 +275,9 @@ void ocb_destroy(ocb_ctx* ctx) {
 	cudaFree(ctx->d_off);
 	cudaFree(ctx->d_strain_ws);
 	cudaFree(ctx->d_cand);
+	for (int i = 0; i < 4; i++)
+		if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
+	if (ctx->pipe_ready) cudaEventDestroy(ctx->pipe_ready);
 	cudaFree(ctx->d_u8);
 	cudaFree(ctx->d_counter);
 	cudaStreamDestroy(ctx->own_stream);
@@ -411,11 +473,7 @@ int ocb_fftcc2d(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry) {
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
-	int rc;
-	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
-	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
-	if ((rc = ocb_fftcc2d_dev(ctx, ctx->d_poi, n, rx, ry))) return rc;
-	return unstage_pois(ctx, poi2d, bytes);
+	return run_host_queue_2d(ctx, poi2d, n, [&](float* d, size_t m, size_t) { return ocb_fftcc2d_dev(ctx, d, m, rx, ry); });
 }
 
 int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz) {
@@ -531,11 +589,7 @@ static int icgn2d_host(ocb_ctx* ctx, int np, void* poi2d, size_t n, int rx, int 
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
-	int rc;
-	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
-	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
-	if ((rc = icgn2d_dev(ctx, np, ctx->d_poi, n, rx, ry, conv, stop))) return rc;
-	return unstage_pois(ctx, poi2d, bytes);
+	return run_host_queue_2d(ctx, poi2d, n, [&](float* d, size_t m, size_t) { return icgn2d_dev(ctx, np, d, m, rx, ry, conv, stop); });
 }
 int ocb_icgn2d1(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 6, p, n, rx, ry, conv, stop); }
 int ocb_icgn2d2(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 12, p, n, rx, ry, conv, stop); }
@@ -547,9 +601,6 @@ int ocb_icgn2d_ex_dev(ocb_ctx* ctx, int order, void* d_poi2d, size_t n, int rx, 
 
 // one launch over a host queue (all POIs share the radius), optional host offsets
 static int icgn2d_host_group(ocb_ctx* ctx, int np, float* poi2d, size_t n, int rx, int ry, float conv, float stop, const float* offsets) {
-	int rc;
-	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
-	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
 	const float* d_off = nullptr;
 	if (offsets) {
 		const size_t ob = n * 2 * sizeof(float);
@@ -563,8 +614,8 @@ static int icgn2d_host_group(ocb_ctx* ctx, int np, float* poi2d, size_t n, int r
 		OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_off, offsets, ob, cudaMemcpyHostToDevice, ctx->stream));
 		d_off = ctx->d_off;
 	}
-	if ((rc = icgn2d_dev(ctx, np, ctx->d_poi, n, rx, ry, conv, stop, d_off))) return rc;
-	return unstage_pois(ctx, poi2d, bytes);
+	return run_host_queue_2d(ctx, poi2d, n,
+		[&](float* d, size_t m, size_t first) { return icgn2d_dev(ctx, np, d, m, rx, ry, conv, stop, d_off ? d_off + 2 * first : nullptr); });
 }
 
 int ocb_icgn2d_ex(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, const float* center_offsets,
@@ -618,11 +669,8 @@ int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, f
 	if (order != 1 && order != 2) return set_error(ctx, OCB_ERR_ARG, "iclm2d: order must be 1 or 2");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
-	int rc;
-	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
-	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
-	if ((rc = ocb_iclm2d_dev(ctx, order, ctx->d_poi, n, rx, ry, conv, stop, lambda, alpha, beta))) return rc;
-	return unstage_pois(ctx, poi2d, bytes);
+	return run_host_queue_2d(ctx, poi2d, n,
+		[&](float* d, size_t m, size_t) { return ocb_iclm2d_dev(ctx, order, d, m, rx, ry, conv, stop, lambda, alpha, beta); });
 }
 
 // ---- NR2D1 ---------------------------------------------------------------
@@ -652,11 +700,7 @@ int ocb_nr2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, f
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "nr2d1: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
-	int rc;
-	const size_t bytes = n * OCB_POI2D_FLOATS * sizeof(float);
-	if ((rc = stage_pois(ctx, poi2d, bytes))) return rc;
-	if ((rc = ocb_nr2d1_dev(ctx, ctx->d_poi, n, rx, ry, conv, stop))) return rc;
-	return unstage_pois(ctx, poi2d, bytes);
+	return run_host_queue_2d(ctx, poi2d, n, [&](float* d, size_t m, size_t) { return ocb_nr2d1_dev(ctx, d, m, rx, ry, conv, stop); });
 }
 
 // ---- EpipolarSearch candidate sweep ----------------------------------------
