@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(F3R_THREADS, fft3reg_min_ctas(N)) fftcc3d_reg_
 				const float rpz = pz + z - R;
 				const float* pa = img.ref + (size_t)(int)rpz * dy * dx + ax;
 				const float* pb = img.tar + (size_t)(int)(rpz + w0) * dy * dx + bx;
-#pragma unroll 4
+#pragma unroll 10
 				for (int r = 0; r < N; r++) {
 					const float rpy = py + r - R;
 					sa += __ldg(pa + (size_t)(int)rpy * dx);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(F3R_THREADS, fft3reg_min_ctas(N)) fftcc3d_reg_
 				const float rpz = pz + z - R;
 				const float* pa = img.ref + (size_t)(int)rpz * dy * dx + ax;
 				const float* pb = img.tar + (size_t)(int)(rpz + w0) * dy * dx + bx;
-#pragma unroll 4
+#pragma unroll 10
 				for (int r = 0; r < N; r++) {
 					const float rpy = py + r - R;
 					const float a = __ldg(pa + (size_t)(int)rpy * dx) - ref_mean;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(F3R_THREADS, fft3reg_min_ctas(N)) fftcc3d_reg_
 			const bool act = lane_ok && z < N;
 			if (act) { // thread = column kx = t: slice into the tile
 				const float2* src = S2 + (size_t)z * NN + t;
-#pragma unroll 4
+#pragma unroll 10
 				for (int ky = 0; ky < N; ky++) {
 					const float2 v = __ldcg(src + ky * N);
 					sre[ky * PITCH + t] = v.x;
