@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(FFTREG_THREADS, fftreg_min_ctas(N)) fftcc2d_re
 		if (active) {
 			const float rpx = px + t - R;
 			const int ax = (int)rpx, bx = (int)(rpx + u0);
-#pragma unroll 8
+#pragma unroll 20
 			for (int r = 0; r < N; r++) {
 				const float rpy = py + r - R;
 				const float a = __ldg(img.ref + (size_t)(int)rpy * w + ax);
