@@ -8,6 +8,9 @@ Outputs
   oht_cfrp_0.bmp, oht_cfrp_4.bmp    the 2D example pair (280x900, 8-bit), verbatim
   oht_cfrp_4_fftcc_icgn1_r16.npz    every 23rd row of the shipped result table + deformation table
   oht_cfrp_4_fftcc_iclm1_r16.npz    the same rows of the shipped ICLM2D1 table
+  oht_cfrp_4_sift_icgn2_gpu_r16.npz every 23rd row of examples/2d_dic/oht_cfrp_4_sift_icgn2(gpu)_r16.csv (the reference's GPU ICGN2D2,
+                                    SIFT-seeded): x,y,u,v,u0,v0,ZNCC,iteration,convergence.  u0, v0 are the seeds; the affine part
+                                    of the seed is not in the table, so iteration counts agree on ~70 % of the rows only
   oht_cfrp_4_fftcc_nr1_r16.npz      every 23rd row of the shipped NR2D1 table (x,y,u,v,u0,v0,ZNCC,iteration,convergence)
                                     + a 96-row band (y in [370,560), all 100 columns, includes the specimen's hole)
                                     of x,y,u,v,ZNCC,exx,eyy,exy for the Strain test; rows with `band_check` have
@@ -122,6 +125,11 @@ def main():
     itab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_fftcc_iclm1_r16.csv"), delimiter=",", skip_header=1)
     np.savez_compressed(os.path.join(OUT, "oht_cfrp_4_fftcc_iclm1_r16.npz"),
                         columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence".split(",")), table=itab[sel, :9], rows=sel)
+
+    # ICGN2D2 known-answer table (reference GPU build, SIFT / FeatureAffine seeds)
+    gtab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_sift_icgn2(gpu)_r16.csv"), delimiter=",", skip_header=1)
+    np.savez_compressed(os.path.join(OUT, "oht_cfrp_4_sift_icgn2_gpu_r16.npz"),
+                        columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence".split(",")), table=gtab[sel, :9], rows=sel)
 
     # NR2D1 + Strain table shipped by the reference (examples/2d_dic/oht_cfrp_4_fftcc_nr1_r16.csv)
     ntab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_fftcc_nr1_r16.csv"), delimiter=",", skip_header=1)

@@ -499,3 +499,21 @@ def test_icgn2d_warps_per_poi_variants(engine, cfg_a, monkeypatch, wpp, order):
     same = a[:, 17] == b[:, 17]
     assert same.mean() > 0.97
     assert np.abs(a[same][:, [2, 8]] - b[same][:, [2, 8]]).max() < 1e-4
+
+
+def test_icgn2d2_known_answers(engine):
+    """ICGN2D2 seeded with the u0, v0 of the reference's shipped GPU table examples/2d_dic/oht_cfrp_4_sift_icgn2(gpu)_r16.csv
+    (see tests/test_oracle_golden.py::test_icgn2d2_known_answers for why only the same-iteration rows are compared)."""
+    ref, tar = util.oht_cfrp_pair()
+    tab = util.oht_cfrp_icgn2_golden()["table"]
+    q = ob.make_poi2d(tab[:, 0:2])
+    q[:, 2], q[:, 8] = tab[:, 4], tab[:, 5]
+    ic = ob.ICGN2D2(16, 16, 0.001, 10, engine=engine)
+    ic.set_images(ref, tar)
+    ic.prepare()
+    ic.compute(q)
+    ok = (q[:, 17] == tab[:, 7]) & (tab[:, 7] < 10) & (tab[:, 6] >= 0.9)
+    assert ok.mean() > 0.6
+    d = np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max(1)
+    assert np.percentile(d, 99) < 1e-4 and np.median(d) < 2e-5
+    assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 1e-5

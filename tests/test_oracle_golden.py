@@ -107,3 +107,20 @@ def test_2d_iclm_golden_table():
     # the shipped ICLM table already carries the -4 code for its non-converged rows
     assert np.array_equal(q[same & (tab[:, 6] == -4), 16] == -4, np.ones((same & (tab[:, 6] == -4)).sum(), bool)) or \
         ((q[same & (tab[:, 6] == -4), 16] == -4).mean() > 0.97)
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_icgn2d2_known_answers(exact):
+    """ICGN2D2 vs the reference's shipped examples/2d_dic/oht_cfrp_4_sift_icgn2(gpu)_r16.csv (its GPU build, SIFT seeds):
+    the table's u0, v0 are fed as the initial guess.  The affine part of the FeatureAffine seed is not in the table, so the
+    iteration counts agree on ~70 % of the rows; those rows are compared."""
+    ref, tar = util.oht_cfrp_pair()
+    tab = util.oht_cfrp_icgn2_golden()["table"]
+    q = make_poi2d(tab[:, 0:2])
+    q[:, 2], q[:, 8] = tab[:, 4], tab[:, 5]
+    Oracle2D(ref, tar).icgn2d2(q, 16, 16, 0.001, 10, exact=exact)
+    ok = (q[:, 17] == tab[:, 7]) & (tab[:, 7] < 10) & (tab[:, 6] >= 0.9)
+    assert ok.mean() > 0.6
+    d = np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max(1)
+    assert np.percentile(d, 99) < 1e-4 and np.median(d) < 2e-5
+    assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 5e-6

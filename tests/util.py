@@ -141,3 +141,7 @@ def gt4_stereo_queue():
     q = np.zeros((t.shape[0], 28), np.float32)
     q[:, 0:20] = t[:, 0:20]
     return q, t[:, 20:26], g["check"]
+
+
+def oht_cfrp_icgn2_golden():
+    return np.load(os.path.join(GOLDEN, "oht_cfrp_4_sift_icgn2_gpu_r16.npz"))
