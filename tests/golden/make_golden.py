@@ -11,6 +11,11 @@ Outputs
   oht_cfrp_4_sift_icgn2_gpu_r16.npz every 23rd row of examples/2d_dic/oht_cfrp_4_sift_icgn2(gpu)_r16.csv (the reference's GPU ICGN2D2,
                                     SIFT-seeded): x,y,u,v,u0,v0,ZNCC,iteration,convergence.  u0, v0 are the seeds; the affine part
                                     of the seed is not in the table, so iteration counts agree on ~70 % of the rows only
+  utn_30_self_adaptive_crop.npz     561 POIs (x in [1500,1700], y in [150,350], every third) of the shipped self-adaptive-subset table
+                                    examples/2d_dic/utn_30_self_adaptive.csv (all 15 columns incl. the per-POI subset radii) and the
+                                    parts of utn_00.bmp / utn_30.bmp they touch (the target window is ~480 px away: 30 % strain); the
+                                    test pastes the crops into zero images of the full 3751x501 size -- checked here to give the
+                                    oracle bit-identical results to the full images
   oht_cfrp_4_fftcc_nr1_r16.npz      every 23rd row of the shipped NR2D1 table (x,y,u,v,u0,v0,ZNCC,iteration,convergence)
                                     + a 96-row band (y in [370,560), all 100 columns, includes the specimen's hole)
                                     of x,y,u,v,ZNCC,exx,eyy,exy for the Strain test; rows with `band_check` have
@@ -64,6 +69,54 @@ def step18_fundamental():
     tx = np.array([[0, -t2[2], t2[1]], [t2[2], 0, -t2[0]], [-t2[1], t2[0], 0]], f32)
     e = (tx @ r2).astype(f32)
     return (np.linalg.inv(k2.astype(np.float64)).T.astype(f32) @ e @ np.linalg.inv(k1.astype(np.float64)).astype(f32)).astype(f32)
+
+
+def make_self_adaptive_fixture():
+    """examples/test_2d_dic_self_adaptive_subset.cpp: ICGN2D1 with setSelfAdaptive(true) after SIFT + FeatureAffine.  The table
+    keeps the seeds' translation (u0, v0) and the per-POI radii; the affine part of the seed is approximated by the table's
+    strains (exx ~ ux, eyy ~ vy), which is enough for IC-GN to land on the same optimum."""
+    import struct
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle.oracle import Oracle2D
+
+    def read_bmp8(path):
+        with open(path, "rb") as f:
+            b = f.read()
+        off, w, h, bpp = struct.unpack_from("<I", b, 10)[0], struct.unpack_from("<i", b, 18)[0], struct.unpack_from("<i", b, 22)[0], struct.unpack_from("<H", b, 28)[0]
+        assert bpp == 8
+        stride = (w + 3) // 4 * 4
+        img = np.frombuffer(b, np.uint8, stride * abs(h), off).reshape(abs(h), stride)[:, :w]
+        return (img[::-1] if h > 0 else img).astype(np.float32)
+
+    ref = read_bmp8(os.path.join(REF, "2d_dic", "utn_00.bmp"))
+    tar = read_bmp8(os.path.join(REF, "2d_dic", "utn_30.bmp"))
+    t = np.genfromtxt(os.path.join(REF, "2d_dic", "utn_30_self_adaptive.csv"), delimiter=",", skip_header=1)[:, :15]
+    box = (t[:, 0] >= 1500) & (t[:, 0] <= 1700) & (t[:, 1] >= 150) & (t[:, 1] <= 350)
+    tb = t[box][::3]
+
+    def run(a, b):
+        q = np.zeros((len(tb), 25), np.float32)
+        q[:, 0:2] = tb[:, 0:2]
+        q[:, 2], q[:, 8], q[:, 3], q[:, 10] = tb[:, 4], tb[:, 5], tb[:, 10], tb[:, 11]
+        q[:, 23], q[:, 24] = tb[:, 13], tb[:, 14]
+        Oracle2D(a, b).icgn2d_ex(1, q, 30, 30, 0.001, 10, None, True)
+        return q
+
+    m = int(max(tb[:, 13].max(), tb[:, 14].max())) + 8
+    a0 = (max(0, int(tb[:, 1].min()) - m), min(ref.shape[0], int(tb[:, 1].max()) + m + 1),
+          max(0, int(tb[:, 0].min()) - m), min(ref.shape[1], int(tb[:, 0].max()) + m + 1))
+    tx, ty = tb[:, 0] + tb[:, 2], tb[:, 1] + tb[:, 3]
+    m2 = int(m * 1.45) + 10
+    b0 = (max(0, int(ty.min()) - m2), min(tar.shape[0], int(ty.max()) + m2 + 1), max(0, int(tx.min()) - m2), min(tar.shape[1], int(tx.max()) + m2 + 1))
+    mr, mt = np.zeros_like(ref), np.zeros_like(tar)
+    mr[a0[0]:a0[1], a0[2]:a0[3]] = ref[a0[0]:a0[1], a0[2]:a0[3]]
+    mt[b0[0]:b0[1], b0[2]:b0[3]] = tar[b0[0]:b0[1], b0[2]:b0[3]]
+    assert np.array_equal(run(mr, mt), run(ref, tar)), "crop changes the result"
+    np.savez_compressed(os.path.join(OUT, "utn_30_self_adaptive_crop.npz"), shape=np.array(ref.shape),
+                        ref=ref[a0[0]:a0[1], a0[2]:a0[3]].astype(np.uint8), ref_origin=np.array([a0[0], a0[2]]),
+                        tar=tar[b0[0]:b0[1], b0[2]:b0[3]].astype(np.uint8), tar_origin=np.array([b0[0], b0[2]]), table=tb,
+                        columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence,feature,exx,eyy,exy,subset_rx,subset_ry".split(",")))
 
 
 def make_epipolar_fixture():
@@ -130,6 +183,8 @@ def main():
     gtab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_sift_icgn2(gpu)_r16.csv"), delimiter=",", skip_header=1)
     np.savez_compressed(os.path.join(OUT, "oht_cfrp_4_sift_icgn2_gpu_r16.npz"),
                         columns=np.array("x,y,u,v,u0,v0,ZNCC,iteration,convergence".split(",")), table=gtab[sel, :9], rows=sel)
+
+    make_self_adaptive_fixture()
 
     # NR2D1 + Strain table shipped by the reference (examples/2d_dic/oht_cfrp_4_fftcc_nr1_r16.csv)
     ntab = np.genfromtxt(os.path.join(REF, "2d_dic", "oht_cfrp_4_fftcc_nr1_r16.csv"), delimiter=",", skip_header=1)

@@ -517,3 +517,18 @@ def test_icgn2d2_known_answers(engine):
     d = np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max(1)
     assert np.percentile(d, 99) < 1e-4 and np.median(d) < 2e-5
     assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 1e-5
+
+
+def test_self_adaptive_icgn2d1_known_answers(engine):
+    """Per-POI subset radii through ocb_icgn2d_ex vs the reference's shipped examples/2d_dic/utn_30_self_adaptive.csv."""
+    ref, tar, tab = util.utn_self_adaptive_fixture()
+    q = util.utn_self_adaptive_queue(tab)
+    ic = ob.ICGN2D1(30, 30, 0.001, 10, engine=engine)
+    ic.set_images(ref, tar)
+    ic.set_self_adaptive(True)
+    ic.prepare()
+    ic.compute(q)
+    assert (q[:, 16] > 0.9).all()
+    assert np.abs(q[:, [2, 8]] - tab[:, [2, 3]]).max() < 1.5e-4     # displacements of ~480 px: a float32 ulp is 3e-5 there
+    assert np.abs(q[:, 16] - tab[:, 6]).max() < 1e-5
+    assert np.array_equal(q[:, 23:25], tab[:, 13:15])

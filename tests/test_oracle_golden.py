@@ -124,3 +124,16 @@ def test_icgn2d2_known_answers(exact):
     d = np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max(1)
     assert np.percentile(d, 99) < 1e-4 and np.median(d) < 2e-5
     assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 5e-6
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_self_adaptive_icgn2d1_known_answers(exact):
+    """ICGN2D1 with per-POI subset radii (setSelfAdaptive, reference src/oc_icgn.cpp:152-158) vs the shipped
+    examples/2d_dic/utn_30_self_adaptive.csv (30 % strain, displacements of ~480 px, radii 18..46)."""
+    ref, tar, tab = util.utn_self_adaptive_fixture()
+    q = util.utn_self_adaptive_queue(tab)
+    Oracle2D(ref, tar).icgn2d_ex(1, q, 30, 30, 0.001, 10, None, True, exact=exact)
+    assert (q[:, 16] > 0.9).all()
+    assert np.abs(q[:, [2, 8]] - tab[:, [2, 3]]).max() < 1e-4
+    assert np.abs(q[:, 16] - tab[:, 6]).max() < 1e-6
+    assert np.array_equal(q[:, 23:25], tab[:, 13:15])

@@ -145,3 +145,25 @@ def gt4_stereo_queue():
 
 def oht_cfrp_icgn2_golden():
     return np.load(os.path.join(GOLDEN, "oht_cfrp_4_sift_icgn2_gpu_r16.npz"))
+
+
+def utn_self_adaptive_fixture():
+    """(ref, tar, table): the cropped self-adaptive-subset example (pasted into zero images of the full size) and the shipped rows."""
+    g = np.load(os.path.join(GOLDEN, "utn_30_self_adaptive_crop.npz"))
+    h, w = (int(v) for v in g["shape"])
+    imgs = []
+    for k in ("ref", "tar"):
+        img = np.zeros((h, w), np.float32)
+        a, o = g[k], g[k + "_origin"]
+        img[o[0]:o[0] + a.shape[0], o[1]:o[1] + a.shape[1]] = a
+        imgs.append(img)
+    return imgs[0], imgs[1], g["table"]
+
+
+def utn_self_adaptive_queue(tab):
+    """POI2D queue seeded like the example: u0, v0 of the table, the affine part from its strains, per-POI radii."""
+    q = np.zeros((tab.shape[0], 25), np.float32)
+    q[:, 0:2] = tab[:, 0:2]
+    q[:, 2], q[:, 8], q[:, 3], q[:, 10] = tab[:, 4], tab[:, 5], tab[:, 10], tab[:, 11]
+    q[:, 23], q[:, 24] = tab[:, 13], tab[:, 14]
+    return q
