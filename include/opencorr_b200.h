@@ -59,7 +59,27 @@ int ocb_device_count(void);
  * (src/oc_icgn.cpp:71-88,612-629,1197-1215): no per-thread pools are needed on the GPU.
  * Returns NULL on failure (see ocb_last_error(NULL)). */
 ocb_ctx* ocb_create(int device);
+/* Several devices behind ONE context (one process, G devices): ocb_create(-1) takes every visible
+ * device, ocb_create_multi() the listed ones.  A GROUP context replaces what the reference does with its OpenMP loop over
+ * the POI queue, FFTCC2D::compute(std::vector<POI2D>&) src/oc_fftcc.cpp:277-285, ICGN2D1::compute(std::vector<POI2D>&)
+ * src/oc_icgn.cpp:343-351 (and the siblings): setImages() uploads the pair to every member, each over its own PCIe link;
+ * prepare() runs on every member; every host-queue compute() call splits the caller's array into contiguous blocks
+ * (member i gets records [n*i/G, n*(i+1)/G)), and each member copies ITS block in, registers it and copies it back
+ * straight into the caller's array, concurrently (one host thread per member).  Results are bit-identical to a
+ * single-device context (the POIs are independent).  Queues too short to fill G devices use fewer of them.  Strain needs
+ * every POI's neighbours and runs on the first member.  The *_dev / stream entry points need a single-device context:
+ * use ocb_member(). */
+ocb_ctx* ocb_create_multi(const int* devices, int n_devices);
+/* 1 for a single-device context, G for a group; ocb_member(ctx, i) = the i-th member's single-device context (owned by the
+ * group), or ctx itself for i == 0 of a single-device context. */
+int ocb_member_count(const ocb_ctx* ctx);
+ocb_ctx* ocb_member(ocb_ctx* ctx, int index);
 void ocb_destroy(ocb_ctx* ctx);
+/* Page-lock / release a caller-owned host buffer (an Image2D's pixels, a std::vector<POI2D>'s storage) so that the copies of
+ * the host-buffer entry points run as asynchronous DMA at full PCIe rate instead of being staged by the driver.  Optional:
+ * every entry point accepts pageable memory.  The range must stay allocated until it is unregistered. */
+int ocb_host_register(void* host, size_t bytes);
+int ocb_host_unregister(void* host);
 /* Last error message of this context (or of the process when ctx == NULL). Never NULL. */
 const char* ocb_last_error(const ocb_ctx* ctx);
 /* Enqueue on an external cudaStream_t (e.g. PyTorch's current stream).  The handle is used as given:
@@ -151,7 +171,7 @@ int ocb_epipolar_search2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, const float
  *      radius = subregion_radius, min_neighbors = neighbor_number_min (constructor :32-36), zncc_threshold = setZnccThreshold
  *      (default 0.9, :38), approximation = setApproximation: 1 Cauchy (default), 2 Green.  Writes strain.exx.. of every POI
  *      whose own ZNCC and enough neighbours' ZNCC pass the threshold; other records are left untouched.
- *      The stereo variant (POI2DS) is out of scope. */
+ *      (The stereo variant, POI2DS records, is ocb_strain2ds below.) */
 int ocb_strain2d(ocb_ctx* ctx, void* poi2d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
 int ocb_strain3d(ocb_ctx* ctx, void* poi3d, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation);
 /* Strain::compute(POI2D* poi, queue) / (POI3D* poi, queue) for the queue member `index`: fitted whatever its own ZNCC. */

@@ -24,6 +24,11 @@ _sz = ctypes.c_size_t
 SIGNATURES = {
     "ocb_device_count": (_i, []),
     "ocb_create": (_vp, [_i]),
+    "ocb_create_multi": (_vp, [_vp, _i]),
+    "ocb_member_count": (_i, [_vp]),
+    "ocb_member": (_vp, [_vp, _i]),
+    "ocb_host_register": (_i, [_vp, _sz]),
+    "ocb_host_unregister": (_i, [_vp]),
     "ocb_destroy": (None, [_vp]),
     "ocb_last_error": (ctypes.c_char_p, [_vp]),
     "ocb_set_stream": (_i, [_vp, _vp]),

@@ -56,15 +56,32 @@ def _check_queue(q, floats):
 
 
 class Engine:
-    """One GPU context (ocb_ctx).  Raises OpenCorrB200Error when no B200-class GPU is usable."""
+    """One GPU context (ocb_ctx), or a GROUP context over several devices: device = -1 / "all" (every visible device) or a
+    list of device indices -- host-queue calls then shard the queue over the devices inside the C ABI (one process, G
+    devices; include/opencorr_b200.h ocb_create_multi).  Raises OpenCorrB200Error when no B200-class GPU is usable."""
 
     def __init__(self, device=0):
         self._lib = _capi.load()
-        self._ctx = self._lib.ocb_create(int(device))
+        if isinstance(device, str):
+            if device != "all":
+                raise ValueError("device must be an index, -1 / 'all', or a list of indices")
+            device = -1
+        if isinstance(device, (list, tuple)):
+            devs = (ctypes.c_int * len(device))(*[int(d) for d in device])
+            self._ctx = self._lib.ocb_create_multi(devs, len(device))
+            self.device = tuple(int(d) for d in device)
+        else:
+            self._ctx = self._lib.ocb_create(int(device))
+            self.device = int(device)
         if not self._ctx:
             raise _capi.OpenCorrB200Error(_capi.OCB_ERR_CUDA, _capi.last_error(None))
-        self.device = int(device)
         self._keep = []  # host arrays referenced by the last upload
+        self.image_token = 0  # bumped by every set_images_*: lets an operator see that another one replaced its images
+
+    @property
+    def member_count(self):
+        """Devices behind this context (1 unless it is a group)."""
+        return int(self._lib.ocb_member_count(self._ctx))
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -96,6 +113,7 @@ class Engine:
             tar = np.ascontiguousarray(tar, dtype=np.float32)
             self._ck(self._lib.ocb_set_images_2d(self._ctx, _vp(ref), _vp(tar), w, h, 0))
         self._ck(self._lib.ocb_sync(self._ctx))
+        self.image_token += 1
 
     def set_images_3d(self, ref, tar):
         ref, tar = np.asarray(ref), np.asarray(tar)
@@ -110,12 +128,15 @@ class Engine:
             tar = np.ascontiguousarray(tar, dtype=np.float32)
             self._ck(self._lib.ocb_set_images_3d(self._ctx, _vp(ref), _vp(tar), dx, dy, dz))
         self._ck(self._lib.ocb_sync(self._ctx))
+        self.image_token += 1
 
     def set_images_2d_dev(self, d_ref, d_tar, width, height):
         self._ck(self._lib.ocb_set_images_2d_dev(self._ctx, int(d_ref), int(d_tar), width, height))
+        self.image_token += 1
 
     def set_images_3d_dev(self, d_ref, d_tar, dim_x, dim_y, dim_z):
         self._ck(self._lib.ocb_set_images_3d_dev(self._ctx, int(d_ref), int(d_tar), dim_x, dim_y, dim_z))
+        self.image_token += 1
 
     def set_stream(self, cuda_stream):
         """Enqueue on this cudaStream_t handle (0/None = CUDA's legacy default stream)."""
@@ -243,13 +264,27 @@ class _DIC:
         self.engine = engine if engine is not None else default_engine()
         self.ref_img = None
         self.tar_img = None
+        self._token = None      # engine.image_token of this object's own upload
+        self._prepared = False  # prepare() has been called since set_images()
 
     def set_images(self, ref_img, tar_img):
         self.ref_img, self.tar_img = ref_img, tar_img
         self.engine.set_images_2d(ref_img, tar_img)
-        self._images_set()
+        self._token = self.engine.image_token
+        self._prepared = False
 
-    def _images_set(self):
+    def _bind(self):
+        """The operators of one engine share its device images (like the reference's objects share Image2D pointers), but
+        each keeps ITS pair and prepared state (the reference keeps per-object tables): if another object has replaced the
+        engine's images since, upload this object's pair again and redo its prepare()."""
+        if self.ref_img is None or self._token == self.engine.image_token:
+            return
+        self.engine.set_images_2d(self.ref_img, self.tar_img)
+        self._token = self.engine.image_token
+        if self._prepared:
+            self._prepare_engine()
+
+    def _prepare_engine(self):
         pass
 
     def set_subset(self, radius_x, radius_y):
@@ -268,13 +303,25 @@ class _DVC:
         self.engine = engine if engine is not None else default_engine()
         self.ref_img = None
         self.tar_img = None
+        self._token = None
+        self._prepared = False
 
     def set_images(self, ref_img, tar_img):
         self.ref_img, self.tar_img = ref_img, tar_img
         self.engine.set_images_3d(ref_img, tar_img)
-        self._images_set()
+        self._token = self.engine.image_token
+        self._prepared = False
 
-    def _images_set(self):
+    def _bind(self):
+        """See _DIC._bind."""
+        if self.ref_img is None or self._token == self.engine.image_token:
+            return
+        self.engine.set_images_3d(self.ref_img, self.tar_img)
+        self._token = self.engine.image_token
+        if self._prepared:
+            self._prepare_engine()
+
+    def _prepare_engine(self):
         pass
 
     def set_subset(self, radius_x, radius_y, radius_z):
@@ -289,6 +336,7 @@ class FFTCC2D(_DIC):
         pass
 
     def compute(self, poi_queue):
+        self._bind()
         self.engine.fftcc2d(poi_queue, self.subset_radius_x, self.subset_radius_y)
         return poi_queue
 
@@ -298,6 +346,7 @@ class FFTCC3D(_DVC):
         pass
 
     def compute(self, poi_queue):
+        self._bind()
         self.engine.fftcc3d(poi_queue, self.subset_radius_x, self.subset_radius_y, self.subset_radius_z)
         return poi_queue
 
@@ -313,17 +362,20 @@ class _ICGN2D(_DIC):
     def set_iteration(self, conv_criterion, stop_condition):
         self.conv_criterion, self.stop_condition = float(conv_criterion), float(stop_condition)
 
-    def prepare_ref(self):
-        self.engine.icgn2d_prepare()
-
-    def prepare_tar(self):
+    def _prepare_engine(self):
         self.engine.icgn2d_prepare()
 
     def prepare(self):
-        self.engine.icgn2d_prepare()
+        self._bind()
+        self._prepare_engine()
+        self._prepared = True
+
+    prepare_ref = prepare
+    prepare_tar = prepare
 
     def compute(self, poi_queue, center_offset_queue=None):
         """compute(queue) and compute(queue, center_offset_queue); honours set_self_adaptive(True)."""
+        self._bind()
         if center_offset_queue is None and not self.self_adaptive:
             fn = self.engine.icgn2d1 if self._order == 1 else self.engine.icgn2d2
             fn(poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion, self.stop_condition)
@@ -361,6 +413,7 @@ class _ICLM2D(_ICGN2D):
         self.damping = (float(lambda_), float(alpha), float(beta))
 
     def compute(self, poi_queue):
+        self._bind()
         self.engine.iclm2d(self._order, poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion,
                            self.stop_condition, self.damping)
         return poi_queue
@@ -387,10 +440,16 @@ class NR2D1(_DIC):
     def set_iteration(self, conv_criterion, stop_condition):
         self.conv_criterion, self.stop_condition = float(conv_criterion), float(stop_condition)
 
-    def prepare(self):
+    def _prepare_engine(self):
         self.engine.nr2d_prepare()
 
+    def prepare(self):
+        self._bind()
+        self._prepare_engine()
+        self._prepared = True
+
     def compute(self, poi_queue):
+        self._bind()
         self.engine.nr2d1(poi_queue, self.subset_radius_x, self.subset_radius_y, self.conv_criterion, self.stop_condition)
         return poi_queue
 
@@ -474,11 +533,17 @@ class EpipolarSearch(_DIC):
         self.view1_cam.update_matrices()
         self.view2_cam.update_matrices()
         self.update_fundamental_matrix()
+        self._bind()
+        self._prepare_engine()
+        self._prepared = True
+
+    def _prepare_engine(self):
         self.engine.icgn2d_prepare()
 
     def compute(self, poi_queue):
         if self._icgn is None or self.fundamental_matrix is None:
             raise _capi.OpenCorrB200Error(_capi.OCB_ERR_STATE, "EpipolarSearch: create_icgn() and prepare() must be called before compute()")
+        self._bind()
         rx, ry, conv, stop = self._icgn
         self.engine.epipolar_search2d(poi_queue, self.fundamental_matrix, self.parallax_x, self.parallax_y, self.search_radius,
                                       self.search_step, rx, ry, conv, stop)
@@ -541,12 +606,18 @@ class ICGN3D1(_DVC):
     def set_iteration(self, conv_criterion, stop_condition):
         self.conv_criterion, self.stop_condition = float(conv_criterion), float(stop_condition)
 
-    def prepare(self):
+    def _prepare_engine(self):
         self.engine.icgn3d_prepare()
+
+    def prepare(self):
+        self._bind()
+        self._prepare_engine()
+        self._prepared = True
 
     prepare_ref = prepare_tar = prepare
 
     def compute(self, poi_queue):
+        self._bind()
         self.engine.icgn3d1(poi_queue, self.subset_radius_x, self.subset_radius_y, self.subset_radius_z,
                             self.conv_criterion, self.stop_condition)
         return poi_queue

@@ -156,6 +156,111 @@ __device__ __forceinline__ void right_divide_2x6(float* rows, float* M) {
 	}
 }
 
+// ---- the reference's `any interpolated sample < 0 -> zncc = -3` rule (src/oc_icgn.cpp:251-255, :792-796) --------------
+// The sampling loops below evaluate the interpolant with explicit weights and fused multiply-adds; the reference goes
+// through its 16-coefficient LUT and a 16-term polynomial (src/oc_cubic_bspline.cpp:98-129,159-177), and forms the warped
+// position with separately rounded products (Deformation2D1::warp, src/oc_deformation.cpp:94-105).  Next to truly black
+// pixels the B-spline overshoots by tiny amounts, so the sign of the smallest sample can hinge on those roundings.
+// The loops therefore only track min(t); the decision is immediate when it is decisively negative (< -TRIGGER) or
+// positive (>= TRIGGER), and otherwise re-made here sample by sample in the reference's own arithmetic: same operation
+// order, every operation rounded separately (no FMA), the LUT cell rebuilt from the 4x4 pixel block.
+constexpr float ICGN_NEG_TRIGGER = 0.125f; // covers one-ulp differences of the position (ulp 4.9e-4 px at x < 8192) times the steepest 8-bit edge
+constexpr float ICGN_NEG_BAND = 4e-3f;     // fused vs separately rounded evaluation at the SAME position differ by < 3e-4 on 8-bit data
+__constant__ float c_bc_matrix[4][4] = { // BC = B*C, src/oc_cubic_bspline.h:52-58
+	{ -144.0f / 336.0f, 384.0f / 336.0f, -384.0f / 336.0f, 144.0f / 336.0f },
+	{ 342.0f / 336.0f, -702.0f / 336.0f, 450.0f / 336.0f, -90.0f / 336.0f },
+	{ -198.0f / 336.0f, -18.0f / 336.0f, 270.0f / 336.0f, -54.0f / 336.0f },
+	{ 0.0f, 1.0f, 0.0f, 0.0f } };
+
+// BicubicBspline::prepare for ONE cell + BicubicBspline::compute, reference operation order, no contraction.
+// q: the 4x4 pixel block (row pitch `pitch`) whose element [1][1] is the pixel at (floor Y, floor X).
+__device__ __noinline__ float bicubic_reference_order(const float* __restrict__ q, int pitch, float xd, float yd) {
+	float coef[4][4]; // coefficient[k][l] = mat_p[3-k][3-l]
+#pragma unroll 1
+	for (int k = 0; k < 4; k++)
+#pragma unroll 1
+		for (int l = 0; l < 4; l++) {
+			float acc = 0.f;
+#pragma unroll
+			for (int m = 0; m < 4; m++)
+#pragma unroll
+				for (int n = 0; n < 4; n++)
+					acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(c_bc_matrix[l][m], c_bc_matrix[k][n]), q[n * pitch + m]));
+			coef[3 - k][3 - l] = acc;
+		}
+	const float x2 = __fmul_rn(xd, xd), y2 = __fmul_rn(yd, yd), x3 = __fmul_rn(x2, xd), y3 = __fmul_rn(y2, yd);
+	const float yp[4] = { 1.f, yd, y2, y3 }, xp[4] = { 1.f, xd, x2, x3 };
+	float value = coef[0][0];
+#pragma unroll
+	for (int a = 0; a < 4; a++)
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			if (a == 0 && b == 0) continue;
+			float term = coef[a][b];
+			if (a > 0) term = __fmul_rn(term, yp[a]);
+			if (b > 0) term = __fmul_rn(term, xp[b]);
+			value = __fadd_rn(value, term);
+		}
+	return value;
+}
+
+// Does any of the samples idx = idx_begin, idx_begin + 32, ... < idx_end (row-major over the subset) of the warp Aw come
+// out negative in the reference's arithmetic?  Aw: the running warp as the kernels keep it (NP == 6: W00 W01 W02 W10 W11
+// W12; NP == 12: rows 3 and 4 of the 6x6 warp).  Reads the target image directly (rare path).
+template <int NP>
+__device__ __noinline__ bool icgn2d_exact_negative(const float* Aw, float pcx, float pcy, float ox, float oy, int rx, int ry,
+	const float* __restrict__ tar, int w, int h, int idx_begin, int idx_end) {
+	const int sw = 2 * rx + 1;
+	bool negative = false;
+	float A[12];
+#pragma unroll
+	for (int k = 0; k < (NP == 6 ? 6 : 12); k++) A[k] = Aw[k];
+	for (int idx = idx_begin; idx < idx_end; idx += 32) {
+		const int r = idx / sw, c = idx - r * sw;
+		const float xl = (float)(c - rx) - ox, yl = (float)(r - ry) - oy;
+		float wx, wy;
+		if constexpr (NP == 6) { // warp_matrix * (x, y, 1): products summed left to right
+			wx = __fadd_rn(__fadd_rn(__fmul_rn(A[0], xl), __fmul_rn(A[1], yl)), A[2]);
+			wy = __fadd_rn(__fadd_rn(__fmul_rn(A[3], xl), __fmul_rn(A[4], yl)), A[5]);
+		} else { // rows 3, 4 of warp_matrix * (x^2, xy, y^2, x, y, 1), src/oc_deformation.cpp:268-282
+			const float v0 = __fmul_rn(xl, xl), v1 = __fmul_rn(xl, yl), v2 = __fmul_rn(yl, yl);
+			wx = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[0], v0), __fmul_rn(A[1], v1)), __fmul_rn(A[2], v2)), __fmul_rn(A[3], xl)),
+						__fmul_rn(A[4], yl)), A[5]);
+			wy = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[6], v0), __fmul_rn(A[7], v1)), __fmul_rn(A[8], v2)), __fmul_rn(A[9], xl)),
+						__fmul_rn(A[10], yl)), A[11]);
+		}
+		const float X = __fadd_rn(pcx, wx), Y = __fadd_rn(pcy, wy); // center + warped, src/oc_icgn.cpp:238-239
+		if (!((X >= 1.f) && (Y >= 1.f) && (X < (float)(w - 2)) && (Y < (float)(h - 2)))) { // BicubicBspline::compute returns -1 (NaN too)
+			negative = true;
+			continue;
+		}
+		const float xf = floorf(X), yf = floorf(Y);
+		const float* q = tar + (size_t)((int)yf - 1) * w + ((int)xf - 1);
+		float blk[16], top = 0.f;
+#pragma unroll
+		for (int n = 0; n < 4; n++)
+#pragma unroll
+			for (int m = 0; m < 4; m++) {
+				blk[n * 4 + m] = __ldg(q + (size_t)n * w + m);
+				top = fmaxf(top, fabsf(blk[n * 4 + m]));
+			}
+		if (top == 0.f) continue; // an all-zero block gives exactly 0 in any arithmetic
+		const float xd = __fsub_rn(X, xf), yd = __fsub_rn(Y, yf);
+		float wxx[4], wyy[4];
+		bicubic_weights(xd, wxx);
+		bicubic_weights(yd, wyy);
+		float t = 0.f;
+#pragma unroll
+		for (int n = 0; n < 4; n++) {
+			const float row = fmaf(blk[n * 4 + 3], wxx[3], fmaf(blk[n * 4 + 2], wxx[2], fmaf(blk[n * 4 + 1], wxx[1], blk[n * 4] * wxx[0])));
+			t = fmaf(row, wyy[n], t);
+		}
+		if (t >= ICGN_NEG_BAND) continue;
+		if (t <= -ICGN_NEG_BAND || bicubic_reference_order(blk, 4, xd, yd) < 0.f) negative = true;
+	}
+	return negative;
+}
+
 // RC > 0: subset radius known at compile time (rx == ry == RC), so tile pitches and trip counts fold
 // into immediates; RC == 0: any radii at run time.
 // LM: inverse-compositional Levenberg-Marquardt siblings ICLM2D1 / ICLM2D2 (reference src/oc_iclm.cpp:150-358,
@@ -488,7 +593,6 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 		const float xlo = fmaxf(1.f, (float)(tx0 + 1)), xhi = fminf((float)(w - 2), (float)(tx0 + TW - 2));
 		const float ylo = fmaxf(1.f, (float)(ty0 + 1)), yhi = fminf((float)(h - 2), (float)(ty0 + TH - 2));
 		const float xmax = (float)(w - 2), ymax = (float)(h - 2);
-		const float neg_limit = -1e-3f; // reference rejects interpolated values < 0 (src/oc_icgn.cpp:251-255)
 
 		// ---------------- IC-GN iterations ----------------
 		// running warp: NP==6 -> A = {W00,W01,W02,W10,W11,W12}; NP==12 -> rows 3,4 of the 6x6 warp
@@ -516,6 +620,7 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 #pragma unroll
 				for (int q = 0; q <= DEG; q++) G[a][q] = 0.f;
 			bool invalid = false;
+			float tmin = 3.0e38f; // smallest interpolated sample of this pass (see icgn2d_exact_negative)
 			// per-lane x part of the warp (Deformation2D1::warp src/oc_deformation.cpp:94-105,
 			// Deformation2D2::warp rows 3,4 :268-282): X = px + (ax2*y^2 + ax1*y + ax0)
 			float ax0, ax1, ax2, ay0, ay1, ay2;
@@ -547,7 +652,6 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 			}
 			if (iter_fast) {
 				// branch-free row loop: no per-sample validity tests (min(t) is tested after the loop)
-				float tmin = 0.f;
 				float yl = (float)(r_lo - ry) - oy;
 				const float* pc = sC + 3 * (r_lo * sw + lane_c);
 				float xs0, xs1, xs2, ys0, ys1, ys2;
@@ -652,7 +756,6 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 					yl += 1.f;
 				}
 #endif
-				if (!LM && tmin < neg_limit) invalid = true;
 			} else {
 				for (int r = r_lo; r < r_hi; r++) {
 					const float yl = (float)(r - ry) - oy;
@@ -671,7 +774,7 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 							invalid = true;
 						} else {
 							const float t = ok ? bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast) : -1.f; // BicubicBspline::compute returns -1 outside
-							if (!LM && t < neg_limit) invalid = true;
+							tmin = fminf(tmin, t);
 							const float* pc = sC + 3 * (r * sw + lane);
 							const float R = pc[0];
 							const float d = t - R;
@@ -721,7 +824,7 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 					invalid = true;
 				} else {
 					const float t = ok ? bicubic_sample(T, TW, tx0, ty0, tar, w, X, Y, fast) : -1.f;
-					if (!LM && t < neg_limit) invalid = true;
+					tmin = fminf(tmin, t);
 					const float* pc = sC + 3 * (r * sw + c);
 					const float R = pc[0];
 					const float d = t - R;
@@ -735,6 +838,19 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 #pragma unroll
 						for (int a = 0; a < 2; a++) SD[a * NPHI + ii] = fmaf(gd[a], mm, SD[a * NPHI + ii]);
 					}
+				}
+			}
+			if constexpr (!LM) { // src/oc_icgn.cpp:251-255: any sample < 0 rejects the POI (the ICLM siblings have no such test)
+				if (tmin < -ICGN_NEG_TRIGGER) invalid = true;
+				const bool borderline = !(tmin >= ICGN_NEG_TRIGGER);
+				if (__any_sync(0xffffffffu, borderline) && !__any_sync(0xffffffffu, invalid)) {
+					float* sA = slab + 16; // the running warp, handed over through the slab header
+					if (lane == 0) {
+#pragma unroll
+						for (int k = 0; k < (NP == 6 ? 6 : 12); k++) sA[k] = A[k];
+					}
+					__syncwarp();
+					if (icgn2d_exact_negative<NP>(sA, pcx, pcy, ox, oy, rx, ry, tar, w, h, lane, N)) invalid = true;
 				}
 			}
 			bool any_invalid = __any_sync(0xffffffffu, invalid);
@@ -881,6 +997,8 @@ static Icgn2dKernel icgn2d_pick(int np, int rx, int ry, bool lm) {
 	if (np == 6) return (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16, false, WPP> : icgn2d_kernel<6, 0, false, WPP>;
 	return (rx == 20 && ry == 20) ? icgn2d_kernel<12, 20, false, WPP> : icgn2d_kernel<12, 0, false, WPP>;
 }
+
+size_t icgn2d_slab_bytes(int rx, int ry) { return (size_t)icgn2d_slab_floats(rx, ry, false, 1) * sizeof(float); }
 
 int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, int ry, float conv, float stop, int sm_count,
 	size_t smem_optin, int* d_counter, const float* d_center_offsets, const float* lm_damping, cudaStream_t stream, cudaError_t* err) {

@@ -137,6 +137,73 @@ __device__ __forceinline__ float tricubic_taps(const float* __restrict__ base, i
 	return value;
 }
 
+// ---- the reference's `any interpolated sample < 0 -> zncc = -3` rule (src/oc_icgn.cpp:1378-1390) ------------------------
+// Same scheme as icgn2d.cu: the sampling loop tracks min(t); a decisively negative (< -TRIGGER) or positive (>= TRIGGER)
+// minimum decides at once, anything in between is re-decided here in the reference's own arithmetic -- Deformation3D1::warp
+// with separately rounded products (src/oc_deformation.cpp:518-530), TricubicBspline::compute with its basis polynomials
+// and its sum order (src/oc_cubic_bspline.cpp:35-53,353-405), no FMA anywhere.
+constexpr float ICGN3D_NEG_TRIGGER = 0.125f;
+constexpr float ICGN3D_NEG_BAND = 4e-3f;
+
+__device__ __forceinline__ void bspline_basis_reference_order(float t, float* b) {
+	const float s = 1.f / 6.f;
+	b[0] = __fmul_rn(s, __fadd_rn(__fmul_rn(t, __fsub_rn(__fmul_rn(t, __fadd_rn(-t, 3.f)), 3.f)), 1.f));
+	b[1] = __fmul_rn(s, __fadd_rn(__fmul_rn(__fmul_rn(t, t), __fsub_rn(__fmul_rn(3.f, t), 6.f)), 4.f));
+	b[2] = __fmul_rn(s, __fadd_rn(__fmul_rn(t, __fadd_rn(__fmul_rn(t, __fadd_rn(__fmul_rn(-3.f, t), 3.f)), 3.f)), 1.f));
+	b[3] = __fmul_rn(s, __fmul_rn(__fmul_rn(t, t), t));
+}
+
+// Does any of the samples i = first, first + stride, ... < N of the warp A (rows [1+ux uy uz u | vx 1+vy vz v | wx wy 1+wz w])
+// come out negative in the reference's arithmetic?  Reads the coefficient volume directly (rare path).
+__device__ __noinline__ bool icgn3d_exact_negative(const float* A, float px, float py, float pz, int rx, int ry, int rz,
+	const float* __restrict__ coef, int dx, int dy, int dz, int first, int stride) {
+	const int sx = 2 * rx + 1, sy = 2 * ry + 1, sz = 2 * rz + 1, slice = sx * sy, N = slice * sz;
+	bool negative = false;
+	for (int i = first; i < N; i += stride) {
+		const int ii = i / slice, r2 = i - ii * slice, j = r2 / sx, k = r2 - j * sx;
+		const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
+		const float wx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[0], xl), __fmul_rn(A[1], yl)), __fmul_rn(A[2], zl)), A[3]);
+		const float wy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[4], xl), __fmul_rn(A[5], yl)), __fmul_rn(A[6], zl)), A[7]);
+		const float wz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A[8], xl), __fmul_rn(A[9], yl)), __fmul_rn(A[10], zl)), A[11]);
+		const float X = __fadd_rn(px, wx), Y = __fadd_rn(py, wy), Z = __fadd_rn(pz, wz); // center + warped, src/oc_icgn.cpp:1376
+		if (!((X >= 1.f) && (Y >= 1.f) && (Z >= 1.f) && (X < (float)(dx - 2)) && (Y < (float)(dy - 2)) && (Z < (float)(dz - 2)))) {
+			negative = true; // TricubicBspline::compute returns -1
+			continue;
+		}
+		const float xf = floorf(X), yf = floorf(Y), zf = floorf(Z);
+		const float xd = __fsub_rn(X, xf), yd = __fsub_rn(Y, yf), zd = __fsub_rn(Z, zf);
+		const float* base = coef + ((size_t)((int)zf - 1) * dy + ((int)yf - 1)) * dx + ((int)xf - 1);
+		float bx[4], by[4], bz[4];
+		bspline_basis_fast(xd, bx);
+		bspline_basis_fast(yd, by);
+		bspline_basis_fast(zd, bz);
+		const float t = tricubic_taps<true>(base, dx, dx * dy, bx, by, bz);
+		if (t >= ICGN3D_NEG_BAND) continue;
+		if (t <= -ICGN3D_NEG_BAND) {
+			negative = true;
+			continue;
+		}
+		bspline_basis_reference_order(xd, bx);
+		bspline_basis_reference_order(yd, by);
+		bspline_basis_reference_order(zd, bz);
+		float sum_y[4];
+#pragma unroll 1
+		for (int a = 0; a < 4; a++) {
+			float sum_x[4];
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const float* row = base + (size_t)a * dx * dy + (size_t)b * dx;
+				sum_x[b] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bx[0], __ldg(row)), __fmul_rn(bx[1], __ldg(row + 1))), __fmul_rn(bx[2], __ldg(row + 2))),
+					__fmul_rn(bx[3], __ldg(row + 3)));
+			}
+			sum_y[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(by[0], sum_x[0]), __fmul_rn(by[1], sum_x[1])), __fmul_rn(by[2], sum_x[2])), __fmul_rn(by[3], sum_x[3]));
+		}
+		const float value = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bz[0], sum_y[0]), __fmul_rn(bz[1], sum_y[1])), __fmul_rn(bz[2], sum_y[2])), __fmul_rn(bz[3], sum_y[3]));
+		if (value < 0.f) negative = true;
+	}
+	return negative;
+}
+
 #ifndef ICGN3D_PACKED
 // 1: 64-tap evaluation from the smem tile in packed f32x2 arithmetic (FFMA2), 53 instead of 84 FP instructions.
 // Measured on B200 (tools/ab_icgn3d.sh, config D): 29.10 vs 29.19 ms -- no effect, the kernel waits on the 64 LDS
@@ -287,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 #pragma unroll
 			for (int k = 0; k < NITER; k++) acc[k] = 0.f;
 			int invalid = 0;
-			float tmin = 0.f;
+			float tmin = 3.0e38f; // smallest interpolated sample of this pass (see icgn3d_exact_negative)
 			// tile origin in x, y follows the CURRENT translation; x is 16-byte aligned for TMA
 			const int tx0 = floor4((int)floorf(px + A[3]) - rx - 1 - ICGN3D_TILE_MARGIN);
 			const int ty0 = (int)floorf(py + A[7]) - ry - 1 - ICGN3D_TILE_MARGIN;
@@ -375,13 +442,18 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 					sample(zs + il, j, k);
 				}
 			}
-			if (tmin < -1e-3f) invalid = 1; // the reference rejects interpolated values < 0 (src/oc_icgn.cpp:1378-1381)
+			// the reference rejects the POI when any interpolated value is < 0 (src/oc_icgn.cpp:1378-1390)
+			if (tmin < -ICGN3D_NEG_TRIGGER) invalid = 1;
+			const int borderline = !(tmin >= ICGN3D_NEG_TRIGGER) ? 2 : 0;
 #pragma unroll
 			for (int k = 0; k < NITER; k++) {
 				float v = warp_sum(acc[k]);
 				if (lane == 0) sh.part[warp][k] = v;
 			}
-			if (__syncthreads_or(invalid)) { // src/oc_icgn.cpp:1386-1390
+			int verdict = __syncthreads_or(invalid | borderline); // bit 0: some sample is decisively out / negative; bit 1: some minimum is borderline
+			if (verdict == 2) // sh.A still holds this iteration's warp (thread 0 updates it after the next barrier)
+				verdict = __syncthreads_or(icgn3d_exact_negative(sh.A, px, py, pz, rx, ry, rz, coef, dx, dy, dz, tid, ICGN3D_THREADS) ? 1 : 0);
+			if (verdict & 1) {
 				left_image = true;
 				break;
 			}

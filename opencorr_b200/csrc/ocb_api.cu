@@ -8,9 +8,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
 #include <map>
-#include <utility>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/opencorr_b200.h"
@@ -44,7 +48,46 @@ __global__ void widen_u8_kernel(const unsigned char* __restrict__ in, float* __r
 
 static thread_local std::string g_last_error = "";
 
+// One persistent host thread per extra member of a GROUP context (ocb_create(-1) / ocb_create_multi): the members' copies
+// and launches are issued concurrently, each device moving its share over its own PCIe link.
+struct ocb_worker {
+	std::thread th;
+	std::mutex mu;
+	std::condition_variable cv;
+	std::function<int()> job;
+	int result = 0;
+	bool pending = false, stop = false;
+	void loop() {
+		std::unique_lock<std::mutex> lk(mu);
+		for (;;) {
+			cv.wait(lk, [&] { return pending || stop; });
+			if (stop) return;
+			lk.unlock();
+			const int r = job();
+			lk.lock();
+			result = r;
+			pending = false;
+			cv.notify_all();
+		}
+	}
+	void post(std::function<int()> f) {
+		std::lock_guard<std::mutex> lk(mu);
+		job = std::move(f);
+		pending = true;
+		cv.notify_all();
+	}
+	int wait() {
+		std::unique_lock<std::mutex> lk(mu);
+		cv.wait(lk, [&] { return !pending; });
+		return result;
+	}
+};
+
 struct ocb_ctx {
+	// GROUP context: non-empty `members` (single-device contexts owned by the group); none of the per-device fields below
+	// is used.  Host-buffer entry points shard their POI queue over the members; *_dev entry points are refused.
+	std::vector<ocb_ctx*> members;
+	std::vector<ocb_worker*> workers; // workers[i] serves members[i + 1]; member 0 runs on the calling thread
 	int device = 0;
 	int sm_count = 0;
 	size_t smem_optin = 0;
@@ -210,6 +253,74 @@ static int run_host_queue_2d(ocb_ctx* ctx, void* host, size_t n, F dev_call) {
 	return rc;
 }
 
+
+// ---- GROUP contexts: one process, several devices -------------------------------------------------------------------
+static inline bool is_group(const ocb_ctx* ctx) { return ctx && !ctx->members.empty(); }
+
+// Run f(member, index) on the first `used` members concurrently (member 0 on the calling thread); first failure wins.
+template <class F>
+static int group_run(ocb_ctx* g, int used, F f) {
+	if (used > (int)g->members.size()) used = (int)g->members.size();
+	for (int i = 1; i < used; i++) {
+		ocb_ctx* m = g->members[i];
+		g->workers[i - 1]->post([f, m, i]() { return f(m, i); });
+	}
+	int rc = f(g->members[0], 0), bad = 0;
+	for (int i = 1; i < used; i++) {
+		const int r = g->workers[i - 1]->wait();
+		if (rc == OCB_OK && r != OCB_OK) { rc = r; bad = i; }
+	}
+	if (rc != OCB_OK) {
+		g->last_error = "device " + std::to_string(g->members[bad]->device) + ": " + g->members[bad]->last_error;
+		g_last_error = g->last_error;
+	}
+	return rc;
+}
+template <class F>
+static int group_each(ocb_ctx* g, F f) {
+	return group_run(g, (int)g->members.size(), [f](ocb_ctx* m, int) { return f(m); });
+}
+// Contiguous block split of a host queue of n records of rec_bytes: member i gets records [n i / G, n (i+1) / G) and
+// copies them in and out of the caller's array itself (its own PCIe link, straight into the caller's slice).  Queues
+// too short to fill every device use fewer of them (min_per_device records each).  f(member, slice, count, first).
+template <class F>
+static int group_shard(ocb_ctx* g, void* queue, size_t n, size_t rec_bytes, size_t min_per_device, F f) {
+	if (n == 0) return OCB_OK;
+	size_t used = n / min_per_device;
+	if (used < 1) used = 1;
+	if (used > g->members.size()) used = g->members.size();
+	const int G = (int)used;
+	char* base = (char*)queue;
+	return group_run(g, G, [=](ocb_ctx* m, int i) {
+		const size_t a = n * (size_t)i / (size_t)G, b = n * (size_t)(i + 1) / (size_t)G;
+		if (b == a) return (int)OCB_OK;
+		return f(m, (void*)(base + a * rec_bytes), b - a, a);
+	});
+}
+static const size_t OCB_GROUP_MIN_2D = 2048, OCB_GROUP_MIN_3D = 64;
+#define OCB_NO_GROUP(ctx, what) \
+	if (is_group(ctx)) return set_error(ctx, OCB_ERR_ARG, what ": device-pointer / stream entry points need a single-device context (ocb_member)")
+
+static ocb_ctx* create_group(const int* devices, int n) {
+	ocb_ctx* g = new ocb_ctx;
+	g->device = -1;
+	for (int i = 0; i < n; i++) {
+		ocb_ctx* m = ocb_create(devices[i]);
+		if (!m) {
+			for (ocb_ctx* p : g->members) ocb_destroy(p);
+			delete g;
+			return nullptr; // ocb_create left the message in the process-wide slot
+		}
+		g->members.push_back(m);
+	}
+	for (int i = 1; i < n; i++) {
+		ocb_worker* w = new ocb_worker;
+		w->th = std::thread([w]() { w->loop(); });
+		g->workers.push_back(w);
+	}
+	return g;
+}
+
 extern "C" {
 
 int ocb_device_count(void) {
@@ -226,6 +337,11 @@ ocb_ctx* ocb_create(int device) {
 		set_error(nullptr, OCB_ERR_CUDA, "no usable CUDA device (%s); this engine has no CPU fallback",
 			e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
 		return nullptr;
+	}
+	if (device == -1) { // every visible device: a GROUP context
+		std::vector<int> all(n);
+		for (int i = 0; i < n; i++) all[i] = i;
+		return n == 1 ? ocb_create(0) : create_group(all.data(), n);
 	}
 	if (device < 0 || device >= n) {
 		set_error(nullptr, OCB_ERR_ARG, "device %d out of range [0,%d)", device, n);
@@ -258,8 +374,64 @@ ocb_ctx* ocb_create(int device) {
 	return ctx;
 }
 
+ocb_ctx* ocb_create_multi(const int* devices, int n_devices) {
+	if (!devices || n_devices < 1) {
+		set_error(nullptr, OCB_ERR_ARG, "create_multi: need at least one device");
+		return nullptr;
+	}
+	for (int i = 0; i < n_devices; i++)
+		for (int j = 0; j < i; j++)
+			if (devices[i] == devices[j]) {
+				set_error(nullptr, OCB_ERR_ARG, "create_multi: device %d listed twice", devices[i]);
+				return nullptr;
+			}
+	return create_group(devices, n_devices);
+}
+
+int ocb_member_count(const ocb_ctx* ctx) { return !ctx ? 0 : (is_group(ctx) ? (int)ctx->members.size() : 1); }
+
+ocb_ctx* ocb_member(ocb_ctx* ctx, int index) {
+	if (!ctx) return nullptr;
+	if (!is_group(ctx)) return index == 0 ? ctx : nullptr;
+	return (index >= 0 && index < (int)ctx->members.size()) ? ctx->members[index] : nullptr;
+}
+
+int ocb_host_register(void* host, size_t bytes) {
+	if (!host || !bytes) return set_error(nullptr, OCB_ERR_ARG, "host_register: bad arguments");
+	cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return set_error(nullptr, OCB_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
+	}
+	return OCB_OK;
+}
+
+int ocb_host_unregister(void* host) {
+	if (!host) return set_error(nullptr, OCB_ERR_ARG, "host_unregister: bad arguments");
+	cudaError_t e = cudaHostUnregister(host);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return set_error(nullptr, OCB_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+	}
+	return OCB_OK;
+}
+
 void ocb_destroy(ocb_ctx* ctx) {
 	if (!ctx) return;
+	if (is_group(ctx)) {
+		for (ocb_worker* w : ctx->workers) {
+			{
+				std::lock_guard<std::mutex> lk(w->mu);
+				w->stop = true;
+				w->cv.notify_all();
+			}
+			w->th.join();
+			delete w;
+		}
+		for (ocb_ctx* m : ctx->members) ocb_destroy(m);
+		delete ctx;
+		return;
+	}
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	cudaFree(ctx->own_ref2);
@@ -288,27 +460,36 @@ const char* ocb_last_error(const ocb_ctx* ctx) { return ctx ? ctx->last_error.c_
 
 int ocb_set_stream(ocb_ctx* ctx, void* cuda_stream) {
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	OCB_NO_GROUP(ctx, "set_stream");
 	ctx->stream = (cudaStream_t)cuda_stream;
 	return OCB_OK;
 }
 
 int ocb_use_own_stream(ocb_ctx* ctx) {
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	if (is_group(ctx)) return OCB_OK;
 	ctx->stream = ctx->own_stream;
 	return OCB_OK;
 }
 
 int ocb_sync(ocb_ctx* ctx) {
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
+	if (is_group(ctx)) return group_each(ctx, [](ocb_ctx* m) { return ocb_sync(m); });
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return OCB_OK;
 }
 
-long long ocb_launch_count(const ocb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+long long ocb_launch_count(const ocb_ctx* ctx) {
+	if (!ctx) return 0;
+	long long total = ctx->launches;
+	for (const ocb_ctx* m : ctx->members) total += m->launches;
+	return total;
+}
 
 // ---- images ----------------------------------------------------------------------------------
 int ocb_set_images_2d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int width, int height) {
+	OCB_NO_GROUP(ctx, "set_images_2d_dev");
 	if (!ctx || !d_ref || !d_tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d: bad arguments");
 	ctx->img2 = ocb::Image2D{ d_ref, d_tar, width, height };
 	ctx->prepared2 = false;
@@ -317,6 +498,7 @@ int ocb_set_images_2d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, 
 }
 
 int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int width, int height, int col_major) {
+	if (is_group(ctx)) return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_2d(m, ref, tar, width, height, col_major); });
 	if (!ctx || !ref || !tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d: bad arguments");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	const size_t elems = (size_t)width * height;
@@ -351,24 +533,27 @@ int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int widt
 
 // upload `elems` bytes twice (ref, tar) and widen into the context-owned float buffers dst_ref/dst_tar
 static int upload_u8_pair(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, size_t elems, float* dst_ref, float* dst_tar) {
-	if (2 * elems > ctx->d_u8_bytes) {
+	// the widening kernel reads uchar4: the second image starts at a 16-byte aligned offset whatever the pixel count
+	const size_t tar_off = (elems + 15) & ~(size_t)15;
+	if (tar_off + elems > ctx->d_u8_bytes) {
 		cudaFree(ctx->d_u8);
 		ctx->d_u8 = nullptr;
 		ctx->d_u8_bytes = 0;
-		OCB_CUDA(ctx, cudaMalloc(&ctx->d_u8, 2 * elems));
-		ctx->d_u8_bytes = 2 * elems;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->d_u8, tar_off + elems));
+		ctx->d_u8_bytes = tar_off + elems;
 	}
 	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_u8, ref, elems, cudaMemcpyHostToDevice, ctx->stream));
-	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_u8 + elems, tar, elems, cudaMemcpyHostToDevice, ctx->stream));
+	OCB_CUDA(ctx, cudaMemcpyAsync(ctx->d_u8 + tar_off, tar, elems, cudaMemcpyHostToDevice, ctx->stream));
 	const int grid = ctx->sm_count * 8;
 	ocb::widen_u8_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_u8, dst_ref, elems);
-	ocb::widen_u8_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_u8 + elems, dst_tar, elems);
+	ocb::widen_u8_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_u8 + tar_off, dst_tar, elems);
 	ctx->launches += 2;
 	OCB_CUDA(ctx, cudaGetLastError());
 	return OCB_OK;
 }
 
 int ocb_set_images_2d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, int width, int height) {
+	if (is_group(ctx)) return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_2d_u8(m, ref, tar, width, height); });
 	if (!ctx || !ref || !tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d_u8: bad arguments");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	const size_t elems = (size_t)width * height;
@@ -387,6 +572,7 @@ int ocb_set_images_2d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned 
 }
 
 int ocb_set_images_3d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned char* tar, int dim_x, int dim_y, int dim_z) {
+	if (is_group(ctx)) return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_3d_u8(m, ref, tar, dim_x, dim_y, dim_z); });
 	if (!ctx || !ref || !tar || dim_x < 15 || dim_y < 15 || dim_z < 15)
 		return set_error(ctx, OCB_ERR_ARG, "set_images_3d_u8: bad arguments (each dimension must be >= 15)");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -406,6 +592,7 @@ int ocb_set_images_3d_u8(ocb_ctx* ctx, const unsigned char* ref, const unsigned 
 }
 
 int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, int dim_x, int dim_y, int dim_z) {
+	OCB_NO_GROUP(ctx, "set_images_3d_dev");
 	if (!ctx || !d_ref || !d_tar || dim_x < 15 || dim_y < 15 || dim_z < 15) // TricubicBspline needs >= 15 (src/oc_cubic_bspline.cpp:201)
 		return set_error(ctx, OCB_ERR_ARG, "set_images_3d: bad arguments (each dimension must be >= 15)");
 	ctx->img3 = ocb::Image3D{ d_ref, d_tar, nullptr, nullptr, dim_x, dim_y, dim_z };
@@ -414,6 +601,7 @@ int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, 
 }
 
 int ocb_set_images_3d(ocb_ctx* ctx, const float* ref, const float* tar, int dim_x, int dim_y, int dim_z) {
+	if (is_group(ctx)) return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_3d(m, ref, tar, dim_x, dim_y, dim_z); });
 	if (!ctx || !ref || !tar || dim_x < 15 || dim_y < 15 || dim_z < 15)
 		return set_error(ctx, OCB_ERR_ARG, "set_images_3d: bad arguments (each dimension must be >= 15)");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -434,6 +622,7 @@ int ocb_set_images_3d(ocb_ctx* ctx, const float* ref, const float* tar, int dim_
 
 // ---- FFT-CC ----------------------------------------------------------------------------------
 int ocb_fftcc2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry) {
+	OCB_NO_GROUP(ctx, "fftcc2d_dev");
 	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: bad arguments");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "fftcc2d: images not set");
 	if (n == 0) return OCB_OK;
@@ -470,6 +659,7 @@ int ocb_fftcc2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry) {
 }
 
 int ocb_fftcc2d(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry) {
+	if (is_group(ctx) && poi2d) return group_shard(ctx, poi2d, n, OCB_POI2D_FLOATS * sizeof(float), OCB_GROUP_MIN_2D, [=](ocb_ctx* m, void* q, size_t c, size_t) { return ocb_fftcc2d(m, q, c, rx, ry); });
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -477,6 +667,7 @@ int ocb_fftcc2d(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry) {
 }
 
 int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz) {
+	OCB_NO_GROUP(ctx, "fftcc3d_dev");
 	if (!ctx || (!d_poi3d && n) || rx < 1 || ry < 1 || rz < 1) return set_error(ctx, OCB_ERR_ARG, "fftcc3d: bad arguments");
 	if (!ctx->img3.ref) return set_error(ctx, OCB_ERR_STATE, "fftcc3d: images not set");
 	if (n == 0) return OCB_OK;
@@ -547,6 +738,7 @@ int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int r
 }
 
 int ocb_fftcc3d(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz) {
+	if (is_group(ctx) && poi3d) return group_shard(ctx, poi3d, n, OCB_POI3D_FLOATS * sizeof(float), OCB_GROUP_MIN_3D, [=](ocb_ctx* m, void* q, size_t c, size_t) { return ocb_fftcc3d(m, q, c, rx, ry, rz); });
 	if (!ctx || (!poi3d && n)) return set_error(ctx, OCB_ERR_ARG, "fftcc3d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -559,6 +751,7 @@ int ocb_fftcc3d(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz) {
 
 // ---- IC-GN -----------------------------------------------------------------------------------
 int ocb_icgn2d_prepare(ocb_ctx* ctx) {
+	if (is_group(ctx)) return group_each(ctx, [](ocb_ctx* m) { return ocb_icgn2d_prepare(m); });
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "icgn2d_prepare: images not set");
 	ctx->prepared2 = true; // gradients and bicubic weights are recomputed on chip per POI
@@ -567,6 +760,7 @@ int ocb_icgn2d_prepare(ocb_ctx* ctx) {
 
 static int icgn2d_dev(ocb_ctx* ctx, int np, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop, const float* d_offsets = nullptr,
 	const float* lm_damping = nullptr) {
+	OCB_NO_GROUP(ctx, "icgn2d_dev");
 	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "icgn2d: images not set");
 	if (!ctx->prepared2) return set_error(ctx, OCB_ERR_STATE, "icgn2d: prepare() has not been called since setImages()");
@@ -586,6 +780,7 @@ int ocb_icgn2d1_dev(ocb_ctx* ctx, void* d, size_t n, int rx, int ry, float conv,
 int ocb_icgn2d2_dev(ocb_ctx* ctx, void* d, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_dev(ctx, 12, d, n, rx, ry, conv, stop); }
 
 static int icgn2d_host(ocb_ctx* ctx, int np, void* poi2d, size_t n, int rx, int ry, float conv, float stop) {
+	if (is_group(ctx) && poi2d) return group_shard(ctx, poi2d, n, OCB_POI2D_FLOATS * sizeof(float), OCB_GROUP_MIN_2D, [=](ocb_ctx* m, void* q, size_t c, size_t) { return icgn2d_host(m, np, q, c, rx, ry, conv, stop); });
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -620,6 +815,10 @@ static int icgn2d_host_group(ocb_ctx* ctx, int np, float* poi2d, size_t n, int r
 
 int ocb_icgn2d_ex(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, const float* center_offsets,
 	int self_adaptive) {
+	if (is_group(ctx) && poi2d)
+		return group_shard(ctx, poi2d, n, OCB_POI2D_FLOATS * sizeof(float), OCB_GROUP_MIN_2D, [=](ocb_ctx* m, void* q, size_t c, size_t first) {
+			return ocb_icgn2d_ex(m, order, q, c, rx, ry, conv, stop, center_offsets ? center_offsets + 2 * first : nullptr, self_adaptive);
+		});
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn2d_ex: bad arguments");
 	if (order != 1 && order != 2) return set_error(ctx, OCB_ERR_ARG, "icgn2d_ex: order must be 1 or 2");
 	if (n == 0) return OCB_OK;
@@ -633,6 +832,11 @@ int ocb_icgn2d_ex(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry
 		const float* p = q + i * OCB_POI2D_FLOATS;
 		groups[std::make_pair((int)p[23], (int)p[24])].push_back(i);
 	}
+	for (auto& kv : groups) // refuse before anything is launched: no partial results
+		if (kv.first.first >= 1 && kv.first.second >= 1
+			&& (size_t)ocb::icgn2d_slab_bytes(kv.first.first, kv.first.second) > ctx->smem_optin)
+			return set_error(ctx, OCB_ERR_UNSUPPORTED, "icgn2d_ex: subset radius (%d,%d) of a self-adaptive POI exceeds the shared-memory design limit",
+				kv.first.first, kv.first.second);
 	std::vector<float> gq, goff;
 	for (auto& kv : groups) {
 		const int grx = kv.first.first, gry = kv.first.second;
@@ -665,6 +869,9 @@ int ocb_iclm2d_dev(ocb_ctx* ctx, int order, void* d_poi2d, size_t n, int rx, int
 }
 
 int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, float lambda, float alpha, float beta) {
+	if (is_group(ctx) && poi2d)
+		return group_shard(ctx, poi2d, n, OCB_POI2D_FLOATS * sizeof(float), OCB_GROUP_MIN_2D,
+			[=](ocb_ctx* m, void* q, size_t c, size_t) { return ocb_iclm2d(m, order, q, c, rx, ry, conv, stop, lambda, alpha, beta); });
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "iclm2d: bad arguments");
 	if (order != 1 && order != 2) return set_error(ctx, OCB_ERR_ARG, "iclm2d: order must be 1 or 2");
 	if (n == 0) return OCB_OK;
@@ -675,6 +882,7 @@ int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, f
 
 // ---- NR2D1 ---------------------------------------------------------------
 int ocb_nr2d_prepare(ocb_ctx* ctx) {
+	if (is_group(ctx)) return group_each(ctx, [](ocb_ctx* m) { return ocb_nr2d_prepare(m); });
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "nr2d_prepare: images not set");
 	ctx->prepared_nr2 = true; // target gradients and the three interpolants are evaluated on chip per POI
@@ -682,6 +890,7 @@ int ocb_nr2d_prepare(ocb_ctx* ctx) {
 }
 
 int ocb_nr2d1_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float conv, float stop) {
+	OCB_NO_GROUP(ctx, "nr2d1_dev");
 	if (!ctx || (!d_poi2d && n) || rx < 1 || ry < 1) return set_error(ctx, OCB_ERR_ARG, "nr2d1: bad arguments");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "nr2d1: images not set");
 	if (!ctx->prepared_nr2) return set_error(ctx, OCB_ERR_STATE, "nr2d1: prepare() has not been called since setImages()");
@@ -697,6 +906,7 @@ int ocb_nr2d1_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, int rx, int ry, float c
 }
 
 int ocb_nr2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, float stop) {
+	if (is_group(ctx) && poi2d) return group_shard(ctx, poi2d, n, OCB_POI2D_FLOATS * sizeof(float), OCB_GROUP_MIN_2D, [=](ocb_ctx* m, void* q, size_t c, size_t) { return ocb_nr2d1(m, q, c, rx, ry, conv, stop); });
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "nr2d1: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -706,6 +916,7 @@ int ocb_nr2d1(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry, float conv, f
 // ---- EpipolarSearch candidate sweep ----------------------------------------
 int ocb_epipolar_search2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, const float* fundamental, const float* parallax_x, const float* parallax_y,
 	int search_radius, int search_step, int rx, int ry, float conv, float stop) {
+	OCB_NO_GROUP(ctx, "epipolar_search2d_dev");
 	if (!ctx || (!d_poi2d && n) || !fundamental || !parallax_x || !parallax_y || rx < 1 || ry < 1)
 		return set_error(ctx, OCB_ERR_ARG, "epipolar_search2d: bad arguments");
 	if (search_step < 1 || search_radius < search_step)
@@ -744,6 +955,10 @@ int ocb_epipolar_search2d_dev(ocb_ctx* ctx, void* d_poi2d, size_t n, const float
 
 int ocb_epipolar_search2d(ocb_ctx* ctx, void* poi2d, size_t n, const float* fundamental, const float* parallax_x, const float* parallax_y,
 	int search_radius, int search_step, int rx, int ry, float conv, float stop) {
+	if (is_group(ctx) && poi2d)
+		return group_shard(ctx, poi2d, n, OCB_POI2D_FLOATS * sizeof(float), 256, [=](ocb_ctx* m, void* q, size_t c, size_t) {
+			return ocb_epipolar_search2d(m, q, c, fundamental, parallax_x, parallax_y, search_radius, search_step, rx, ry, conv, stop);
+		});
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "epipolar_search2d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -757,6 +972,7 @@ int ocb_epipolar_search2d(ocb_ctx* ctx, void* poi2d, size_t n, const float* fund
 // ---- Strain ---------------------------------------------------------------
 static int strain_dev(ocb_ctx* ctx, int dim, void* d_poi, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation,
 	long long only = -1) {
+	OCB_NO_GROUP(ctx, "strain_dev");
 	if (!ctx || (!d_poi && n) || only >= (long long)n) return set_error(ctx, OCB_ERR_ARG, "strain: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (n > 0x7fffffffull) return set_error(ctx, OCB_ERR_ARG, "strain: too many POIs in one call");
@@ -778,6 +994,11 @@ static int strain_dev(ocb_ctx* ctx, int dim, void* d_poi, size_t n, float radius
 
 static int strain_host(ocb_ctx* ctx, int dim, void* poi, size_t n, float radius, int min_neighbors, float zncc_threshold, int approximation,
 	long long only = -1) {
+	if (is_group(ctx)) { // every POI needs its neighbours wherever they are in the queue: not sharded, the first member runs it
+		const int rc = strain_host(ctx->members[0], dim, poi, n, radius, min_neighbors, zncc_threshold, approximation, only);
+		if (rc) ctx->last_error = ctx->members[0]->last_error;
+		return rc;
+	}
 	if (!ctx || (!poi && n)) return set_error(ctx, OCB_ERR_ARG, "strain: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -814,6 +1035,7 @@ int ocb_strain3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, float radius, int mi
 }
 
 int ocb_icgn3d_prepare(ocb_ctx* ctx) {
+	if (is_group(ctx)) return group_each(ctx, [](ocb_ctx* m) { return ocb_icgn3d_prepare(m); });
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
 	if (!ctx->img3.ref) return set_error(ctx, OCB_ERR_STATE, "icgn3d_prepare: images not set");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -845,6 +1067,7 @@ int ocb_icgn3d_prepare(ocb_ctx* ctx) {
 }
 
 int ocb_icgn3d1_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz, float conv, float stop) {
+	OCB_NO_GROUP(ctx, "icgn3d1_dev");
 	if (!ctx || (!d_poi3d && n) || rx < 1 || ry < 1 || rz < 1) return set_error(ctx, OCB_ERR_ARG, "icgn3d1: bad arguments");
 	if (!ctx->img3.ref) return set_error(ctx, OCB_ERR_STATE, "icgn3d1: images not set");
 	if (!ctx->prepared3) return set_error(ctx, OCB_ERR_STATE, "icgn3d1: prepare() has not been called since setImages()");
@@ -862,6 +1085,7 @@ int ocb_icgn3d1_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int r
 }
 
 int ocb_icgn3d1(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz, float conv, float stop) {
+	if (is_group(ctx) && poi3d) return group_shard(ctx, poi3d, n, OCB_POI3D_FLOATS * sizeof(float), OCB_GROUP_MIN_3D, [=](ocb_ctx* m, void* q, size_t c, size_t) { return ocb_icgn3d1(m, q, c, rx, ry, rz, conv, stop); });
 	if (!ctx || (!poi3d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn3d1: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -873,6 +1097,7 @@ int ocb_icgn3d1(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz, flo
 }
 
 int ocb_get_tables_3d(ocb_ctx* ctx, float* gx, float* gy, float* gz, float* coefficient) {
+	if (is_group(ctx)) return ocb_get_tables_3d(ctx->members[0], gx, gy, gz, coefficient);
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
 	if (!ctx->prepared3) return set_error(ctx, OCB_ERR_STATE, "get_tables_3d: prepare() has not been called");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;

@@ -75,8 +75,8 @@ def displacement_3d(x, y, z, dim_x, dim_y, dim_z):
     return 1.3 + 1e-3 * xt, -0.7 + 1.2e-3 * yt, 2.4 - 1.5e-3 * zt
 
 
-def speckle_pair_2d(width, height, second_order=False, rho=2.0, seed=REF_SEED, quantise=True, device=None):
-    """(ref, tar) float32 [height, width]."""
+def speckle_pair_2d(width, height, second_order=False, rho=2.0, seed=REF_SEED, quantise=True, device=None, background=BACKGROUND):
+    """(ref, tar) float32 [height, width].  background=0 is SURVEY.md's formula (truly black gaps between the speckles)."""
     rng = np.random.default_rng(seed)
     n = int(0.5 * width * height / (np.pi * rho * rho))
     cx = rng.uniform(-8, width + 8, n)
@@ -87,14 +87,14 @@ def speckle_pair_2d(width, height, second_order=False, rho=2.0, seed=REF_SEED, q
     tar = _render((height, width), np.stack([cy + v, cx + u], 1), amp, rho, device)
     out = []
     for im in (ref, tar):
-        im = np.clip(BACKGROUND + (255.0 - BACKGROUND) * im, 0, 255)
+        im = np.clip(background + (255.0 - background) * im, 0, 255)
         if quantise:
             im = np.round(im)
         out.append(im.astype(np.float32))
     return out[0], out[1]
 
 
-def speckle_pair_3d(dim_x, dim_y, dim_z, rho=2.0, seed=REF_SEED, quantise=True, device=None):
+def speckle_pair_3d(dim_x, dim_y, dim_z, rho=2.0, seed=REF_SEED, quantise=True, device=None, background=BACKGROUND):
     """(ref, tar) float32 [dim_z, dim_y, dim_x]."""
     rng = np.random.default_rng(seed)
     n = int(0.35 * dim_x * dim_y * dim_z / (4.0 / 3.0 * np.pi * rho ** 3))
@@ -107,7 +107,7 @@ def speckle_pair_3d(dim_x, dim_y, dim_z, rho=2.0, seed=REF_SEED, quantise=True, 
     tar = _render((dim_z, dim_y, dim_x), np.stack([cz + w, cy + v, cx + u], 1), amp, rho, device)
     out = []
     for im in (ref, tar):
-        im = np.clip(BACKGROUND + (255.0 - BACKGROUND) * im, 0, 255)
+        im = np.clip(background + (255.0 - background) * im, 0, 255)
         if quantise:
             im = np.round(im)
         out.append(im.astype(np.float32))

@@ -134,31 +134,42 @@ def test_icgn2d1_config_a(engine, cfg_a, exact):
 
 
 def test_icgn2d1_golden_table(engine):
-    """FFTCC2D -> ICGN2D1 on the reference's example pair vs its shipped result table."""
+    """FFTCC2D -> ICGN2D1 on the reference's example pair: all 30 000 POIs of examples/test_2d_dic_fftcc_icgn1.cpp:50-66 against
+    the oracle (every sentinel code identical -- the specimen has a black hole, so the `sample < 0` rule fires), and the
+    committed rows of the shipped result table as known answers."""
     ref, tar = util.oht_cfrp_pair()
     g = util.oht_cfrp_golden()
-    tab = g["table"]
-    q = ob.make_poi2d(tab[:, 0:2])
+    xy = synth.grid_2d(30, 30, 100, 300, 2, 2)
+    assert len(xy) == 30000
+    q = ob.make_poi2d(xy)
     f = ob.FFTCC2D(16, 16, engine=engine)
     f.set_images(ref, tar)
     f.compute(q)
+    qc = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(qc, 16, 16)
+    # FFT-CC: identical integer guess everywhere except, possibly, where two correlation bins tie exactly (the three POIs
+    # enumerated in the fixture, tests/test_oracle_golden.py::test_2d_fftcc_ties): there the arg-max hangs on the last bit
+    ties = set(int(r) for r in g["fftcc_tie_rows"])
+    guess_differs = np.where((q[:, 14] != qc[:, 14]) | (q[:, 15] != qc[:, 15]))[0]
+    assert set(int(i) for i in guess_differs) <= ties, guess_differs
+    q[:, 2:17] = qc[:, 2:17]  # same seed for both IC-GN runs, ties included
     icgn = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
     icgn.set_images(ref, tar)
     icgn.prepare()
     icgn.compute(q)
-    guess_same = (q[:, 14] == tab[:, 4]) & (q[:, 15] == tab[:, 5])
-    assert guess_same.mean() > 0.998
-    ok = guess_same & (tab[:, 7] < 10) & (q[:, 17] == tab[:, 7])
-    assert ok.sum() > 0.93 * len(tab)
-    assert np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max() < 1e-4
-    assert np.abs(q[ok, 16] - tab[ok, 6]).max() < 1e-5
-    # and against the oracle on the very same POIs
-    qc = ob.make_poi2d(tab[:, 0:2])
-    o = Oracle2D(ref, tar)
-    o.fftcc2d(qc, 16, 16)
     o.icgn2d1(qc, 16, 16, 0.001, 10)
-    conv = (qc[:, 16] >= 0) & (q[:, 16] >= 0)
-    util.compare_2d(q[conv], qc[conv], "oht_cfrp", max_iter_mismatch_frac=0.02)
+    assert (qc[:, 16] == -3).sum() > 100 and (qc[:, 16] == -4).sum() > 100
+    stats = util.compare_2d(q, qc, "oht_cfrp, all 30 000 POIs", max_iter_mismatch_frac=0.02)  # asserts identical sentinel codes
+    assert stats["n_compared"] > 0.9 * len(q)
+    # known answers: the shipped table (it predates the -4 code: converged rows only)
+    tab, rows = g["table"], g["rows"]
+    qt = q[rows]
+    assert np.array_equal(qt[:, 0:2], tab[:, 0:2].astype(np.float32))
+    ok = (qt[:, 14] == tab[:, 4]) & (qt[:, 15] == tab[:, 5]) & (tab[:, 7] < 10) & (qt[:, 17] == tab[:, 7])
+    assert ok.sum() > 0.93 * len(tab)
+    assert np.abs(qt[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max() < 1e-4
+    assert np.abs(qt[ok, 16] - tab[ok, 6]).max() < 1e-5
 
 
 @pytest.mark.parametrize("r", [20, 12])
@@ -320,27 +331,6 @@ def test_borrowed_device_images_and_device_queue(engine):
     util.compare_2d(q_gpu, q_cpu, "device-resident", max_iter_mismatch_frac=0.03)
     assert eng.launch_count() == 2
     eng.close()
-
-
-def test_negative_interpolated_sample_is_rejected(engine):
-    """The reference rejects a POI when ANY interpolated sample is < 0 (src/oc_icgn.cpp:251-255); bicubic
-    overshoot next to black pixels produces such samples.  A black-background pattern must give -3 on
-    both sides for the same POIs."""
-    ref, tar = synth.speckle_pair_2d(256, 256)
-    ref = np.clip(ref - 24.0, 0, 255).astype(np.float32) * 1.1
-    tar = np.clip(tar - 24.0, 0, 255).astype(np.float32) * 1.1
-    xy = synth.grid_2d(50, 50, 6, 6, 30, 30)
-    q = ob.make_poi2d(xy)
-    q[:, 2], q[:, 8] = 2.0, -2.0
-    q_gpu, q_cpu = q.copy(), q.copy()
-    icgn = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
-    icgn.set_images(ref, tar)
-    icgn.prepare()
-    icgn.compute(q_gpu)
-    Oracle2D(ref, tar).icgn2d1(q_cpu, 16, 16, 0.001, 10)
-    assert (q_cpu[:, 16] == -3).sum() > 0
-    # borderline samples (|t| < 1e-3) may be classified differently; require agreement on >= 90 %
-    assert ((q_gpu[:, 16] == -3) == (q_cpu[:, 16] == -3)).mean() >= 0.9
 
 
 @pytest.mark.parametrize("order", [1, 2])
@@ -532,3 +522,56 @@ def test_self_adaptive_icgn2d1_known_answers(engine):
     assert np.abs(q[:, [2, 8]] - tab[:, [2, 3]]).max() < 1.5e-4     # displacements of ~480 px: a float32 ulp is 3e-5 there
     assert np.abs(q[:, 16] - tab[:, 6]).max() < 1e-5
     assert np.array_equal(q[:, 23:25], tab[:, 13:15])
+
+
+def test_u8_upload_of_odd_sized_images(engine):
+    """Pixel counts that are not a multiple of 4 (501 x 333): the second image of the 8-bit staging buffer must still start
+    on an aligned address (the widening kernel reads uchar4)."""
+    ref, tar = synth.speckle_pair_2d(501, 333)
+    xy = synth.grid_2d(40, 40, 14, 9, 30, 28)
+    res = []
+    for cast in (np.float32, np.uint8):
+        q = ob.make_poi2d(xy)
+        engine.set_images_2d(ref.astype(cast), tar.astype(cast))
+        engine.fftcc2d(q, 16, 16)
+        engine.icgn2d_prepare()
+        engine.icgn2d1(q, 16, 16, 0.001, 10)
+        res.append(q)
+    assert np.array_equal(res[0], res[1])
+    assert (res[0][:, 16] > 0.9).all()
+
+
+def test_two_operators_with_different_pairs_interleaved(engine):
+    """Each DIC object keeps ITS image pair and prepared state, like the reference's per-object tables: preparing B between
+    A.prepare() and A.compute() must not change A's result (nor make it fail)."""
+    ref_a, tar_a = synth.speckle_pair_2d(320, 300)
+    ref_b, tar_b = synth.speckle_pair_2d(320, 300, seed=99)
+    xy = synth.grid_2d(40, 40, 10, 9, 24, 24)
+    seed_a, seed_b = ob.make_poi2d(xy), ob.make_poi2d(xy)
+    Oracle2D(ref_a, tar_a).fftcc2d(seed_a, 16, 16)
+    Oracle2D(ref_b, tar_b).fftcc2d(seed_b, 16, 16)
+
+    def alone(ref, tar, seed):
+        q = seed.copy()
+        op = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+        op.set_images(ref, tar)
+        op.prepare()
+        op.compute(q)
+        return q
+
+    want_a, want_b = alone(ref_a, tar_a, seed_a), alone(ref_b, tar_b, seed_b)
+    assert not np.array_equal(want_a[:, 2], want_b[:, 2])
+    a = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+    b = ob.ICGN2D1(16, 16, 0.001, 10, engine=engine)
+    a.set_images(ref_a, tar_a)
+    a.prepare()
+    b.set_images(ref_b, tar_b)
+    b.prepare()
+    qa, qb = seed_a.copy(), seed_b.copy()
+    a.compute(qa)  # B's images are on the device at this point
+    b.compute(qb)
+    assert np.array_equal(qa, want_a) and np.array_equal(qb, want_b)
+    f = ob.FFTCC2D(16, 16, engine=engine)
+    f.set_images(ref_a, tar_a)
+    b.compute(qb)  # and again after a third object took the engine
+    assert np.array_equal(qb, want_b)

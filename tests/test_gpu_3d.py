@@ -251,3 +251,19 @@ def test_u8_volume_upload_gives_identical_results(engine):
         res.append(q)
     assert np.array_equal(res[0], res[1])
     assert (res[0][:, 18] > 0.8).sum() >= 3  # some r=16 foam subvolumes do not converge (-4): same on both paths
+
+
+def test_u8_upload_of_odd_sized_volume(engine):
+    """101 x 99 x 97 voxels (not a multiple of 4): see test_gpu_2d.py::test_u8_upload_of_odd_sized_images."""
+    ref, tar = synth.speckle_pair_3d(101, 99, 97)
+    xyz = synth.grid_3d(30, 30, 30, 3, 3, 3, 18, 17, 16)
+    res = []
+    for cast in (np.float32, np.uint8):
+        q = ob.make_poi3d(xyz)
+        engine.set_images_3d(ref.astype(cast), tar.astype(cast))
+        engine.fftcc3d(q, 8, 8, 8)
+        engine.icgn3d_prepare()
+        engine.icgn3d1(q, 8, 8, 8, 0.001, 20)
+        res.append(q)
+    assert np.array_equal(res[0], res[1])
+    assert (res[0][:, 18] > 0.9).all()

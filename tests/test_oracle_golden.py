@@ -29,7 +29,7 @@ def test_2d_golden_table(exact):
     o.icgn2d1(q, 16, 16, 0.001, 10, exact=exact)
     # the shipped table stores the FFT-CC result in u0, v0
     mism = (q[:, 14] != tab[:, 4]) | (q[:, 15] != tab[:, 5])
-    assert mism.mean() < 0.002, "FFT-CC guess differs on %d POIs" % mism.sum()
+    assert not mism.any(), "FFT-CC guess differs on POIs %s" % np.where(mism)[0]
     assert np.array_equal(fft_u0, q[:, 14]) and np.array_equal(fft_v0, q[:, 15])
     # The shipped table predates the -4 (not converged) code: its non-converged rows keep a ZNCC.
     conv = (tab[:, 7] < 10) & ~mism
@@ -47,6 +47,32 @@ def test_2d_golden_table(exact):
     # rows the reference left unconverged at iteration 10 carry -4 under the current source
     nonconv = (tab[:, 7] >= 10) & (tab[:, 8] >= 0.001) & ~mism
     assert np.all(q[nonconv & (q[:, 17] >= 10), 16] == -4)
+
+
+def test_2d_fftcc_ties():
+    """The only three POIs (of the 30 000 in the shipped table) whose FFT-CC guess differs between the reference and the oracle
+    are exact ties: two bins of the correlation map hold the same value (the subsets lie in the specimen's featureless hole),
+    and the arg-max is decided by the last bit of the transform -- FFTW in the reference, the oracle's own FFT here."""
+    ref, tar = util.oht_cfrp_pair()
+    g = util.oht_cfrp_golden()
+    rows, tab = g["fftcc_tie_rows"], g["fftcc_tie_table"]
+    assert list(rows) == [22154, 22472, 22557]
+    assert np.array_equal(tab[:, 0:2], [[138, 472], [174, 478], [144, 480]])
+    differing = {}
+    for exact in (0, 1):
+        q = make_poi2d(tab[:, 0:2])
+        Oracle2D(ref, tar).fftcc2d(q, 16, 16, exact=exact)
+        differing[exact] = [int(r) for r, a, t in zip(rows, q, tab) if (a[2], a[8]) != (t[4], t[5])]
+        for a, t in zip(q, tab):  # float64 correlation map: the oracle's bin and the table's bin hold the same value
+            x0, y0 = int(t[0]) - 16, int(t[1]) - 16
+            wa = ref[y0:y0 + 32, x0:x0 + 32].astype(np.float64)
+            wb = tar[y0:y0 + 32, x0:x0 + 32].astype(np.float64)
+            wa, wb = wa - wa.mean(), wb - wb.mean()
+            c = np.fft.ifft2(np.conj(np.fft.fft2(wa)) * np.fft.fft2(wb)).real / np.sqrt((wa * wa).sum() * (wb * wb).sum())
+            at = lambda u, v: c[int(v) % 32, int(u) % 32]
+            assert abs(at(a[2], a[8]) - at(t[4], t[5])) < 1e-12
+            assert abs(c.max() - at(t[4], t[5])) < 1e-12
+    assert differing[0] == [22154, 22472, 22557] and differing[1] == [22154, 22472]
 
 
 def test_dvc_golden_tables():
@@ -79,7 +105,7 @@ def test_2d_full_table_against_reference_checkout():
     o.fftcc2d(q, 16, 16)
     o.icgn2d1(q, 16, 16, 0.001, 10)
     guess_same = (q[:, 14] == tab[:, 4]) & (q[:, 15] == tab[:, 5])
-    assert guess_same.mean() > 0.9995
+    assert list(np.where(~guess_same)[0]) == [22154, 22472, 22557]  # exact ties of the correlation map, see test_2d_fftcc_ties
     ok = guess_same & (tab[:, 7] < 10) & (q[:, 17] == tab[:, 7])
     assert ok.sum() >= 28000
     assert np.abs(q[ok][:, [2, 8]] - tab[ok][:, [2, 3]]).max() < 5e-5
