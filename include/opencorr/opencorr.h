@@ -22,6 +22,7 @@
 #define _OPENCORR_B200_SHIM_H_
 
 #include <algorithm>
+#include <atomic>
 #if __cplusplus >= 201703L
 #include <charconv>
 #endif
@@ -37,6 +38,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../opencorr_b200.h"
@@ -229,6 +231,18 @@ namespace opencorr
 
 	namespace b200
 	{
+		// Every load / allocation of an image gets a process-wide unique id, so that a new Image2D that happens to sit at
+		// the address of a destroyed one is never mistaken for it by the engine's "already on the device?" test.
+		inline unsigned long long nextGeneration()
+		{
+			static std::atomic<unsigned long long> counter{ 0 };
+			return ++counter;
+		}
+		// Starts creating the GPU context on a background thread (defined with Engine below): called from the image
+		// constructors, i.e. as early as an OpenCorr program can tell that it is going to correlate something, so that driver
+		// and context start-up overlap the image decoding and the POI set-up instead of landing in the first compute().
+		inline void warmEngineAsync();
+
 		// Baseline TIFF reader (no OpenCV here): classic TIFF (not BigTIFF), grayscale, 8 or 16 bits per sample (16-bit is scaled
 		// to 8 bits like cv::IMREAD_GRAYSCALE), strips, uncompressed or PackBits, any number of pages.  Returns one 8-bit
 		// plane per page, all of the first page's size.
@@ -322,16 +336,22 @@ namespace opencorr
 		unsigned int size;
 		std::string file_path;
 		MatrixXf eg_mat;
-		unsigned long long generation = 0; // bumped on every load(); lets the engine know when to re-upload
+		unsigned long long generation = 0; // unique per load()/construction; lets the engine know when to re-upload
 
 		inline Image2D(int width, int height)
 		{
+			b200::warmEngineAsync();
+			generation = b200::nextGeneration();
 			eg_mat.resize(height, width);
 			this->width = width;
 			this->height = height;
 			size = height * width;
 		}
-		inline Image2D(std::string file_path) : height(0), width(0), size(0) { load(file_path); }
+		inline Image2D(std::string file_path) : height(0), width(0), size(0)
+		{
+			b200::warmEngineAsync();
+			load(file_path);
+		}
 		~Image2D() = default;
 
 		// cv::imread(path, IMREAD_GRAYSCALE) for what the reference's examples feed it: uncompressed
@@ -397,7 +417,7 @@ namespace opencorr
 				throw std::string("Fail to load file: " + file_path);
 			}
 			this->file_path = file_path;
-			generation++;
+			generation = b200::nextGeneration();
 		}
 	};
 
@@ -410,8 +430,16 @@ namespace opencorr
 		float*** vol_mat = nullptr; // [z][y][x]; payload is one contiguous block at vol_mat[0][0] (src/oc_array.h:56-74)
 		unsigned long long generation = 0;
 
-		inline Image3D(int dim_x, int dim_y, int dim_z) { allocate(dim_x, dim_y, dim_z); }
-		inline Image3D(std::string file_path) : dim_x(0), dim_y(0), dim_z(0), size(0) { load(file_path); }
+		inline Image3D(int dim_x, int dim_y, int dim_z)
+		{
+			b200::warmEngineAsync();
+			allocate(dim_x, dim_y, dim_z);
+		}
+		inline Image3D(std::string file_path) : dim_x(0), dim_y(0), dim_z(0), size(0)
+		{
+			b200::warmEngineAsync();
+			load(file_path);
+		}
 		~Image3D() = default; // like the reference, the volume is released explicitly with release()
 
 		inline void allocate(int dx, int dy, int dz)
@@ -426,7 +454,7 @@ namespace opencorr
 				for (int j = 0; j < dy; j++) p2[(size_t)i * dy + j] = p1 + ((size_t)i * dy + j) * dx;
 				vol_mat[i] = p2 + (size_t)i * dy;
 			}
-			generation++;
+			generation = b200::nextGeneration();
 		}
 		// binary volume: int32[3] header (dim_x, dim_y, dim_z) + float32 payload (src/oc_image.cpp:76-110)
 		inline void loadBin(std::string file_path)
@@ -476,28 +504,64 @@ namespace opencorr
 		// One process-wide GPU context shared by every DIC/DVC object, so that FFTCC and ICGN objects
 		// set up on the same Image pair share ONE device copy (the reference's objects share the host
 		// Image2D through borrowed pointers, src/oc_dic.cpp:22-26).
+		//   OPENCORR_B200_DEVICES=all | 0,1,3   several GPUs behind the one context (ocb_create(-1) / ocb_create_multi):
+		//                                        compute(std::vector<POI>&) shards the queue over them inside the C ABI
+		//   OPENCORR_B200_DEVICE=<n>             one GPU (default 0)
 		struct Engine
 		{
 			ocb_ctx* ctx = nullptr;
 			std::mutex lock;
+			std::thread warm_thread;
+			bool warm_started = false;
+			std::string warm_error;
 			const void* ref_key = nullptr;
 			const void* tar_key = nullptr;
 			unsigned long long ref_gen = 0, tar_gen = 0;
-			bool prepared = false;
-			bool prepared_nr = false;
+			unsigned long long upload_serial = 0; // bumped by every upload: an object's prepare() is valid while this has not moved
 
 			static Engine& get()
 			{
 				static Engine e;
 				return e;
 			}
-			ocb_ctx* context()
+			static ocb_ctx* create(std::string& error)
 			{
-				if (!ctx) {
+				ocb_ctx* c = nullptr;
+				const char* list = std::getenv("OPENCORR_B200_DEVICES");
+				if (list && *list) {
+					if (std::string(list) == "all") c = ocb_create(-1);
+					else {
+						std::vector<int> devs;
+						for (const char* p = list; *p;) {
+							char* end = nullptr;
+							const long v = std::strtol(p, &end, 10);
+							if (end == p) break;
+							devs.push_back((int)v);
+							p = (*end == ',') ? end + 1 : end;
+						}
+						c = ocb_create_multi(devs.data(), (int)devs.size());
+					}
+				} else {
 					int dev = 0;
 					if (const char* s = std::getenv("OPENCORR_B200_DEVICE")) dev = std::atoi(s);
-					ctx = ocb_create(dev);
-					if (!ctx) throw std::string(std::string("opencorr_b200: ") + ocb_last_error(nullptr));
+					c = ocb_create(dev);
+				}
+				if (!c) error = ocb_last_error(nullptr);
+				return c;
+			}
+			// (callers hold `lock`; the warm-up thread itself never takes it)
+			void startWarm()
+			{
+				if (ctx || warm_started) return;
+				warm_started = true;
+				warm_thread = std::thread([this]() { ctx = create(warm_error); });
+			}
+			ocb_ctx* context()
+			{
+				if (warm_thread.joinable()) warm_thread.join();
+				if (!ctx) {
+					if (warm_error.empty()) ctx = create(warm_error);
+					if (!ctx) throw std::string("opencorr_b200: " + warm_error);
 				}
 				return ctx;
 			}
@@ -508,32 +572,58 @@ namespace opencorr
 			void warm()
 			{
 				std::lock_guard<std::mutex> g(lock);
-				context();
+				startWarm();
 			}
 
 			~Engine()
 			{
+				if (warm_thread.joinable()) warm_thread.join();
 				if (ctx) ocb_destroy(ctx);
 			}
-			void useImages(Image2D* ref, Image2D* tar)
+			// Make (ref, tar) the pair on the device.  force = false: skip the copy when this very pair (same objects, same
+			// load generation) is already there -- what FFT-CC's compute() uses.  force = true: copy the pixels as they are NOW,
+			// what prepare() means in the reference (its tables are built from the live image, src/oc_icgn.cpp:138-142).
+			void useImages(Image2D* ref, Image2D* tar, bool force)
 			{
 				if (!ref || !tar) throw std::string("opencorr_b200: setImages() has not been called");
-				if (ref_key == ref && tar_key == tar && ref_gen == ref->generation && tar_gen == tar->generation) return;
+				if (!force && ref_key == ref && tar_key == tar && ref_gen == ref->generation && tar_gen == tar->generation) return;
 				if (ref->width != tar->width || ref->height != tar->height) throw std::string("opencorr_b200: reference and target image sizes differ");
 				check(ocb_set_images_2d(context(), ref->eg_mat.data.data(), tar->eg_mat.data.data(), ref->width, ref->height, 0));
 				ref_key = ref; tar_key = tar; ref_gen = ref->generation; tar_gen = tar->generation;
-				prepared = false;
-				prepared_nr = false;
+				upload_serial++;
 			}
-			void useImages(Image3D* ref, Image3D* tar)
+			void useImages(Image3D* ref, Image3D* tar, bool force)
 			{
 				if (!ref || !tar || !ref->vol_mat || !tar->vol_mat) throw std::string("opencorr_b200: setImages() has not been called");
-				if (ref_key == ref && tar_key == tar && ref_gen == ref->generation && tar_gen == tar->generation) return;
+				if (!force && ref_key == ref && tar_key == tar && ref_gen == ref->generation && tar_gen == tar->generation) return;
 				if (ref->dim_x != tar->dim_x || ref->dim_y != tar->dim_y || ref->dim_z != tar->dim_z) throw std::string("opencorr_b200: reference and target volume sizes differ");
 				check(ocb_set_images_3d(context(), **ref->vol_mat, **tar->vol_mat, ref->dim_x, ref->dim_y, ref->dim_z));
 				ref_key = ref; tar_key = tar; ref_gen = ref->generation; tar_gen = tar->generation;
-				prepared = false;
-				prepared_nr = false;
+				upload_serial++;
+			}
+		};
+		inline void warmEngineAsync() { Engine::get().warm(); }
+
+		// What an object with a prepare() step remembers: the reference keeps per-object tables, so objects prepared on
+		// different pairs can be used in any order.  Here the device holds ONE pair at a time; an object whose pair has been
+		// displaced since its prepare() uploads it again and redoes the (cheap, on-device) prepare before computing.
+		struct Prepared
+		{
+			bool called = false;
+			unsigned long long serial = 0;
+			template <class Img, class F>
+			void prepare(Engine& e, Img* ref, Img* tar, F device_prepare)
+			{
+				e.useImages(ref, tar, true);
+				e.check(device_prepare(e.context()));
+				called = true;
+				serial = e.upload_serial;
+			}
+			template <class Img, class F>
+			void bind(Engine& e, Img* ref, Img* tar, F device_prepare)
+			{
+				if (!called) throw std::string("opencorr_b200: prepare() must be called before compute()");
+				if (serial != e.upload_serial) prepare(e, ref, tar, device_prepare);
 			}
 		};
 	} // namespace b200
@@ -601,7 +691,7 @@ namespace opencorr
 		{
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
-			e.useImages(ref_img, tar_img);
+			e.useImages(ref_img, tar_img, false);
 			e.check(ocb_fftcc2d(e.context(), p, n, subset_radius_x, subset_radius_y));
 		}
 	};
@@ -626,7 +716,7 @@ namespace opencorr
 		{
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
-			e.useImages(ref_img, tar_img);
+			e.useImages(ref_img, tar_img, false);
 			e.check(ocb_fftcc3d(e.context(), p, n, subset_radius_x, subset_radius_y, subset_radius_z));
 		}
 	};
@@ -640,6 +730,7 @@ namespace opencorr
 		protected:
 			float conv_criterion;
 			float stop_condition;
+			Prepared prepared;
 
 		public:
 			ICGN2D(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
@@ -667,10 +758,10 @@ namespace opencorr
 			{
 				Engine& e = Engine::get();
 				std::lock_guard<std::mutex> g(e.lock);
-				e.useImages(ref_img, tar_img);
-				e.check(ocb_icgn2d_prepare(e.context()));
-				e.prepared = true;
+				prepared.prepare(e, ref_img, tar_img, ocb_icgn2d_prepare);
 			}
+			// (engine lock held) make this object's pair and prepare() current on the device
+			void bindLocked(Engine& e) { prepared.bind(e, ref_img, tar_img, ocb_icgn2d_prepare); }
 			void compute(POI2D* poi) { run(poi, 1, nullptr); }
 			void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size(), nullptr); }
 			// off-centre subsets, src/oc_icgn.cpp:353-557 / :910-1136 (Point2D is two packed floats)
@@ -686,8 +777,7 @@ namespace opencorr
 			{
 				Engine& e = Engine::get();
 				std::lock_guard<std::mutex> g(e.lock);
-				e.useImages(ref_img, tar_img);
-				if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+				bindLocked(e);
 				if (self_adaptive || offsets)
 					e.check(ocb_icgn2d_ex(e.context(), ORDER, p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition, offsets, self_adaptive ? 1 : 0));
 				else if (ORDER == 1) e.check(ocb_icgn2d1(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
@@ -727,6 +817,7 @@ namespace opencorr
 			float conv_criterion;
 			float stop_condition;
 			DampingParameter damping;
+			Prepared prepared;
 
 		public:
 			ICLM2D(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
@@ -760,9 +851,7 @@ namespace opencorr
 			{
 				Engine& e = Engine::get();
 				std::lock_guard<std::mutex> g(e.lock);
-				e.useImages(ref_img, tar_img);
-				e.check(ocb_icgn2d_prepare(e.context()));
-				e.prepared = true;
+				prepared.prepare(e, ref_img, tar_img, ocb_icgn2d_prepare);
 			}
 			void compute(POI2D* poi) { run(poi, 1); }
 			void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
@@ -773,8 +862,7 @@ namespace opencorr
 				if (self_adaptive) throw std::string("opencorr_b200: self-adaptive subsets are implemented for ICGN2D1/ICGN2D2 only");
 				Engine& e = Engine::get();
 				std::lock_guard<std::mutex> g(e.lock);
-				e.useImages(ref_img, tar_img);
-				if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+				prepared.bind(e, ref_img, tar_img, ocb_icgn2d_prepare);
 				e.check(ocb_iclm2d(e.context(), ORDER, p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition, damping.lambda, damping.alpha,
 					damping.beta));
 			}
@@ -877,6 +965,7 @@ namespace opencorr
 	private:
 		float conv_criterion;
 		float stop_condition;
+		b200::Prepared prepared;
 
 	public:
 		NR2D1(int subset_radius_x, int subset_radius_y, float conv_criterion, float stop_condition, int thread_number)
@@ -902,9 +991,7 @@ namespace opencorr
 		{
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
-			e.useImages(ref_img, tar_img);
-			e.check(ocb_nr2d_prepare(e.context()));
-			e.prepared_nr = true;
+			prepared.prepare(e, ref_img, tar_img, ocb_nr2d_prepare);
 		}
 		void compute(POI2D* poi) { run(poi, 1); }
 		void compute(std::vector<POI2D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
@@ -914,8 +1001,7 @@ namespace opencorr
 		{
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
-			e.useImages(ref_img, tar_img);
-			if (!e.prepared_nr) throw std::string("opencorr_b200: prepare() must be called before compute()");
+			prepared.bind(e, ref_img, tar_img, ocb_nr2d_prepare);
 			e.check(ocb_nr2d1(e.context(), p, n, subset_radius_x, subset_radius_y, conv_criterion, stop_condition));
 		}
 	};
@@ -1129,8 +1215,7 @@ namespace opencorr
 			if (icgn1 == nullptr) throw std::string("opencorr_b200: createICGN() and prepare() must be called before compute()");
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
-			e.useImages(ref_img, tar_img);
-			if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+			icgn1->bindLocked(e);
 			e.check(ocb_epipolar_search2d(e.context(), p, n, fundamental_matrix, parallax_x, parallax_y, search_radius, search_step, icgn1->subset_radius_x,
 				icgn1->subset_radius_y, icgn_conv, icgn_stop));
 		}
@@ -1141,6 +1226,7 @@ namespace opencorr
 	private:
 		float conv_criterion;
 		float stop_condition;
+		b200::Prepared prepared;
 
 	public:
 		ICGN3D1(int subset_radius_x, int subset_radius_y, int subset_radius_z, float conv_criterion, float stop_condition, int thread_number)
@@ -1169,9 +1255,7 @@ namespace opencorr
 		{
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
-			e.useImages(ref_img, tar_img);
-			e.check(ocb_icgn3d_prepare(e.context()));
-			e.prepared = true;
+			prepared.prepare(e, ref_img, tar_img, ocb_icgn3d_prepare);
 		}
 		void compute(POI3D* poi) { run(poi, 1); }
 		void compute(std::vector<POI3D>& poi_queue) { run(poi_queue.data(), poi_queue.size()); }
@@ -1181,8 +1265,7 @@ namespace opencorr
 		{
 			b200::Engine& e = b200::Engine::get();
 			std::lock_guard<std::mutex> g(e.lock);
-			e.useImages(ref_img, tar_img);
-			if (!e.prepared) throw std::string("opencorr_b200: prepare() must be called before compute()");
+			prepared.bind(e, ref_img, tar_img, ocb_icgn3d_prepare);
 			e.check(ocb_icgn3d1(e.context(), p, n, subset_radius_x, subset_radius_y, subset_radius_z, conv_criterion, stop_condition));
 		}
 	};

@@ -34,12 +34,16 @@
 
 namespace ocb {
 
-#ifndef ICGN2D_PACKED
-// 1: fast row loop in packed f32x2 arithmetic (FFMA2/FMUL2/FADD2).  Measured on B200 (tools/ab_icgn2d.sh, config B/C/E):
-// 65 instead of 80 issue slots per sample, but ICGN2D1 gets 10 % SLOWER (0.95 vs 0.865 ms) and ICGN2D2 2 % faster: the
-// kernel is bound by dependent-issue latency at 11 warps/SM, and the packed ops lengthen the dependency chains
-// (Horner weights, the 4-row accumulation) more than they relieve the issue port.  Kept for reference, off.
-#define ICGN2D_PACKED 0
+#ifndef ICGN2D_PAIRS
+// 1: the fast sampling loop takes TWO subset rows per lane and step and does their arithmetic in packed f32x2 pairs
+// (FFMA2 / FMUL2 / FADD2, ocb_f32x2.cuh) -- position, bicubic weights, taps and all sums of rows r and r + 1 go through ONE
+// instruction per pair, and the two 4x4 pixel blocks, which overlap in three rows, are fetched as one 4x5 block (20 LDS
+// instead of 32).  The two rows are independent, so unlike packing WITHIN one sample (tried in round 1: 10 % slower)
+// no dependency chain gets longer.  0: one row per step, scalar arithmetic (the round-1 loop), kept for A/B runs.
+#define ICGN2D_PAIRS 1
+#endif
+#ifndef ICGN2D_PAIR_UNROLL
+#define ICGN2D_PAIR_UNROLL 2 // row pairs in flight per lane
 #endif
 #ifndef ICGN2D_MINB
 #define ICGN2D_MINB 16 // resident one-warp CTAs the 6-parameter kernels' register budget is sized for (16 -> 128 registers; measured best of 11/16/20)
@@ -48,6 +52,7 @@ namespace ocb {
 #define ICGN2D_UNROLL 3
 #endif
 constexpr int ICGN2D_ROW_UNROLL = ICGN2D_UNROLL; // rows of the fast sampling loop in flight per lane
+constexpr int ICGN2D_PAIR_UNROLL_N = ICGN2D_PAIR_UNROLL;
 constexpr int ICGN2D_TILE_MARGIN = 1; // slack (pixels) around subset+support in the target tile
 // TMA tile loads need the innermost coordinate 16-byte aligned (x multiple of 4 floats; measured: an
 // unaligned x raises 'illegal instruction'), so tile origins are rounded down to a multiple of 4 and
@@ -669,54 +674,93 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 					}
 				}
 				const float* tbase = T - (ty0 + 1) * TW - (tx0 + 1);
-#if ICGN2D_PACKED
-				// Packed-pair arithmetic (fma/mul/add.rn.f32x2 -> FFMA2/FMUL2/FADD2, ocb_f32x2.cuh): the x and y parts of the
-				// position, the weights {w0,w1},{w2,w3} of each axis, the column pairs of the 4x4 block and the two
-				// gradient channels each go through ONE instruction per pair -- ~55 instead of ~80 issue slots per sample.
-				const float2 pc2 = make_float2(pcx, pcy);
-				const float2 s0 = make_float2(xs0, ys0), s1 = make_float2(xs1, ys1), s2 = make_float2(xs2, ys2);
-				float2 G2[DEG + 1]; // {sum gx d y^Q, sum gy d y^Q}
+				int r_first = r_lo; // first row of the one-row-per-step loop below
+#if ICGN2D_PAIRS
+				{
+					// rows (r, r + 1) as lanes {.x, .y} of packed pairs; the same operations, in the same order, as the one-row loop
+					float2 d1p = make_float2(0.f, 0.f), d2p = d1p, rdp = d1p;
+					float2 Gp[2][DEG + 1];
 #pragma unroll
-				for (int qq = 0; qq <= DEG; qq++) G2[qq] = make_float2(0.f, 0.f);
-#pragma unroll ICGN2D_ROW_UNROLL
-				for (int r = r_lo; r < r_hi; r++) {
-					const float2 yl2 = bcast2(yl);
-					float2 XY;
-					if constexpr (NP == 6) XY = fadd2(pc2, ffma2(s1, yl2, s0));
-					else XY = fadd2(pc2, ffma2(ffma2(s2, yl2, s1), yl2, s0));
-					const float xf = floorf(XY.x), yf = floorf(XY.y);
-					const float2 fr = fsub2(XY, make_float2(xf, yf));
-					float2 wx01, wx23, wy01, wy23;
-					bicubic_weights2(fr.x, wx01, wx23);
-					bicubic_weights2(fr.y, wy01, wy23);
-					const float* q = tbase + (int)yf * TW + (int)xf;
-					// {q0 w0 + q2 w2, q1 w1 + q3 w3} per block row, weighted by wy and summed over the rows in both halves
-					float2 T2 = fmul2(ffma2(make_float2(q[2], q[3]), wx23, fmul2(make_float2(q[0], q[1]), wx01)), bcast2(wy01.x));
-					T2 = ffma2(ffma2(make_float2(q[TW + 2], q[TW + 3]), wx23, fmul2(make_float2(q[TW], q[TW + 1]), wx01)), bcast2(wy01.y), T2);
-					T2 = ffma2(ffma2(make_float2(q[2 * TW + 2], q[2 * TW + 3]), wx23, fmul2(make_float2(q[2 * TW], q[2 * TW + 1]), wx01)), bcast2(wy23.x), T2);
-					T2 = ffma2(ffma2(make_float2(q[3 * TW + 2], q[3 * TW + 3]), wx23, fmul2(make_float2(q[3 * TW], q[3 * TW + 1]), wx01)), bcast2(wy23.y), T2);
-					const float t = T2.x + T2.y;
-					tmin = fminf(tmin, t);
-					const float R = pc[0];
-					const float d = lane_on ? t - R : 0.f;
-					d1 += d;
-					d2 = fmaf(d, d, d2);
-					rd = fmaf(R, d, rd);
-					float2 gd = fmul2(make_float2(pc[1], pc[2]), bcast2(d));
-					G2[0] = fadd2(G2[0], gd);
+					for (int a = 0; a < 2; a++)
 #pragma unroll
-					for (int qq = 1; qq <= DEG; qq++) {
-						gd = fmul2(gd, yl2);
-						G2[qq] = fadd2(G2[qq], gd);
+						for (int qq = 0; qq <= DEG; qq++) Gp[a][qq] = d1p;
+					const float2 pcx2 = bcast2(pcx), pcy2 = bcast2(pcy);
+					const float2 xs0p = bcast2(xs0), xs1p = bcast2(xs1), xs2p = bcast2(xs2), ys0p = bcast2(ys0), ys1p = bcast2(ys1), ys2p = bcast2(ys2);
+					constexpr float s336 = 1.0f / 336.0f;
+					// w_j(t) = ((a_j t + b_j) t + c_j) t + e_j, the reference's BC matrix by columns (ocb_common.cuh bicubic_weights)
+					constexpr float BA[4] = { -144.0f * s336, 384.0f * s336, -384.0f * s336, 144.0f * s336 };
+					constexpr float BB[4] = { 342.0f * s336, -702.0f * s336, 450.0f * s336, -90.0f * s336 };
+					constexpr float BC_[4] = { -198.0f * s336, -18.0f * s336, 270.0f * s336, -54.0f * s336 };
+					constexpr float BE[4] = { 0.f, 1.f, 0.f, 0.f };
+					float2 yl2 = make_float2(yl, yl + 1.f);
+					const int npair = (r_hi - r_lo) >> 1;
+#pragma unroll ICGN2D_PAIR_UNROLL_N
+					for (int pr = 0; pr < npair; pr++) {
+						float2 X2, Y2;
+						if constexpr (NP == 6) {
+							X2 = fadd2(pcx2, ffma2(xs1p, yl2, xs0p));
+							Y2 = fadd2(pcy2, ffma2(ys1p, yl2, ys0p));
+						} else {
+							X2 = fadd2(pcx2, ffma2(ffma2(xs2p, yl2, xs1p), yl2, xs0p));
+							Y2 = fadd2(pcy2, ffma2(ffma2(ys2p, yl2, ys1p), yl2, ys0p));
+						}
+						const float xfa = floorf(X2.x), xfb = floorf(X2.y), yfa = floorf(Y2.x), yfb = floorf(Y2.y);
+						const float2 tx = fsub2(X2, make_float2(xfa, xfb)), ty = fsub2(Y2, make_float2(yfa, yfb));
+						// weights of both rows: WX[j] = {w_j(tx.x), w_j(tx.y)}; in y the rows of the shared 4x5 block are j = 0..4 and row
+						// r + 1 starts one block row lower: WY[j] = {w_j(ty.x), w_{j-1}(ty.y)} (a missing weight is an exact 0)
+						float2 WX[4], WYu[4], WY[5];
+#pragma unroll
+						for (int j = 0; j < 4; j++) {
+							WX[j] = ffma2(ffma2(ffma2(bcast2(BA[j]), tx, bcast2(BB[j])), tx, bcast2(BC_[j])), tx, bcast2(BE[j]));
+							WYu[j] = ffma2(ffma2(ffma2(bcast2(BA[j]), ty, bcast2(BB[j])), ty, bcast2(BC_[j])), ty, bcast2(BE[j]));
+						}
+						WY[0] = make_float2(WYu[0].x, 0.f);
+#pragma unroll
+						for (int j = 1; j < 4; j++) WY[j] = make_float2(WYu[j].x, WYu[j - 1].y);
+						WY[4] = make_float2(0.f, WYu[3].y);
+						const float* q = tbase + (int)yfa * TW + (int)xfa;
+						float2 t2 = make_float2(0.f, 0.f);
+#pragma unroll
+						for (int j = 0; j < 5; j++) {
+							const float2 row = ffma2(bcast2(q[j * TW + 3]), WX[3], ffma2(bcast2(q[j * TW + 2]), WX[2], ffma2(bcast2(q[j * TW + 1]), WX[1], fmul2(bcast2(q[j * TW]), WX[0]))));
+							t2 = ffma2(row, WY[j], t2);
+						}
+						// row r + 1 normally sits one block row below row r in the same columns; where the warp's shear or stretch
+						// breaks that (a few lanes per POI), its sample is evaluated on its own
+						if (xfb != xfa || yfb != yfa + 1.f) t2.y = bicubic_sample(T, TW, tx0, ty0, tar, w, X2.y, Y2.y, true);
+						tmin = fminf(tmin, fminf(t2.x, t2.y));
+						const float2 R2 = make_float2(pc[0], pc[3 * sw]);
+						float2 dd = fsub2(t2, R2);
+						if (!lane_on) dd = make_float2(0.f, 0.f);
+						d1p = fadd2(d1p, dd);
+						d2p = ffma2(dd, dd, d2p);
+						rdp = ffma2(R2, dd, rdp);
+						float2 gd[2] = { fmul2(make_float2(pc[1], pc[3 * sw + 1]), dd), fmul2(make_float2(pc[2], pc[3 * sw + 2]), dd) };
+#pragma unroll
+						for (int a = 0; a < 2; a++) {
+							float2 tt = gd[a];
+#pragma unroll
+							for (int qq = 0; qq <= DEG; qq++) {
+								Gp[a][qq] = fadd2(Gp[a][qq], tt);
+								if (qq < DEG) tt = fmul2(tt, yl2);
+							}
+						}
+						pc += 6 * sw;
+						yl2 = fadd2(yl2, bcast2(2.f));
 					}
-					pc += 3 * sw;
-					yl += 1.f;
-				}
+					d1 = d1p.x + d1p.y;
+					d2 = d2p.x + d2p.y;
+					rd = rdp.x + rdp.y;
 #pragma unroll
-				for (int qq = 0; qq <= DEG; qq++) { G[0][qq] = G2[qq].x; G[1][qq] = G2[qq].y; }
-#else
+					for (int a = 0; a < 2; a++)
+#pragma unroll
+						for (int qq = 0; qq <= DEG; qq++) G[a][qq] = Gp[a][qq].x + Gp[a][qq].y;
+					r_first = r_lo + 2 * npair;
+					yl += (float)(2 * npair);
+				}
+#endif
 #pragma unroll ICGN2D_ROW_UNROLL
-				for (int r = r_lo; r < r_hi; r++) {
+				for (int r = r_first; r < r_hi; r++) {
 					float X, Y;
 					if constexpr (NP == 6) {
 						X = pcx + fmaf(xs1, yl, xs0);
@@ -755,7 +799,6 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 					pc += 3 * sw;
 					yl += 1.f;
 				}
-#endif
 			} else {
 				for (int r = r_lo; r < r_hi; r++) {
 					const float yl = (float)(r - ry) - oy;

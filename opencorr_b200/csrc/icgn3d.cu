@@ -204,29 +204,23 @@ __device__ __noinline__ bool icgn3d_exact_negative(const float* A, float px, flo
 	return negative;
 }
 
-#ifndef ICGN3D_PACKED
-// 1: 64-tap evaluation from the smem tile in packed f32x2 arithmetic (FFMA2), 53 instead of 84 FP instructions.
-// Measured on B200 (tools/ab_icgn3d.sh, config D): 29.10 vs 29.19 ms -- no effect, the kernel waits on the 64 LDS
-// per sample (shared-memory pipe), not on the FP issue slots.  Kept for reference, off.
-#define ICGN3D_PACKED 0
+#ifndef ICGN3D_PAIRS
+// 1: when a whole z-slab of samples has its support inside the staged tile (the normal case: one warp-uniform corner test
+// per slab replaces the per-sample range tests), every lane takes TWO y-adjacent samples per step.  Their 4x4x4 blocks
+// overlap in three of four block rows, so the pair is evaluated from ONE 4x5x4 block (80 LDS instead of 128 -- the kernel
+// was bound by the shared-memory pipe at 64 LDS per sample), and the arithmetic of the two samples runs in packed f32x2
+// pairs (FFMA2), rows (j, j+1) in lanes {.x, .y}: 104 instead of 168 issue slots for the taps, the same operations in the
+// same order as the one-sample path (the results are bit-identical).  0: one sample per step (round-1 loop), for A/B runs.
+#define ICGN3D_PAIRS 1
 #endif
-// The same 64 taps with the x-taps paired {c0 b0 + c2 b2, c1 b1 + c3 b3}: both halves are weighted by by[j], bz[i]
-// (scalar operands broadcast by the instruction) and added at the end.
-__device__ __forceinline__ float tricubic_taps_packed(const float* base, int py_, int pz_, const float* bx, const float* by, const float* bz) {
-	const float2 bx01 = make_float2(bx[0], bx[1]), bx23 = make_float2(bx[2], bx[3]);
-	float2 value = make_float2(0.f, 0.f);
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		float2 sy_acc = make_float2(0.f, 0.f);
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const float* row = base + i * pz_ + j * py_;
-			const float2 sx = ffma2(make_float2(row[2], row[3]), bx23, fmul2(make_float2(row[0], row[1]), bx01));
-			sy_acc = j == 0 ? fmul2(sx, bcast2(by[0])) : ffma2(sx, bcast2(by[j]), sy_acc);
-		}
-		value = i == 0 ? fmul2(sy_acc, bcast2(bz[0])) : ffma2(sy_acc, bcast2(bz[i]), value);
-	}
-	return value.x + value.y;
+
+// packed cubic B-spline basis: bspline_basis_fast on two arguments at once
+__device__ __forceinline__ void bspline_basis_fast2(float2 t, float2* b) {
+	const float2 om = fsub2(bcast2(1.f), t), t2 = fmul2(t, t);
+	b[0] = fmul2(fmul2(fmul2(om, om), om), bcast2(1.f / 6.f));
+	b[3] = fmul2(fmul2(t2, t), bcast2(1.f / 6.f));
+	b[1] = ffma2(t2, ffma2(bcast2(0.5f), t, bcast2(-1.f)), bcast2(2.f / 3.f));
+	b[2] = fsub2(fsub2(fsub2(bcast2(1.f), b[0]), b[1]), b[3]);
 }
 
 __host__ __device__ inline int icgn3d_tile_x(int rx) { return round_up4(2 * rx + 1 + 3 + 2 * ICGN3D_TILE_MARGIN + 3); }
@@ -388,35 +382,8 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 					__syncthreads();
 				}
 				const float* tbase = T - ((tz0 + 1) * TXY + (ty0 + 1) * TX + (tx0 + 1));
-				// One sample: warp, 64-tap B-spline evaluation, single-pass sums.
-				auto sample = [&](int ii, int j, int k) {
-					const float4 c4 = __ldg(img.rg + (goff + ((size_t)ii * dy + j) * dx + k)); // issued first: its latency hides under the taps
-					const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
-					// Deformation3D1::warp, src/oc_deformation.cpp:518-530; centre + warped (:1376)
-					const float X = px + fmaf(A[0], xl, fmaf(A[1], yl, fmaf(A[2], zl, A[3])));
-					const float Y = py + fmaf(A[4], xl, fmaf(A[5], yl, fmaf(A[6], zl, A[7])));
-					const float Z = pz + fmaf(A[8], xl, fmaf(A[9], yl, fmaf(A[10], zl, A[11])));
-					const bool fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi) && (Z >= zlo) && (Z < zhi);
-					if (!fast) {
-						// TricubicBspline::compute validity, src/oc_cubic_bspline.cpp:356-361 (NaN fails too)
-						const bool ok = (X >= 1.f) && (Y >= 1.f) && (Z >= 1.f) && (X < xmax) && (Y < ymax) && (Z < zmax);
-						if (!ok) {
-							invalid = 1;
-							return;
-						}
-					}
-					const float xf = floorf(X), yf = floorf(Y), zf = floorf(Z);
-					float bx[4], by[4], bz[4];
-					bspline_basis_fast(X - xf, bx);
-					bspline_basis_fast(Y - yf, by);
-					bspline_basis_fast(Z - zf, bz);
-					float t;
-#if ICGN3D_PACKED
-					if (fast) t = tricubic_taps_packed(tbase + ((int)zf * TXY + (int)yf * TX + (int)xf), TX, TXY, bx, by, bz);
-#else
-					if (fast) t = tricubic_taps<false>(tbase + ((int)zf * TXY + (int)yf * TX + (int)xf), TX, TXY, bx, by, bz);
-#endif
-					else t = tricubic_taps<true>(coef + ((size_t)((int)zf - 1) * dy + ((int)yf - 1)) * dx + ((int)xf - 1), dx, dx * dy, bx, by, bz);
+				// single-pass sums of one sample (DESIGN.md "single-pass IC-GN sums"); c4 = {R, gx, gy, gz}
+				auto accumulate = [&](float t, const float4& c4, float xl, float yl, float zl) {
 					tmin = fminf(tmin, t);
 					const float R = c4.x;
 					const float d = t - R;
@@ -428,18 +395,123 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 					acc[7] += gyd; acc[8] = fmaf(gyd, xl, acc[8]); acc[9] = fmaf(gyd, yl, acc[9]); acc[10] = fmaf(gyd, zl, acc[10]);
 					acc[11] += gzd; acc[12] = fmaf(gzd, xl, acc[12]); acc[13] = fmaf(gzd, yl, acc[13]); acc[14] = fmaf(gzd, zl, acc[14]);
 				};
+				// One sample: warp, 64-tap B-spline evaluation, single-pass sums.  CHECKED: per-sample range tests (tile / volume).
+				auto sample = [&](int ii, int j, int k, bool checked) {
+					const float4 c4 = __ldg(img.rg + (goff + ((size_t)ii * dy + j) * dx + k)); // issued first: its latency hides under the taps
+					const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
+					// Deformation3D1::warp, src/oc_deformation.cpp:518-530; centre + warped (:1376)
+					const float X = px + fmaf(A[0], xl, fmaf(A[1], yl, fmaf(A[2], zl, A[3])));
+					const float Y = py + fmaf(A[4], xl, fmaf(A[5], yl, fmaf(A[6], zl, A[7])));
+					const float Z = pz + fmaf(A[8], xl, fmaf(A[9], yl, fmaf(A[10], zl, A[11])));
+					bool fast = true;
+					if (checked) {
+						fast = (X >= xlo) && (X < xhi) && (Y >= ylo) && (Y < yhi) && (Z >= zlo) && (Z < zhi);
+						if (!fast) {
+							// TricubicBspline::compute validity, src/oc_cubic_bspline.cpp:356-361 (NaN fails too)
+							const bool ok = (X >= 1.f) && (Y >= 1.f) && (Z >= 1.f) && (X < xmax) && (Y < ymax) && (Z < zmax);
+							if (!ok) {
+								invalid = 1;
+								return;
+							}
+						}
+					}
+					const float xf = floorf(X), yf = floorf(Y), zf = floorf(Z);
+					float bx[4], by[4], bz[4];
+					bspline_basis_fast(X - xf, bx);
+					bspline_basis_fast(Y - yf, by);
+					bspline_basis_fast(Z - zf, bz);
+					float t;
+					if (fast) t = tricubic_taps<false>(tbase + ((int)zf * TXY + (int)yf * TX + (int)xf), TX, TXY, bx, by, bz);
+					else t = tricubic_taps<true>(coef + ((size_t)((int)zf - 1) * dy + ((int)yf - 1)) * dx + ((int)xf - 1), dx, dx * dy, bx, by, bz);
+					accumulate(t, c4, xl, yl, zl);
+				};
+#if ICGN3D_PAIRS
+				// Two y-adjacent samples (ii, j, k) and (ii, j + 1, k), support known to be inside the tile: packed pairs, lanes {.x, .y}
+				auto sample_pair = [&](int ii, int j, int k) {
+					const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
+					const float4 ca = __ldg(img.rg + o), cb = __ldg(img.rg + o + dx);
+					const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
+					const float2 yl2 = make_float2(yl, yl + 1.f), xl2 = bcast2(xl);
+					const float2 X2 = fadd2(bcast2(px), ffma2(bcast2(A[0]), xl2, ffma2(bcast2(A[1]), yl2, bcast2(fmaf(A[2], zl, A[3])))));
+					const float2 Y2 = fadd2(bcast2(py), ffma2(bcast2(A[4]), xl2, ffma2(bcast2(A[5]), yl2, bcast2(fmaf(A[6], zl, A[7])))));
+					const float2 Z2 = fadd2(bcast2(pz), ffma2(bcast2(A[8]), xl2, ffma2(bcast2(A[9]), yl2, bcast2(fmaf(A[10], zl, A[11])))));
+					const float2 xf = make_float2(floorf(X2.x), floorf(X2.y)), yf = make_float2(floorf(Y2.x), floorf(Y2.y)), zf = make_float2(floorf(Z2.x), floorf(Z2.y));
+					float2 BX[4], BY[4], BZ[4];
+					bspline_basis_fast2(fsub2(X2, xf), BX);
+					bspline_basis_fast2(fsub2(Y2, yf), BY);
+					bspline_basis_fast2(fsub2(Z2, zf), BZ);
+					// block rows jj = 0..4 of the shared 4x5x4 block: the second sample starts one row lower, its y weights are shifted
+					float2 BYs[5];
+					BYs[0] = make_float2(BY[0].x, 0.f);
+#pragma unroll
+					for (int jj = 1; jj < 4; jj++) BYs[jj] = make_float2(BY[jj].x, BY[jj - 1].y);
+					BYs[4] = make_float2(0.f, BY[3].y);
+					const float* base = tbase + ((int)zf.x * TXY + (int)yf.x * TX + (int)xf.x);
+					float2 val = make_float2(0.f, 0.f);
+#pragma unroll
+					for (int i = 0; i < 4; i++) {
+						float2 ys = make_float2(0.f, 0.f);
+#pragma unroll
+						for (int jj = 0; jj < 5; jj++) {
+							const float* row = base + i * TXY + jj * TX;
+							float2 rs = fmul2(bcast2(row[0]), BX[0]);
+							rs = ffma2(bcast2(row[1]), BX[1], rs);
+							rs = ffma2(bcast2(row[2]), BX[2], rs);
+							rs = ffma2(bcast2(row[3]), BX[3], rs);
+							ys = ffma2(rs, BYs[jj], ys);
+						}
+						val = ffma2(ys, BZ[i], val);
+					}
+					// the second sample normally sits one block row below the first in the same columns and planes; where the
+					// warp's shear or stretch breaks that (a few lanes per POI) it is evaluated on its own
+					if (xf.y != xf.x || zf.y != zf.x || yf.y != yf.x + 1.f) {
+						const float bx1[4] = { BX[0].y, BX[1].y, BX[2].y, BX[3].y }, by1[4] = { BY[0].y, BY[1].y, BY[2].y, BY[3].y };
+						const float bz1[4] = { BZ[0].y, BZ[1].y, BZ[2].y, BZ[3].y };
+						val.y = tricubic_taps<false>(tbase + ((int)zf.y * TXY + (int)yf.y * TX + (int)xf.y), TX, TXY, bx1, by1, bz1);
+					}
+					accumulate(val.x, ca, xl, yl, zl);
+					accumulate(val.y, cb, xl, yl + 1.f, zl);
+				};
+				// Can every sample of this slab take the unchecked path (valid, support inside the tile)?  The affine warp maps
+				// the slab's box of local coordinates to a parallelepiped: centre +- half extents per axis.
+				bool slab_fast;
+				{
+					const float zh = 0.5f * (float)(nz - 1), zc = zl0 + zh, fx = (float)rx, fy = (float)ry, eps = 2e-3f;
+					const float cx = px + fmaf(A[2], zc, A[3]), ex = fabsf(A[0]) * fx + fabsf(A[1]) * fy + fabsf(A[2]) * zh + eps;
+					const float cy = py + fmaf(A[6], zc, A[7]), ey = fabsf(A[4]) * fx + fabsf(A[5]) * fy + fabsf(A[6]) * zh + eps;
+					const float cz = pz + fmaf(A[10], zc, A[11]), ez = fabsf(A[8]) * fx + fabsf(A[9]) * fy + fabsf(A[10]) * zh + eps;
+					slab_fast = (cx - ex >= xlo) && (cx + ex < xhi) && (cy - ey >= ylo) && (cy + ey < yhi) && (cz - ez >= zlo) && (cz + ez < zhi); // false for NaN
+				}
+#else
+				const bool slab_fast = false;
+#endif
 				// Lanes run along x within ONE row (y, z) per warp: consecutive tile addresses, no bank
 				// conflicts (a linear index over 33-wide rows straddles two rows and conflicts 2-way);
 				// columns >= 32 form a short tail with lanes over rows.
 				const int nrows = nz * sy;
-				for (int row = warp; row < nrows; row += ICGN3D_WARPS) {
-					const int il = fdiv3(row, inv_sy), j = row - il * sy;
-					if (lane < ncol) sample(zs + il, j, lane);
+#if ICGN3D_PAIRS
+				if (slab_fast) {
+					const int npy = (sy + 1) >> 1; // row pairs per layer; the last one is a single row when sy is odd
+					const float inv_npy = 1.0f / (float)npy;
+					for (int u = warp; u < nz * npy; u += ICGN3D_WARPS) {
+						const int il = fdiv3(u, inv_npy), j = 2 * (u - il * npy);
+						if (lane < ncol) {
+							if (j + 1 < sy) sample_pair(zs + il, j, lane);
+							else sample(zs + il, j, lane, false);
+						}
+					}
+				} else
+#endif
+				{
+					for (int row = warp; row < nrows; row += ICGN3D_WARPS) {
+						const int il = fdiv3(row, inv_sy), j = row - il * sy;
+						if (lane < ncol) sample(zs + il, j, lane, true);
+					}
 				}
 				for (int i = tid; i < nrows * rem; i += ICGN3D_THREADS) {
 					const int row = fdiv3(i, inv_rem), k = 32 + (i - row * rem);
 					const int il = fdiv3(row, inv_sy), j = row - il * sy;
-					sample(zs + il, j, k);
+					sample(zs + il, j, k, true);
 				}
 			}
 			// the reference rejects the POI when any interpolated value is < 0 (src/oc_icgn.cpp:1378-1390)

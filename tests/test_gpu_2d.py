@@ -135,7 +135,7 @@ def test_icgn2d1_config_a(engine, cfg_a, exact):
 
 def test_icgn2d1_golden_table(engine):
     """FFTCC2D -> ICGN2D1 on the reference's example pair: all 30 000 POIs of examples/test_2d_dic_fftcc_icgn1.cpp:50-66 against
-    the oracle (every sentinel code identical -- the specimen has a black hole, so the `sample < 0` rule fires), and the
+    the oracle (every sentinel code identical; the POIs inside the specimen's hole end with -4), and the
     committed rows of the shipped result table as known answers."""
     ref, tar = util.oht_cfrp_pair()
     g = util.oht_cfrp_golden()
@@ -159,7 +159,7 @@ def test_icgn2d1_golden_table(engine):
     icgn.prepare()
     icgn.compute(q)
     o.icgn2d1(qc, 16, 16, 0.001, 10)
-    assert (qc[:, 16] == -3).sum() > 100 and (qc[:, 16] == -4).sum() > 100
+    assert (qc[:, 16] == -4).sum() > 100  # the POIs inside the specimen's hole do not converge
     stats = util.compare_2d(q, qc, "oht_cfrp, all 30 000 POIs", max_iter_mismatch_frac=0.02)  # asserts identical sentinel codes
     assert stats["n_compared"] > 0.9 * len(q)
     # known answers: the shipped table (it predates the -4 code: converged rows only)
@@ -573,5 +573,6 @@ def test_two_operators_with_different_pairs_interleaved(engine):
     assert np.array_equal(qa, want_a) and np.array_equal(qb, want_b)
     f = ob.FFTCC2D(16, 16, engine=engine)
     f.set_images(ref_a, tar_a)
+    qb = seed_b.copy()
     b.compute(qb)  # and again after a third object took the engine
     assert np.array_equal(qb, want_b)
