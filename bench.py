@@ -7,15 +7,21 @@
 A step = one pass of the hot path (FFT-CC initial guess + IC-GN to convergence, prepare() included)
 over one batch of synthetic POIs.  At N=1 the default workload is BASELINE.json configs[1]
 ("2D DIC 2048x2048 synthetic speckle, 50k POIs, 33x33 subset, FFTCC->ICGN2D1").  For N>1 every rank
-works on its own 50k-POI shard of a denser grid on the same image pair (weak scaling, no data-path
-collective); the image pair is broadcast from rank 0 over NCCL and the records are gathered to rank 0
-inside the e2e leg.
+works on its own 50k-POI shard of a denser grid on the same image pair (weak scaling; the path shards over
+independent POIs, so there is NO data-path collective: every rank moves its own host buffers over its own
+PCIe link).
 
   value  : whole-job POIs/s with images and the pristine POI queue resident in HBM
            (sum over ranks of POIs / max-over-ranks device time, CUDA events, L2 flushed between steps)
-  e2e    : same metric through the host-buffer C-ABI calls (pinned host memory): image H2D (+ NCCL
-           broadcast), prepare, POI H2D, kernels, (gather,) POI D2H inside the timed region
+  e2e    : same metric through the host-buffer C-ABI calls (pinned host memory), per rank: image H2D,
+           prepare, POI H2D, kernels, POI D2H inside the timed region; max over ranks
   e2e_u8_images: the e2e step with the pair handed over as 8-bit arrays (what the image files hold), N=1 only
+  e2e_shim: the same step through the C++ shim (examples/shim_bench.cpp: the reference's class API, the caller's pageable
+           Image2D / std::vector<POI2D>), rank 0 only, 2D configs
+  capi_multi: ONE process driving all N devices through a GROUP context of the C ABI (ocb_create_multi): the weak
+           workload as one queue of N x 50k POIs, and BASELINE.json's strong-scaling configs E (4096^2, 500k POIs) and D
+           (256^3, 20k POIs) sharded over the N devices, each with host buffers (e2e); rank 0 only, the other ranks idle
+  cold_start: a fresh process's ocb_create() and first calls (rank 0, N=1 only)
   roofline: dominant kernel (IC-GN) algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS hbm_gbs; `traffic` and
            `binding_resources_ncu` (issue-slot / FMA / shared-memory pipe utilisation) come from the committed ncu capture
   cpu_baseline: the oracle port of the reference (oracle/, g++ -O3 -fopenmp, nproc-1 threads like
@@ -92,59 +98,211 @@ def workload_name(cfg_name, cfg):
         cfg_name, cfg["size"][0], cfg["size"][1], cfg["size"][2], cfg["n_poi"], 2 * cfg["r"] + 1)
 
 
+def common_config(cfg_name, cfg, n_gpus):
+    """The `config` object of the JSON line: identical in the GPU arm and the reference (CPU) arm."""
+    return {"workload": workload_name(cfg_name, cfg), "pois_per_gpu": cfg["n_poi"], "conv": cfg["conv"], "stop": cfg["stop"],
+            "parallelism": "GPU arm: POI shards over %d rank(s), one per GPU, no data-path collective; CPU arm: OpenMP threads of one host" % n_gpus,
+            "l2": "GPU arm: flushed between timed steps (256 MiB write), timing = sum of per-step CUDA-event intervals; CPU arm: not applicable"}
+
+
 # ---------------------------------------------------------------------------------------------------
+def cpu_model():
+    """CPU model string and logical core count of this host (BASELINE.md section 3 asks for both)."""
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return model, os.cpu_count()
+
+
+def pin_openmp():
+    """Thread placement of the CPU arm: one thread per core, neighbours first.  Must be in the environment before the
+    OpenMP runtime of the oracle library starts (it is loaded lazily, after this call)."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_DYNAMIC", "false")
+
+
+def time_cpu_path(cfg, ref, tar, pts, n_sample, repeats, threads):
+    """The oracle port on `n_sample` evenly spaced POIs of the workload: ONE oracle object (image tables built once, like one
+    set of reference DIC objects), `repeats` timed passes of FFT-CC + IC-GN after one untimed pass; the whole-workload time is
+    prepare() once + per-POI stages scaled from the sample to all POIs.  Returns a dict with best-of-N and mean."""
+    from oracle.oracle import Oracle2D, Oracle3D
+    from opencorr_b200 import make_poi2d, make_poi3d
+    kind, r, n = cfg["kind"], cfg["r"], cfg["n_poi"]
+    sel = np.linspace(0, n - 1, n_sample).astype(np.int64)
+    scale = n / float(n_sample)
+    o = (Oracle2D if kind == "2d" else Oracle3D)(ref, tar, threads)
+    t0 = time.perf_counter()
+    o.prepare()
+    t_prepare = time.perf_counter() - t0
+    passes, q = [], None
+    for rep in range(repeats + 1):
+        q = make_poi2d(pts[sel]) if kind == "2d" else make_poi3d(pts[sel])
+        t0 = time.perf_counter()
+        if kind == "2d":
+            o.fftcc2d(q, r, r)
+            t1 = time.perf_counter()
+            (o.icgn2d1 if cfg["order"] == 1 else o.icgn2d2)(q, r, r, cfg["conv"], cfg["stop"])
+        else:
+            o.fftcc3d(q, r, r, r)
+            t1 = time.perf_counter()
+            o.icgn3d1(q, r, r, r, cfg["conv"], cfg["stop"])
+        t2 = time.perf_counter()
+        if rep > 0:  # pass 0 warms caches / the OpenMP pool
+            passes.append((t1 - t0, t2 - t1))
+    whole = [t_prepare + scale * (a + b) for a, b in passes]
+    best, mean = min(whole), sum(whole) / len(whole)
+    model, ncpu = cpu_model()
+    return {
+        "value_best": n / best, "value_mean": n / mean, "ms_best": 1e3 * best, "ms_mean": 1e3 * mean, "passes": len(passes),
+        "fftcc_s_best": min(a for a, _ in passes), "icgn_s_best": min(b for _, b in passes), "prepare_s": t_prepare,
+        "n_sample": int(n_sample), "scale": scale, "threads": threads, "cpu_model": model, "logical_cpus": ncpu,
+        "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES")}, "queue": q, "sel": sel,
+    }
+
+
 def run_reference(args):
     """CPU arm: the oracle port of the reference on the host cores, all threads it would use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle.oracle import Oracle2D, Oracle3D, max_threads
-    from opencorr_b200 import make_poi2d, make_poi3d
+    pin_openmp()
+    from oracle.oracle import max_threads
     cfg, ref, tar, pts = make_workload(args.config, 0, 1)
     threads = max(1, max_threads() - 1)  # omp_get_num_procs() - 1, reference examples/test_2d_dic_fftcc_icgn1.cpp:40-41
-    r = cfg["r"]
     n_sample = min(cfg["n_poi"], args.cpu_sample if args.cpu_sample > 0 else (cfg["n_poi"] if cfg["kind"] == "2d" else 400))
-    sel = np.linspace(0, cfg["n_poi"] - 1, n_sample).astype(np.int64)
-    times = []
-    scale = cfg["n_poi"] / float(n_sample)
-    for step in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        if cfg["kind"] == "2d":
-            q = make_poi2d(pts[sel])
-            o = Oracle2D(ref, tar, threads)
-            o.fftcc2d(q, r, r)
-            t1 = time.perf_counter()
-            o.prepare()
-            t2 = time.perf_counter()
-            (o.icgn2d1 if cfg["order"] == 1 else o.icgn2d2)(q, r, r, cfg["conv"], cfg["stop"])
-        else:
-            q = make_poi3d(pts[sel])
-            o = Oracle3D(ref, tar, threads)
-            o.fftcc3d(q, r, r, r)
-            t1 = time.perf_counter()
-            o.prepare()
-            t2 = time.perf_counter()
-            o.icgn3d1(q, r, r, r, cfg["conv"], cfg["stop"])
-        t3 = time.perf_counter()
-        # whole-workload time: prepare() once + per-POI stages scaled from the sample to all POIs
-        dt = (t2 - t1) + scale * ((t1 - t0) + (t3 - t2))
-        if step >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    value = cfg["n_poi"] / (ms * 1e-3)
-    sample = "%d of %d POIs of the workload per step (evenly spaced); prepare() once + per-POI stages x %.1f; mean of %d steps" % (
-        n_sample, cfg["n_poi"], scale, len(times))
+    c = time_cpu_path(cfg, ref, tar, pts, n_sample, max(1, args.steps), threads)
+    ms = c["ms_best"]
+    value = c["value_best"]
+    sample = ("%d of %d POIs of the workload per pass (evenly spaced); one oracle object, prepare() once (%.3f s) + per-POI stages x %.1f; "
+              "best of %d passes after 1 warm-up pass (mean %.0f POI/s); %s, %d logical CPUs, %d OpenMP threads, OMP_PROC_BIND=%s OMP_PLACES=%s"
+              % (n_sample, cfg["n_poi"], c["prepare_s"], c["scale"], c["passes"], c["value_mean"], c["cpu_model"], c["logical_cpus"], threads,
+                 c["omp"]["OMP_PROC_BIND"], c["omp"]["OMP_PLACES"]))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.config, cfg), "reference_impl": "oracle port (oracle/oc_oracle.cpp); the reference itself needs Eigen/FFTW/OpenCV, absent here"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        # the same keys as the GPU arm's config
+        "config": common_config(args.config, cfg, args.gpus),
+        "reference_impl": "oracle port (oracle/oc_oracle.cpp); the reference itself needs Eigen/FFTW/OpenCV, absent here",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "value_mean": c["value_mean"],
+                         "cpu_model": c["cpu_model"], "logical_cpus": c["logical_cpus"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def write_pgm(path, img):
+    a = np.ascontiguousarray(img).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (a.shape[1], a.shape[0]))
+        f.write(a.tobytes())
+
+
+def shim_e2e(cfg, ref, tar, steps, warmup, env_extra=None):
+    """The step through the C++ shim (examples/shim_bench.cpp): the reference's class API on the caller's pageable memory."""
+    binp = os.path.join(ROOT, "examples", "bin", "shim_bench")
+    if cfg["kind"] != "2d" or not os.path.exists(binp) or float(np.abs(ref - np.round(ref)).max()) != 0.0:
+        return None
+    import tempfile
+    d = tempfile.mkdtemp(prefix="ocb_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        write_pgm(os.path.join(d, "ref.pgm"), ref)
+        write_pgm(os.path.join(d, "tar.pgm"), tar)
+        x0, y0, nx, ny, sx, sy = cfg["grid"]
+        cmd = [binp, os.path.join(d, "ref.pgm"), os.path.join(d, "tar.pgm")] + [str(v) for v in (x0, y0, nx, ny, sx, sy, cfg["r"], cfg["order"],
+                                                                                    cfg["conv"], cfg["stop"], steps, warmup)]
+        env = dict(os.environ)
+        env.update(env_extra or {})
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        if out.returncode != 0:
+            return {"error": (out.stderr or out.stdout).strip()[-300:]}
+        rec = json.loads(out.stdout.strip().splitlines()[-1])
+        ms = rec["ms"]
+        mean = sum(ms) / len(ms)
+        return {"value": rec["n_poi"] / (mean * 1e-3), "unit": UNIT, "ms_per_step": mean, "ms_min": min(ms), "n_poi": rec["n_poi"],
+                "converged": rec["converged"], "first_step_incl_start_up_ms": rec["first_step_incl_start_up_ms"],
+                "memory": "pageable (Image2D pixels, std::vector<POI2D>)", "devices": (env_extra or {}).get("OPENCORR_B200_DEVICES", "1"),
+                "step": "FFTCC2D::compute + ICGN2D%d::prepare + compute on one pair (prepare() re-uploads the pair)" % cfg["order"]}
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def cold_start_record():
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cold_start_probe.py")], capture_output=True, text=True, timeout=300)
+        rec = json.loads(out.stdout.strip().splitlines()[-1])
+        rec["note"] = ("fresh process, C ABI; measured while this bench process keeps the GPU initialised (a first-ever process on an idle GPU "
+                       "without persistence mode pays the driver's GPU initialisation on top)")
+        return rec
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
+def group_e2e(ob, torch, devices, cfg_name, weak_ranks, steps, warmup, render_device):
+    """One process, len(devices) GPUs, through a GROUP context of the C ABI (ocb_create_multi): host buffers in, host buffers
+    out, the queue sharded inside the library.  weak_ranks > 0: the weak-scaling workload as ONE queue (the grids of that many
+    ranks); 0: the config's own queue (strong scaling)."""
+    cfg, ref, tar, pts = make_workload(cfg_name, 0, 1, device=render_device)
+    if weak_ranks > 1:
+        pts = np.concatenate([make_points(cfg_name, k) for k in range(weak_ranks)])
+    kind, r = cfg["kind"], cfg["r"]
+    n = len(pts)
+    eng = ob.Engine(devices if len(devices) > 1 else devices[0])
+    q0 = ob.make_poi2d(pts) if kind == "2d" else ob.make_poi3d(pts)
+    h_ref, h_tar = torch.from_numpy(ref).pin_memory(), torch.from_numpy(tar).pin_memory()
+    h_q0, h_q = torch.from_numpy(q0).pin_memory(), torch.empty((n, q0.shape[1]), dtype=torch.float32).pin_memory()
+
+    def step():
+        qn = h_q.numpy()
+        if kind == "2d":
+            eng._ck(eng._lib.ocb_set_images_2d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[1], ref.shape[0], 0))
+            eng.fftcc2d(qn, r, r)
+            eng.icgn2d_prepare()
+            (eng.icgn2d1 if cfg["order"] == 1 else eng.icgn2d2)(qn, r, r, cfg["conv"], cfg["stop"])
+        else:
+            eng._ck(eng._lib.ocb_set_images_3d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[2], ref.shape[1], ref.shape[0]))
+            eng.fftcc3d(qn, r, r, r)
+            eng.icgn3d_prepare()
+            eng.icgn3d1(qn, r, r, r, cfg["conv"], cfg["stop"])
+
+    ts = []
+    gc.collect()
+    gc.disable()
+    try:
+        for i in range(warmup + steps):
+            np.copyto(h_q.numpy(), h_q0.numpy())
+            t0 = time.perf_counter()
+            step()  # blocking like the reference's compute(): every member has synchronised when it returns
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    finally:
+        gc.enable()
+    res = h_q.numpy()
+    zc = 16 if kind == "2d" else 18
+    ms = 1e3 * sum(ts) / len(ts)
+    eng.close()
+    return {"workload": workload_name(cfg_name, dict(cfg, n_poi=n)), "devices": len(devices), "n_poi": n, "value": n / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "ms_min": 1e3 * min(ts), "converged_frac": float((res[:, zc] >= 0).mean()),
+            "h2d_bytes_per_step": int(len(devices) * (ref.nbytes + tar.nbytes) + 2 * q0.nbytes), "d2h_bytes_per_step": int(2 * q0.nbytes),
+            "scaling": "weak" if weak_ranks else "strong"}
+
+
+def make_points(cfg_name, rank):
+    from opencorr_b200 import synth
+    cfg = synth.CONFIGS[cfg_name]
+    g = list(cfg["grid"])
+    g[0] += rank
+    return synth.grid_2d(*g) if cfg["kind"] == "2d" else synth.grid_3d(*g)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -229,9 +387,11 @@ def run_ours(args):
         return 2
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    idle_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        idle_group = dist.new_group(backend="gloo")  # CPU-side barrier for the phases in which only rank 0 works
     if args.gpus != world and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE=%d" % (args.gpus, world), file=sys.stderr)
 
@@ -317,17 +477,17 @@ def run_ours(args):
     hist = np.bincount(res[good, ic].astype(np.int64), minlength=int(cfg["stop"]) + 1).tolist()
 
     # ---------------- end-to-end leg ("e2e"): host buffers through the C ABI ----------------
+    # Every rank is a caller with ITS OWN host buffers (pinned): the pair, its POI queue.  No collective: the path shards over
+    # independent POIs, each GPU moves its data over its own PCIe link.
     h_ref = torch.from_numpy(ref).pin_memory()
     h_tar = torch.from_numpy(tar).pin_memory()
     h_q0 = torch.from_numpy(q0).pin_memory()
     h_q = torch.empty_like(h_q0).pin_memory()
     h_q0_np = h_q0.numpy()
     n_total = world * n
-    h_all = torch.empty((n_total, floats), dtype=torch.float32).pin_memory() if (world > 1 and rank == 0) else None
     img_bytes = ref.nbytes + tar.nbytes
     poi_bytes = q0.nbytes
     eng.use_own_stream()
-
     phases = []  # per-step host-side phase times (ms): set_images, (unused), FFTCC call, ICGN call
 
     def reset_queue():
@@ -337,49 +497,25 @@ def run_ours(args):
         np.copyto(h_q.numpy(), h_q0_np)
 
     def step_e2e():
-        if world == 1:
-            # exactly what a caller of the reference API does: setImages, FFTCC compute, prepare, ICGN compute
-            if kind == "2d":
-                t = [time.perf_counter()]
-                eng._ck(eng._lib.ocb_set_images_2d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[1], ref.shape[0], 0))
-                t.append(time.perf_counter())
-                qn = h_q.numpy()
-                t.append(time.perf_counter())
-                eng.fftcc2d(qn, r, r)
-                t.append(time.perf_counter())
-                eng.icgn2d_prepare()
-                (eng.icgn2d1 if cfg["order"] == 1 else eng.icgn2d2)(qn, r, r, cfg["conv"], cfg["stop"])
-                t.append(time.perf_counter())
-                phases.append([1e3 * (b - a) for a, b in zip(t[:-1], t[1:])])
-            else:
-                eng._ck(eng._lib.ocb_set_images_3d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[2], ref.shape[1], ref.shape[0]))
-                qn = h_q.numpy()
-                eng.fftcc3d(qn, r, r, r)
-                eng.icgn3d_prepare()
-                eng.icgn3d1(qn, r, r, r, cfg["conv"], cfg["stop"])
-            return
-        # N > 1: rank 0 uploads the pair, NCCL broadcast, every rank uploads its POI shard, computes,
-        # records are gathered to rank 0 on the device and downloaded there
-        eng.set_stream(stream.cuda_stream)
-        if rank == 0:
-            d_ref.copy_(h_ref, non_blocking=True)
-            d_tar.copy_(h_tar, non_blocking=True)
-        obd.broadcast_images(d_ref, d_tar, src=0)
-        d_q.copy_(h_q0, non_blocking=True)
+        # exactly what a caller of the reference API does: setImages, FFTCC compute, prepare, ICGN compute
         if kind == "2d":
-            eng.set_images_2d_dev(d_ref.data_ptr(), d_tar.data_ptr(), ref.shape[1], ref.shape[0])
-            eng.fftcc2d_dev(d_q.data_ptr(), n, r, r)
+            t = [time.perf_counter()]
+            eng._ck(eng._lib.ocb_set_images_2d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[1], ref.shape[0], 0))
+            t.append(time.perf_counter())
+            qn = h_q.numpy()
+            t.append(time.perf_counter())
+            eng.fftcc2d(qn, r, r)
+            t.append(time.perf_counter())
             eng.icgn2d_prepare()
-            (eng.icgn2d1_dev if cfg["order"] == 1 else eng.icgn2d2_dev)(d_q.data_ptr(), n, r, r, cfg["conv"], cfg["stop"])
+            (eng.icgn2d1 if cfg["order"] == 1 else eng.icgn2d2)(qn, r, r, cfg["conv"], cfg["stop"])
+            t.append(time.perf_counter())
+            phases.append([1e3 * (b - a) for a, b in zip(t[:-1], t[1:])])
         else:
-            eng.set_images_3d_dev(d_ref.data_ptr(), d_tar.data_ptr(), ref.shape[2], ref.shape[1], ref.shape[0])
-            eng.fftcc3d_dev(d_q.data_ptr(), n, r, r, r)
+            eng._ck(eng._lib.ocb_set_images_3d(eng._ctx, h_ref.data_ptr(), h_tar.data_ptr(), ref.shape[2], ref.shape[1], ref.shape[0]))
+            qn = h_q.numpy()
+            eng.fftcc3d(qn, r, r, r)
             eng.icgn3d_prepare()
-            eng.icgn3d1_dev(d_q.data_ptr(), n, r, r, r, cfg["conv"], cfg["stop"])
-        allq = obd.gather_pois(d_q, n_total, dst=0)
-        if rank == 0:
-            h_all.copy_(allq, non_blocking=True)
-        torch.cuda.synchronize(dev)
+            eng.icgn3d1(qn, r, r, r, cfg["conv"], cfg["stop"])
 
     # warm-up: at least `warmup` steps AND ~0.2 s of wall clock -- on the pool's boxes one host-side stall of 60-80 ms
     # (seen inside a plain pinned-memory memcpy, i.e. not in this library) follows the pinned allocations above by
@@ -387,8 +523,7 @@ def run_ours(args):
     # (count derived from the all-reduced resident step time, so every rank runs the same number of steps)
     n_w = int(min(100, max(3, args.warmup, math.ceil(200.0 / max(ms_per_step, 1e-3)))))
     for _ in range(n_w):
-        if world == 1:
-            reset_queue()
+        reset_queue()
         step_e2e()
     barrier()
     # a generation-2 pass of Python's cyclic GC over the ~1e6 objects torch leaves on the heap takes 60-80 ms and used
@@ -397,8 +532,7 @@ def run_ours(args):
     gc.disable()
     e2e_times = []
     for _ in range(args.steps):
-        if world == 1:
-            reset_queue()
+        reset_queue()
         barrier()
         t0 = time.perf_counter()
         step_e2e()
@@ -417,10 +551,7 @@ def run_ours(args):
         ph = phases[-len(e2e_times):]
         e2e_spread["phases_ms_of_slowest_step[set_images,-,fftcc,icgn]"] = ph[int(np.argmax(e2e_times))]
         e2e_spread["phases_ms_median"] = [float(np.median([p[i] for p in ph])) for i in range(4)]
-    if world == 1:
-        h2d, d2h = img_bytes + 2 * poi_bytes, 2 * poi_bytes
-    else:
-        h2d, d2h = img_bytes + world * poi_bytes, world * poi_bytes
+    h2d, d2h = world * (img_bytes + 2 * poi_bytes), world * 2 * poi_bytes  # whole job: every rank copies its own pair and queue
 
     # same end-to-end step with the images handed over as 8-bit arrays (what an image file holds; the
     # reference converts them to float on the host, src/oc_image.cpp:39,56): extra information, N=1 only
@@ -487,35 +618,21 @@ def run_ours(args):
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.oracle import Oracle2D, Oracle3D, max_threads
+        pin_openmp()
+        from oracle.oracle import max_threads
         threads = max(1, max_threads() - 1)
         n_sample = n if kind == "2d" else min(n, 300)
-        sel = np.linspace(0, n - 1, n_sample).astype(np.int64)
-        t0 = time.perf_counter()
-        if kind == "2d":
-            qc = ob.make_poi2d(pts[sel])
-            o = Oracle2D(ref, tar, threads)
-            o.fftcc2d(qc, r, r)
-            t1 = time.perf_counter()
-            o.prepare()
-            t2 = time.perf_counter()
-            (o.icgn2d1 if cfg["order"] == 1 else o.icgn2d2)(qc, r, r, cfg["conv"], cfg["stop"])
-        else:
-            qc = ob.make_poi3d(pts[sel])
-            o = Oracle3D(ref, tar, threads)
-            o.fftcc3d(qc, r, r, r)
-            t1 = time.perf_counter()
-            o.prepare()
-            t2 = time.perf_counter()
-            o.icgn3d1(qc, r, r, r, cfg["conv"], cfg["stop"])
-        t3 = time.perf_counter()
+        c = time_cpu_path(cfg, ref, tar, pts, n_sample, 2, threads)
+        qc, sel = c["queue"], c["sel"]
         # prepare() is paid once per image pair; the per-POI stages scale with the POI count, so the
         # whole-workload time is prepare + (fftcc + icgn) * n / n_sample
-        scale = n / float(n_sample)
-        cpu = {"value": n / ((t2 - t1) + scale * ((t1 - t0) + (t3 - t2))), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d of %d POIs, one pass; fftcc %.3fs + prepare %.3fs + icgn %.3fs; value = whole workload extrapolated "
-                         "(prepare once, per-POI stages x %.1f)" % (n_sample, n, t1 - t0, t2 - t1, t3 - t2, scale),
-               "value_compute_only": n_sample / ((t1 - t0) + (t3 - t2))}
+        cpu = {"value": c["value_best"], "unit": UNIT, "cores": threads, "kind": "port", "value_mean": c["value_mean"],
+               "cpu_model": c["cpu_model"], "logical_cpus": c["logical_cpus"],
+               "sample": "%d of %d POIs per pass, one oracle object; best of %d passes after 1 warm-up pass: fftcc %.3fs + prepare %.3fs + icgn %.3fs; "
+                         "value = whole workload extrapolated (prepare once, per-POI stages x %.1f); OMP_PROC_BIND=%s OMP_PLACES=%s"
+                         % (n_sample, n, c["passes"], c["fftcc_s_best"], c["prepare_s"], c["icgn_s_best"], c["scale"], c["omp"]["OMP_PROC_BIND"],
+                            c["omp"]["OMP_PLACES"]),
+               "value_compute_only": n_sample / (c["fftcc_s_best"] + c["icgn_s_best"])}
         # parity of the benchmarked run against the oracle on the sample (reported, not asserted)
         same = (res[sel, ic] == qc[:, ic]) & (res[sel, zc] >= 0) & (qc[:, zc] >= 0)
         cols = [2, 8] if kind == "2d" else [3, 7, 11]
@@ -524,19 +641,47 @@ def run_ours(args):
                                     "max_abs_disp": float(np.abs(res[sel][same][:, cols] - qc[same][:, cols]).max()),
                                     "max_abs_zncc": float(np.abs(res[sel][same, zc] - qc[same, zc]).max())}
 
+    # ---------------- rank 0 only: the shim, the group context, a cold start (the other ranks wait on the CPU) ----------------
+    e2e_shim, capi_multi, cold = None, None, None
+    torch.cuda.synchronize(dev)
+    if rank == 0 and not args.no_extras:
+        sub_steps = max(3, min(args.steps, 5))
+        if world == 1:
+            e2e_shim = shim_e2e(cfg, ref, tar, sub_steps, 2, {"OPENCORR_B200_DEVICE": str(local_rank)})
+            cold = cold_start_record()
+        capi_multi = {"note": "one process, %d device(s), GROUP context of the C ABI (ocb_create_multi); host buffers (pinned) in and out; "
+                              "wall clock around the blocking calls" % world}
+        if torch.cuda.device_count() >= world:
+            devices = list(range(world))
+            try:
+                if world > 1:
+                    capi_multi["weak_%s" % args.config] = group_e2e(ob, torch, devices, args.config, world, sub_steps, 2, dev)
+                    if kind == "2d":
+                        capi_multi["shim_weak_%s_pageable" % args.config] = shim_e2e(cfg, ref, tar, sub_steps, 2, {"OPENCORR_B200_DEVICES": ",".join(map(str, devices))})
+                for name in ("E", "D"):
+                    if name != args.config or world > 1:
+                        capi_multi["strong_%s" % name] = group_e2e(ob, torch, devices, name, 0, sub_steps, 2, dev)
+            except Exception as e:  # noqa: BLE001
+                capi_multi["error"] = str(e)[:300]
+        else:
+            capi_multi["skipped"] = "only %d of %d devices visible to rank 0" % (torch.cuda.device_count(), world)
+    if idle_group is not None:
+        dist.barrier(group=idle_group)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args.config, cfg), "pois_per_gpu": n, "conv": cfg["conv"], "stop": cfg["stop"],
-                       "parallelism": "POI shards, %d rank(s), no data-path collective" % world,
-                       "l2": "flushed between timed steps (256 MiB write); timing = sum of per-step CUDA-event intervals",
-                       "wall_s_timed_region_incl_flush": wall},
+            "config": common_config(args.config, cfg, world),
+            "wall_s_timed_region_incl_flush": wall,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                     "ms_per_step_spread_rank0": e2e_spread},
             "e2e_u8_images": e2e_u8,
+            "e2e_shim": e2e_shim,
+            "capi_multi": capi_multi,
+            "cold_start": cold,
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -560,6 +705,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="POIs per step for --impl reference (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rank-0 extras (e2e_shim, capi_multi, cold_start)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

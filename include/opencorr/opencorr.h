@@ -217,11 +217,77 @@ namespace opencorr
 
 	// ------------------------------------------------------------------ src/oc_image.h
 	// Row-major float matrix standing in for the reference's Eigen::MatrixXf member `eg_mat`.
+	namespace b200
+	{
+		// Page-locked memory from the engine's device context, or nullptr without a usable GPU (defined with Engine below).
+		// The first call waits for the context that warmEngineAsync() started.
+		inline void* pinnedAlloc(size_t bytes);
+
+		// Pixel storage of Image2D / Image3D: page-locked host memory (ocb_host_alloc) when a CUDA device is present, so that
+		// every upload of the image runs as asynchronous DMA at the PCIe rate instead of being staged through the driver's
+		// bounce buffers (about 5x slower for a 2048 x 2048 pair); ordinary memory on a machine without a GPU (loading and
+		// saving images must work there).  Zero-initialised like the reference's containers.
+		class PixelBuffer
+		{
+			float* p = nullptr;
+			size_t n = 0;
+			bool pinned = false;
+
+		public:
+			PixelBuffer() = default;
+			PixelBuffer(const PixelBuffer& o) { *this = o; }
+			PixelBuffer& operator=(const PixelBuffer& o)
+			{
+				if (this != &o) {
+					assign(o.n, 0.f);
+					if (o.n) std::memcpy(p, o.p, o.n * sizeof(float));
+				}
+				return *this;
+			}
+			~PixelBuffer() { release(); }
+			static float* allocate(size_t count, bool& pinned_out)
+			{
+				float* q = count ? (float*)pinnedAlloc(count * sizeof(float)) : nullptr;
+				pinned_out = q != nullptr;
+				if (!q && count) q = (float*)std::malloc(count * sizeof(float));
+				if (!q && count) throw std::string("opencorr_b200: out of host memory");
+				return q;
+			}
+			static void deallocate(float* q, bool was_pinned)
+			{
+				if (!q) return;
+				if (was_pinned) ocb_host_free(q);
+				else std::free(q);
+			}
+			void release()
+			{
+				deallocate(p, pinned);
+				p = nullptr;
+				n = 0;
+			}
+			void assign(size_t count, float value)
+			{
+				if (count != n) {
+					release();
+					p = allocate(count, pinned);
+					n = count;
+				}
+				if (value == 0.f) { if (n) std::memset(p, 0, n * sizeof(float)); }
+				else std::fill(p, p + n, value);
+			}
+			float* data() { return p; }
+			const float* data() const { return p; }
+			size_t size() const { return n; }
+			float& operator[](size_t i) { return p[i]; }
+			float operator[](size_t i) const { return p[i]; }
+		};
+	} // namespace b200
+
 	class MatrixXf
 	{
 	public:
 		int n_rows = 0, n_cols = 0;
-		std::vector<float> data; // row-major [rows][cols]
+		b200::PixelBuffer data; // row-major [rows][cols]
 		inline void resize(int rows, int cols) { n_rows = rows; n_cols = cols; data.assign((size_t)rows * cols, 0.f); }
 		inline float& operator()(int r, int c) { return data[(size_t)r * n_cols + c]; }
 		inline float operator()(int r, int c) const { return data[(size_t)r * n_cols + c]; }
@@ -429,6 +495,7 @@ namespace opencorr
 		std::string file_path;
 		float*** vol_mat = nullptr; // [z][y][x]; payload is one contiguous block at vol_mat[0][0] (src/oc_array.h:56-74)
 		unsigned long long generation = 0;
+		bool payload_pinned = false;
 
 		inline Image3D(int dim_x, int dim_y, int dim_z)
 		{
@@ -447,7 +514,8 @@ namespace opencorr
 			release();
 			dim_x = dx; dim_y = dy; dim_z = dz;
 			size = (unsigned long)dz * dy * dx;
-			float* p1 = (float*)calloc(size, sizeof(float));
+			float* p1 = b200::PixelBuffer::allocate(size, payload_pinned); // page-locked when a GPU is present (see PixelBuffer)
+			std::memset(p1, 0, size * sizeof(float));
 			float** p2 = (float**)malloc((size_t)dz * dy * sizeof(float*));
 			vol_mat = (float***)malloc((size_t)dz * sizeof(float**));
 			for (int i = 0; i < dz; i++) {
@@ -490,7 +558,7 @@ namespace opencorr
 		inline void release()
 		{
 			if (vol_mat != nullptr) {
-				free(vol_mat[0][0]);
+				b200::PixelBuffer::deallocate(vol_mat[0][0], payload_pinned);
 				free(vol_mat[0]);
 				free(vol_mat);
 				vol_mat = nullptr;
@@ -603,6 +671,17 @@ namespace opencorr
 			}
 		};
 		inline void warmEngineAsync() { Engine::get().warm(); }
+		inline void* pinnedAlloc(size_t bytes)
+		{
+			Engine& e = Engine::get();
+			std::lock_guard<std::mutex> g(e.lock);
+			e.startWarm();
+			try {
+				return ocb_host_alloc_on(e.context(), bytes);
+			} catch (const std::string&) {
+				return nullptr; // no GPU here: images live in ordinary memory (loading / saving still works)
+			}
+		}
 
 		// What an object with a prepare() step remembers: the reference keeps per-object tables, so objects prepared on
 		// different pairs can be used in any order.  Here the device holds ONE pair at a time; an object whose pair has been

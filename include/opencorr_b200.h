@@ -80,6 +80,11 @@ void ocb_destroy(ocb_ctx* ctx);
  * every entry point accepts pageable memory.  The range must stay allocated until it is unregistered. */
 int ocb_host_register(void* host, size_t bytes);
 int ocb_host_unregister(void* host);
+/* Page-locked host memory for buffers the caller allocates anew (the shim's Image2D / Image3D keep their pixels in it).
+ * ocb_host_alloc returns NULL when there is no usable CUDA device (callers then use ordinary memory). */
+void* ocb_host_alloc(size_t bytes);
+void* ocb_host_alloc_on(ocb_ctx* ctx, size_t bytes); /* same, after making ctx's (first) device current: no stray context on device 0 */
+void ocb_host_free(void* host);
 /* Last error message of this context (or of the process when ctx == NULL). Never NULL. */
 const char* ocb_last_error(const ocb_ctx* ctx);
 /* Enqueue on an external cudaStream_t (e.g. PyTorch's current stream).  The handle is used as given:

@@ -29,6 +29,9 @@ SIGNATURES = {
     "ocb_member": (_vp, [_vp, _i]),
     "ocb_host_register": (_i, [_vp, _sz]),
     "ocb_host_unregister": (_i, [_vp]),
+    "ocb_host_alloc": (_vp, [_sz]),
+    "ocb_host_alloc_on": (_vp, [_vp, _sz]),
+    "ocb_host_free": (None, [_vp]),
     "ocb_destroy": (None, [_vp]),
     "ocb_last_error": (ctypes.c_char_p, [_vp]),
     "ocb_set_stream": (_i, [_vp, _vp]),

@@ -11,21 +11,42 @@
 //   inverse: DIT FFT along kx (bit-reversed in -> natural out), transpose back, DIT along ky;
 //   first-maximum argmax over registers + warp shuffle reduction.
 // No CTA barrier, no integer division, ~2.6k warp instructions per POI (the generic kernel: ~23k).
+//
+// Window loads: when the POI and its guess sit on whole pixels (the normal FFT-CC case: grid POIs, integer guess) and the
+// image pitch allows it, the two 32x32 windows arrive by TMA -- one cp.async.bulk.tensor.2d box of 36 x 32 floats each
+// (x origin rounded down to 16 bytes), straight into the shared tiles the transposes use afterwards, completion on a
+// per-warp mbarrier -- and every lane then picks its column out of shared memory.  Otherwise the lanes gather their
+// columns with coalesced global loads (the reference's float-coordinate truncation, src/oc_fftcc.cpp:204-219, evaluated
+// per pixel).  Both paths deliver the same 2 x 1024 values.
+#include <stdlib.h>
+#include <string.h>
+
 #include "fft32.cuh"
 #include "ocb_kernels.h"
+#include "ocb_tma.cuh"
 
 namespace ocb {
 
 constexpr int FFTW32_WARPS = 4;
 constexpr int FFTW32_PITCH = 33;
+constexpr int FFTW32_BOX_W = 36;                 // TMA box: 32 columns + up to 3 of alignment slack
+constexpr int FFTW32_TILE = 32 * FFTW32_BOX_W;   // floats per tile: holds a TMA box (36 x 32) or a transpose tile (32 x 33)
 
-__global__ void __launch_bounds__(FFTW32_WARPS * 32) fftcc2d_w32_kernel(Image2D img, float* __restrict__ pois, int n_poi) {
-	__shared__ float s_re[FFTW32_WARPS][32 * FFTW32_PITCH];
-	__shared__ float s_im[FFTW32_WARPS][32 * FFTW32_PITCH];
+__global__ void __launch_bounds__(FFTW32_WARPS * 32) fftcc2d_w32_kernel(Image2D img, float* __restrict__ pois, int n_poi,
+	const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_tar, int use_tma) {
+	__shared__ __align__(128) float s_re[FFTW32_WARPS][FFTW32_TILE];
+	__shared__ __align__(128) float s_im[FFTW32_WARPS][FFTW32_TILE];
+	__shared__ __align__(8) uint64_t s_bar[FFTW32_WARPS];
 	constexpr int R = 16, NW = 32, M = NW * NW;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	float* sre = s_re[warp];
 	float* sim = s_im[warp];
+	uint64_t* bar = &s_bar[warp];
+	uint32_t bar_phase = 0;
+	if (use_tma) {
+		if (lane == 0) mbar_init(bar, 1);
+		__syncwarp();
+	}
 	const int w = img.w, h = img.h;
 	const int plane = (32 - lane) & 31;
 
@@ -41,16 +62,39 @@ __global__ void __launch_bounds__(FFTW32_WARPS * 32) fftcc2d_w32_kernel(Image2D 
 		// gather: lane = column; float coordinate arithmetic then (int) truncation (src/oc_fftcc.cpp:204-219)
 		float re[32], im[32];
 		{
-			const float rpx = px + lane - R;
-			const int ax = (int)rpx, bx = (int)(rpx + u0);
 			float sa = 0.f, sb = 0.f;
+			// whole-pixel POI and guess (warp-uniform): every truncation below is the identity, the windows are two boxes
+			if (use_tma && px == floorf(px) && py == floorf(py) && u0 == floorf(u0) && v0 == floorf(v0)) {
+				const int x0r = (int)px - R, y0r = (int)py - R, x0t = (int)(px + u0) - R, y0t = (int)(py + v0) - R;
+				const int axr = floor4(x0r), axt = floor4(x0t);
+				if (lane == 0) {
+					fence_proxy_async(); // the previous POI's generic-proxy accesses to the tiles come first
+					mbar_expect_tx(bar, (uint32_t)(2 * FFTW32_TILE * sizeof(float)));
+					tma_load_2d(sre, &tm_ref, axr, y0r, bar);
+					tma_load_2d(sim, &tm_tar, axt, y0t, bar);
+				}
+				mbar_wait(bar, bar_phase);
+				bar_phase ^= 1;
+				const float* cr = sre + (x0r - axr) + lane;
+				const float* ci = sim + (x0t - axt) + lane;
 #pragma unroll
-			for (int r = 0; r < 32; r++) {
-				const float rpy = py + r - R;
-				re[r] = __ldg(img.ref + (size_t)(int)rpy * w + ax);
-				im[r] = __ldg(img.tar + (size_t)(int)(rpy + v0) * w + bx);
-				sa += re[r];
-				sb += im[r];
+				for (int r = 0; r < 32; r++) {
+					re[r] = cr[r * FFTW32_BOX_W];
+					im[r] = ci[r * FFTW32_BOX_W];
+					sa += re[r];
+					sb += im[r];
+				}
+			} else {
+				const float rpx = px + lane - R;
+				const int ax = (int)rpx, bx = (int)(rpx + u0);
+#pragma unroll
+				for (int r = 0; r < 32; r++) {
+					const float rpy = py + r - R;
+					re[r] = __ldg(img.ref + (size_t)(int)rpy * w + ax);
+					im[r] = __ldg(img.tar + (size_t)(int)(rpy + v0) * w + bx);
+					sa += re[r];
+					sb += im[r];
+				}
 			}
 			sa = warp_sum(sa) / (float)M;
 			sb = warp_sum(sb) / (float)M;
@@ -152,7 +196,12 @@ int fftcc2d_w32_launch(const Image2D& img, float* d_pois, size_t n, int sm_count
 	long long grid = (long long)sm_count * 16;
 	if (grid > blocks_needed) grid = blocks_needed;
 	if (grid < 1) grid = 1;
-	fftcc2d_w32_kernel<<<(int)grid, FFTW32_WARPS * 32, 0, stream>>>(img, d_pois, (int)n);
+	CUtensorMap tm_ref, tm_tar;
+	memset(&tm_ref, 0, sizeof(tm_ref));
+	memset(&tm_tar, 0, sizeof(tm_tar));
+	const int dims[2] = { img.w, img.h }, box[2] = { FFTW32_BOX_W, 32 };
+	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm_ref, img.ref, 2, dims, box) && tma_make_map(&tm_tar, img.tar, 2, dims, box);
+	fftcc2d_w32_kernel<<<(int)grid, FFTW32_WARPS * 32, 0, stream>>>(img, d_pois, (int)n, tm_ref, tm_tar, use_tma);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;
 }

@@ -393,7 +393,86 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 		{
 			const int xg = x0 + lane;
 			const bool gx_ok = lane_on && xg >= 2 && xg < w - 2; // gradient maps are zero on a 2-pixel border (src/oc_gradient.cpp:42,46)
-			for (int r = r_lo; r < r_hi; r++) {
+			int r_first = r_lo;
+#if ICGN2D_PAIRS
+			if (lane_on) {
+				// rows (r, r + 1) in lanes {.x, .y} of packed pairs: the same operations as the one-row loop below (the gradients keep
+				// the reference's separately rounded products and sums), and the six pixels of this lane's column that the two y
+				// gradients need are fetched once
+				float2 r1p = make_float2(0.f, 0.f), r2p = r1p;
+				float2 accH2[3][D2 + 1], accS2[2][DEG + 1], accR2[2][DEG + 1];
+#pragma unroll
+				for (int a = 0; a < 3; a++)
+#pragma unroll
+					for (int qq = 0; qq <= D2; qq++) accH2[a][qq] = r1p;
+#pragma unroll
+				for (int a = 0; a < 2; a++)
+#pragma unroll
+					for (int qq = 0; qq <= DEG; qq++) { accS2[a][qq] = r1p; accR2[a][qq] = r1p; }
+				const float2 f1 = bcast2(1.f / 12.f), f2 = bcast2(2.f / 3.f);
+				const int npair = (r_hi - r_lo) >> 1;
+#pragma unroll 2
+				for (int pr = 0; pr < npair; pr++) {
+					const int r = r_lo + 2 * pr;
+					const int yg = y0 + r;
+					const float* q = T + (r + 2) * RW + lane + 2 + ex;
+					const float v0 = q[-2 * RW], v1 = q[-RW], v2 = q[0], v3 = q[RW], v4 = q[2 * RW], v5 = q[3 * RW];
+					const float2 yl2 = make_float2((float)(r - ry) - oy, (float)(r + 1 - ry) - oy);
+					const float2 Rraw = make_float2(v2, v3);
+					const float2 R2 = fsub2(Rraw, bcast2(c0));
+					// grad4: ((0 - f(+2)/12) + f(+1)*2/3) - f(-1)*2/3 + f(-2)/12, every operation rounded separately (src/oc_gradient.cpp:49-54)
+					float2 gx2 = fsub2(bcast2(0.f), fmul2(make_float2(q[2], q[RW + 2]), f1));
+					gx2 = fadd2(gx2, fmul2(make_float2(q[1], q[RW + 1]), f2));
+					gx2 = fsub2(gx2, fmul2(make_float2(q[-1], q[RW - 1]), f2));
+					gx2 = fadd2(gx2, fmul2(make_float2(q[-2], q[RW - 2]), f1));
+					float2 gy2 = fsub2(bcast2(0.f), fmul2(make_float2(v4, v5), f1));
+					gy2 = fadd2(gy2, fmul2(make_float2(v3, v4), f2));
+					gy2 = fsub2(gy2, fmul2(make_float2(v1, v2), f2));
+					gy2 = fadd2(gy2, fmul2(make_float2(v0, v1), f1));
+					if (!gx_ok) gx2 = make_float2(0.f, 0.f);
+					if (!(yg >= 2 && yg < h - 2)) gy2.x = 0.f;
+					if (!(yg + 1 >= 2 && yg + 1 < h - 2)) gy2.y = 0.f;
+					float* pc = sC + 3 * (r * sw + lane);
+					pc[0] = v2; pc[1] = gx2.x; pc[2] = gy2.x;
+					pc[3 * sw] = v3; pc[3 * sw + 1] = gx2.y; pc[3 * sw + 2] = gy2.y;
+					r1p = fadd2(r1p, R2);
+					r2p = ffma2(R2, R2, r2p);
+					float2 g[3] = { fmul2(gx2, gx2), fmul2(gx2, gy2), fmul2(gy2, gy2) };
+#pragma unroll
+					for (int a = 0; a < 3; a++) {
+						float2 t = g[a];
+#pragma unroll
+						for (int qq = 0; qq <= D2; qq++) {
+							accH2[a][qq] = fadd2(accH2[a][qq], t);
+							if (qq < D2) t = fmul2(t, yl2);
+						}
+					}
+					float2 g1[2] = { gx2, gy2 };
+#pragma unroll
+					for (int a = 0; a < 2; a++) {
+						float2 t = g1[a], tr = fmul2(g1[a], R2);
+#pragma unroll
+						for (int qq = 0; qq <= DEG; qq++) {
+							accS2[a][qq] = fadd2(accS2[a][qq], t);
+							accR2[a][qq] = fadd2(accR2[a][qq], tr);
+							if (qq < DEG) { t = fmul2(t, yl2); tr = fmul2(tr, yl2); }
+						}
+					}
+				}
+				r1 = r1p.x + r1p.y;
+				r2 = r2p.x + r2p.y;
+#pragma unroll
+				for (int a = 0; a < 3; a++)
+#pragma unroll
+					for (int qq = 0; qq <= D2; qq++) accH[a][qq] = accH2[a][qq].x + accH2[a][qq].y;
+#pragma unroll
+				for (int a = 0; a < 2; a++)
+#pragma unroll
+					for (int qq = 0; qq <= DEG; qq++) { accS[a][qq] = accS2[a][qq].x + accS2[a][qq].y; accR[a][qq] = accR2[a][qq].x + accR2[a][qq].y; }
+				r_first = r_lo + 2 * npair;
+			}
+#endif
+			for (int r = r_first; r < r_hi; r++) {
 				const int yg = y0 + r;
 				const bool gy_ok = yg >= 2 && yg < h - 2;
 				const float yl = (float)(r - ry) - oy;
@@ -706,24 +785,31 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 						}
 						const float xfa = floorf(X2.x), xfb = floorf(X2.y), yfa = floorf(Y2.x), yfb = floorf(Y2.y);
 						const float2 tx = fsub2(X2, make_float2(xfa, xfb)), ty = fsub2(Y2, make_float2(yfa, yfb));
-						// weights of both rows: WX[j] = {w_j(tx.x), w_j(tx.y)}; in y the rows of the shared 4x5 block are j = 0..4 and row
-						// r + 1 starts one block row lower: WY[j] = {w_j(ty.x), w_{j-1}(ty.y)} (a missing weight is an exact 0)
-						float2 WX[4], WYu[4], WY[5];
+						// weights of both rows: WX[j] = {w_j(tx.x), w_j(tx.y)}, WYu[j] likewise in y.  The rows of the shared 4x5 block
+						// are j = 0..4 and row r + 1 starts one block row lower: block rows 1..3 serve both samples (packed, y weights
+						// {w_j(ty.x), w_{j-1}(ty.y)}), row 0 only the first and row 4 only the second (scalar on that half of the pair)
+						float2 WX[4], WYu[4], WY[3];
 #pragma unroll
 						for (int j = 0; j < 4; j++) {
 							WX[j] = ffma2(ffma2(ffma2(bcast2(BA[j]), tx, bcast2(BB[j])), tx, bcast2(BC_[j])), tx, bcast2(BE[j]));
 							WYu[j] = ffma2(ffma2(ffma2(bcast2(BA[j]), ty, bcast2(BB[j])), ty, bcast2(BC_[j])), ty, bcast2(BE[j]));
 						}
-						WY[0] = make_float2(WYu[0].x, 0.f);
 #pragma unroll
-						for (int j = 1; j < 4; j++) WY[j] = make_float2(WYu[j].x, WYu[j - 1].y);
-						WY[4] = make_float2(0.f, WYu[3].y);
+						for (int j = 1; j < 4; j++) WY[j - 1] = make_float2(WYu[j].x, WYu[j - 1].y);
 						const float* q = tbase + (int)yfa * TW + (int)xfa;
-						float2 t2 = make_float2(0.f, 0.f);
+						float2 t2;
+						{
+							const float row = fmaf(q[3], WX[3].x, fmaf(q[2], WX[2].x, fmaf(q[1], WX[1].x, q[0] * WX[0].x)));
+							t2 = make_float2(fmaf(row, WYu[0].x, 0.f), 0.f);
+						}
 #pragma unroll
-						for (int j = 0; j < 5; j++) {
+						for (int j = 1; j < 4; j++) {
 							const float2 row = ffma2(bcast2(q[j * TW + 3]), WX[3], ffma2(bcast2(q[j * TW + 2]), WX[2], ffma2(bcast2(q[j * TW + 1]), WX[1], fmul2(bcast2(q[j * TW]), WX[0]))));
-							t2 = ffma2(row, WY[j], t2);
+							t2 = ffma2(row, WY[j - 1], t2);
+						}
+						{
+							const float row = fmaf(q[4 * TW + 3], WX[3].y, fmaf(q[4 * TW + 2], WX[2].y, fmaf(q[4 * TW + 1], WX[1].y, q[4 * TW] * WX[0].y)));
+							t2.y = fmaf(row, WYu[3].y, t2.y);
 						}
 						// row r + 1 normally sits one block row below row r in the same columns; where the warp's shear or stretch
 						// breaks that (a few lanes per POI), its sample is evaluated on its own

@@ -278,10 +278,18 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 			float acc[NSETUP];
 #pragma unroll
 			for (int k = 0; k < NSETUP; k++) acc[k] = 0.f;
+			// the loop body carries 104 accumulators, so the compiler keeps a single load in flight: fetch the next sample's
+			// constants one trip ahead (L2 latency, nothing in L1), or every trip waits for its own load
+			auto sample_offset = [&](int i) {
+				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
+				return goff + ((size_t)ii * dy + j) * dx + k;
+			};
+			float4 c_next = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (tid < N) c_next = __ldg(img.rg + sample_offset(tid));
 			for (int i = tid; i < N; i += ICGN3D_THREADS) {
 				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
-				const size_t o = goff + ((size_t)ii * dy + j) * dx + k;
-				const float4 c4 = __ldg(img.rg + o);
+				const float4 c4 = c_next;
+				if (i + ICGN3D_THREADS < N) c_next = __ldg(img.rg + sample_offset(i + ICGN3D_THREADS));
 				const float R = c4.x - c0;
 				const float gx = c4.y, gy = c4.z, gz = c4.w;
 				const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
@@ -440,25 +448,42 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 					bspline_basis_fast2(fsub2(X2, xf), BX);
 					bspline_basis_fast2(fsub2(Y2, yf), BY);
 					bspline_basis_fast2(fsub2(Z2, zf), BZ);
-					// block rows jj = 0..4 of the shared 4x5x4 block: the second sample starts one row lower, its y weights are shifted
-					float2 BYs[5];
-					BYs[0] = make_float2(BY[0].x, 0.f);
+					// block rows jj = 0..4 of the shared 4x5x4 block: the second sample starts one row lower.  Rows 1..3 serve both
+					// samples (packed, y weights {by_a[jj], by_b[jj-1]}); row 0 serves only the first and row 4 only the second
+					// (scalar on that half of the pair): no multiply is spent on a padded zero weight, and each sample still sees
+					// its four rows in the order of the one-sample path
+					float2 BYs[3];
 #pragma unroll
-					for (int jj = 1; jj < 4; jj++) BYs[jj] = make_float2(BY[jj].x, BY[jj - 1].y);
-					BYs[4] = make_float2(0.f, BY[3].y);
+					for (int jj = 1; jj < 4; jj++) BYs[jj - 1] = make_float2(BY[jj].x, BY[jj - 1].y);
 					const float* base = tbase + ((int)zf.x * TXY + (int)yf.x * TX + (int)xf.x);
 					float2 val = make_float2(0.f, 0.f);
 #pragma unroll
 					for (int i = 0; i < 4; i++) {
-						float2 ys = make_float2(0.f, 0.f);
+						float2 ys;
+						{
+							const float* row = base + i * TXY;
+							float rs = row[0] * BX[0].x;
+							rs = fmaf(row[1], BX[1].x, rs);
+							rs = fmaf(row[2], BX[2].x, rs);
+							rs = fmaf(row[3], BX[3].x, rs);
+							ys = make_float2(fmaf(rs, BY[0].x, 0.f), 0.f);
+						}
 #pragma unroll
-						for (int jj = 0; jj < 5; jj++) {
+						for (int jj = 1; jj < 4; jj++) {
 							const float* row = base + i * TXY + jj * TX;
 							float2 rs = fmul2(bcast2(row[0]), BX[0]);
 							rs = ffma2(bcast2(row[1]), BX[1], rs);
 							rs = ffma2(bcast2(row[2]), BX[2], rs);
 							rs = ffma2(bcast2(row[3]), BX[3], rs);
-							ys = ffma2(rs, BYs[jj], ys);
+							ys = ffma2(rs, BYs[jj - 1], ys);
+						}
+						{
+							const float* row = base + i * TXY + 4 * TX;
+							float rs = row[0] * BX[0].y;
+							rs = fmaf(row[1], BX[1].y, rs);
+							rs = fmaf(row[2], BX[2].y, rs);
+							rs = fmaf(row[3], BX[3].y, rs);
+							ys.y = fmaf(rs, BY[3].y, ys.y);
 						}
 						val = ffma2(ys, BZ[i], val);
 					}

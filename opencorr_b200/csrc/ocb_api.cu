@@ -396,6 +396,33 @@ ocb_ctx* ocb_member(ocb_ctx* ctx, int index) {
 	return (index >= 0 && index < (int)ctx->members.size()) ? ctx->members[index] : nullptr;
 }
 
+void* ocb_host_alloc_on(ocb_ctx* ctx, size_t bytes) {
+	if (ctx) {
+		const ocb_ctx* c = is_group(ctx) ? ctx->members[0] : ctx;
+		if (cudaSetDevice(c->device) != cudaSuccess) {
+			cudaGetLastError();
+			return nullptr;
+		}
+	}
+	return ocb_host_alloc(bytes);
+}
+
+void* ocb_host_alloc(size_t bytes) {
+	if (!bytes) return nullptr;
+	void* p = nullptr;
+	cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		set_error(nullptr, OCB_ERR_CUDA, "cudaHostAlloc failed: %s", cudaGetErrorString(e));
+		return nullptr;
+	}
+	return p;
+}
+
+void ocb_host_free(void* host) {
+	if (host) cudaFreeHost(host);
+}
+
 int ocb_host_register(void* host, size_t bytes) {
 	if (!host || !bytes) return set_error(nullptr, OCB_ERR_ARG, "host_register: bad arguments");
 	cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterPortable);

@@ -215,3 +215,40 @@ def test_reference_stereo_strain_example_runs_unchanged(tmp_path):
     good = check & np.all(q[:, 5:8] >= 0.9, axis=1)
     d = np.abs(tab[good][:, 20:26] - gold[good]).max(1)
     assert np.median(d) < 2e-5 and d.max() < 1e-3
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "test_dvc_fftcc_icgn1")), reason="example binary not built")
+def test_reference_dvc_example_runs_unchanged(tmp_path):
+    """examples/test_dvc_fftcc_icgn1.cpp of the reference (north_star's second acceptance program: FFTCC3D -> ICGN3D1 with 61^3
+    subvolumes on al_foam4_{0,1}.bin, 7 x 7 x 117 POIs), compiled unchanged against the shim.  The example hard-codes
+    d:/dic_tests/dvc/al_foam4_{0,1}.bin (100 x 100 x 706 voxels); the committed fixture holds z-slices [18, 118) of that pair,
+    so the volumes are rebuilt at full size with the remaining slices zero.  The POIs at z = 60..75 (the first four layers of
+    the grid, 196 POIs) see only fixture data -- their 61^3 subvolumes, the 60^3 FFT-CC windows and the 15-tap prefilter stay
+    inside [23, 112] -- and must reproduce the rows of the table the reference ships
+    (examples/dvc/al_foam4_1_fftcc_icgn1_r30.csv); the other POIs reach into the zero padding and only have to come back."""
+    ref, tar, z0, cpu_tab, _ = util.al_foam_crop()
+    data = tmp_path / "d:" / "dic_tests" / "dvc"
+    data.mkdir(parents=True)
+    for name, crop in (("al_foam4_0.bin", ref), ("al_foam4_1.bin", tar)):
+        vol = np.zeros((706, 100, 100), np.float32)
+        vol[z0:z0 + crop.shape[0]] = crop
+        with open(data / name, "wb") as f:
+            np.array([100, 100, 706], np.int32).tofile(f)  # dim_x, dim_y, dim_z header, src/oc_image.cpp:76-110
+            vol.tofile(f)
+    out = subprocess.run([os.path.join(BIN, "test_dvc_fftcc_icgn1")], cwd=tmp_path, stdin=subprocess.DEVNULL,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "5733 POIs" in out.stdout
+    header, tab = _read_table(data / "al_foam4_1_fftcc_icgn1_r30.csv")
+    assert header[:12] == ["x", "y", "z", "u", "v", "w", "u0", "v0", "w0", "ZNCC", "iteration", "convergence"]
+    assert tab.shape[0] == 5733
+    mine = tab[:196]  # the grid runs z-slowest: the first 4 x 49 rows are z = 60, 65, 70, 75
+    assert np.array_equal(mine[:, 0:3], cpu_tab[:, 0:3])
+    assert np.array_equal(mine[:, 6:9], cpu_tab[:, 6:9]), "FFT-CC guess differs from the shipped table"
+    same_it = mine[:, 10] == cpu_tab[:, 10]
+    assert same_it.mean() > 0.97
+    # the shipped CPU table carries the float32 summation noise of the reference's sequential sums (61^3 samples):
+    # ~3e-5 px / 2e-5 ZNCC away from exact arithmetic (DESIGN.md section 2); the GPU sums are trees
+    assert np.abs(mine[same_it][:, 3:6] - cpu_tab[same_it][:, 3:6]).max() < 1e-4
+    assert np.abs(mine[same_it, 9] - cpu_tab[same_it, 9]).max() < 5e-5
+    assert (data / "al_foam4_1_fftcc_icgn1_r30_time.csv").exists()
