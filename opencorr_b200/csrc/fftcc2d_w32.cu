@@ -177,15 +177,17 @@ __global__ void __launch_bounds__(FFTW32_WARPS * 32) fftcc2d_w32_kernel(Image2D 
 			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
 			if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
 		}
-		if (lane == 0) {
+		{ // one store instruction for the five result fields (the queue may sit in page-locked host memory)
 			int du = bi & 31, dv = bi >> 5;
 			if (du > R) du -= NW;
 			if (dv > R) dv -= NW;
-			P[P2_DEF + D2_U] = (float)du + u0;
-			P[P2_DEF + D2_V] = (float)dv + v0;
-			P[P2_U0] = u0;
-			P[P2_V0] = v0;
-			P[P2_ZNCC] = bv / (sqrtf(na * nb) * (float)M); // src/oc_fftcc.cpp:274
+			float out = 0.f;
+			if (lane == P2_DEF + D2_U) out = (float)du + u0;
+			if (lane == P2_DEF + D2_V) out = (float)dv + v0;
+			if (lane == P2_U0) out = u0;
+			if (lane == P2_V0) out = v0;
+			if (lane == P2_ZNCC) out = bv / (sqrtf(na * nb) * (float)M); // src/oc_fftcc.cpp:274
+			if (lane == P2_DEF + D2_U || lane == P2_DEF + D2_V || lane == P2_U0 || lane == P2_V0 || lane == P2_ZNCC) P[lane] = out;
 		}
 		__syncwarp();
 	}

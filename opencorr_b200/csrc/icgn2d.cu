@@ -1083,33 +1083,39 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 			continue;
 		}
 		// ---------------- results, src/oc_icgn.cpp:310-340 / :859-897 ----------------
-		if (threadIdx.x == 0) {
+		// Every lane holds the same final state; the record goes out as ONE coalesced store, lane k writing float k (fields the
+		// reference leaves alone keep the value read at the start) -- the queue may live in page-locked host memory, where
+		// separate 4-byte stores would each cross PCIe on their own.
+		if (threadIdx.x < 32) {
 			float u, v;
+			float out = rec;
+			auto put = [&](int field, float value) { if (lane == field) out = value; };
 			if constexpr (NP == 6) {
 				u = A[2]; v = A[5];
-				P[P2_DEF + D2_U] = u; P[P2_DEF + D2_UX] = A[0] - 1.f; P[P2_DEF + D2_UY] = A[1];
-				P[P2_DEF + D2_V] = v; P[P2_DEF + D2_VX] = A[3]; P[P2_DEF + D2_VY] = A[4] - 1.f;
+				put(P2_DEF + D2_U, u); put(P2_DEF + D2_UX, A[0] - 1.f); put(P2_DEF + D2_UY, A[1]);
+				put(P2_DEF + D2_V, v); put(P2_DEF + D2_VX, A[3]); put(P2_DEF + D2_VY, A[4] - 1.f);
 			} else { // Deformation2D2::setDeformation(), src/oc_deformation.cpp:284-299
 				u = A[5]; v = A[11];
-				P[P2_DEF + D2_U] = u; P[P2_DEF + D2_UX] = A[3] - 1.f; P[P2_DEF + D2_UY] = A[4];
-				P[P2_DEF + D2_UXX] = A[0] * 2.f; P[P2_DEF + D2_UXY] = A[1]; P[P2_DEF + D2_UYY] = A[2] * 2.f;
-				P[P2_DEF + D2_V] = v; P[P2_DEF + D2_VX] = A[9]; P[P2_DEF + D2_VY] = A[10] - 1.f;
-				P[P2_DEF + D2_VXX] = A[6] * 2.f; P[P2_DEF + D2_VXY] = A[7]; P[P2_DEF + D2_VYY] = A[8] * 2.f;
+				put(P2_DEF + D2_U, u); put(P2_DEF + D2_UX, A[3] - 1.f); put(P2_DEF + D2_UY, A[4]);
+				put(P2_DEF + D2_UXX, A[0] * 2.f); put(P2_DEF + D2_UXY, A[1]); put(P2_DEF + D2_UYY, A[2] * 2.f);
+				put(P2_DEF + D2_V, v); put(P2_DEF + D2_VX, A[9]); put(P2_DEF + D2_VY, A[10] - 1.f);
+				put(P2_DEF + D2_VXX, A[6] * 2.f); put(P2_DEF + D2_VXY, A[7]); put(P2_DEF + D2_VYY, A[8] * 2.f);
 			}
-			P[P2_U0] = u_in;
-			P[P2_V0] = v_in;
+			put(P2_U0, u_in);
+			put(P2_V0, v_in);
 			float zout = zncc;
-			P[P2_ITER] = (float)iteration;
-			P[P2_CONV] = dp_norm;
-			P[P2_RX] = (float)rx;
-			P[P2_RY] = (float)ry;
+			put(P2_ITER, (float)iteration);
+			put(P2_CONV, dp_norm);
+			put(P2_RX, (float)rx);
+			put(P2_RY, (float)ry);
 			if (dp_norm >= conv_criterion && (float)iteration >= stop_condition) zout = -4.f;
 			if (is_nan_f(zout) || is_nan_f(u) || is_nan_f(v)) {
-				P[P2_DEF + D2_U] = u_in;
-				P[P2_DEF + D2_V] = v_in;
+				put(P2_DEF + D2_U, u_in);
+				put(P2_DEF + D2_V, v_in);
 				zout = -5.f;
 			}
-			P[P2_ZNCC] = zout;
+			put(P2_ZNCC, zout);
+			if (lane < P2_N) P[lane] = out;
 		}
 		__syncwarp();
 	}

@@ -88,6 +88,8 @@ struct ocb_ctx {
 	// is used.  Host-buffer entry points shard their POI queue over the members; *_dev entry points are refused.
 	std::vector<ocb_ctx*> members;
 	std::vector<ocb_worker*> workers; // workers[i] serves members[i + 1]; member 0 runs on the calling thread
+	bool peer_ok = false;             // group: every member can address every other member's memory (NVLink / NVSwitch)
+	cudaEvent_t ev_idle = nullptr, ev_pushed = nullptr; // member of a group: see group_distribute
 	int device = 0;
 	int sm_count = 0;
 	size_t smem_optin = 0;
@@ -133,6 +135,11 @@ struct ocb_ctx {
 	// streams, so the PCIe transfers of one chunk overlap the kernel of another
 	cudaStream_t pipe[4] = { nullptr, nullptr, nullptr, nullptr };
 	cudaEvent_t pipe_ready = nullptr;
+	// ocb_set_images_2d uploads the pair in OCB_BANDS row bands (ref band, tar band, event) so that the FFT-CC call that follows
+	// can start on the POIs of the first rows while the rest of the pair is still crossing PCIe
+	cudaEvent_t band_done[4] = { nullptr, nullptr, nullptr, nullptr };
+	int band_end[4] = { 0, 0, 0, 0 }; // first row NOT covered once band_done[b] has fired
+	bool bands_fresh = false;         // nothing has been enqueued on `stream` since the banded upload
 	float* d_cand = nullptr; // EpipolarSearch candidate queue
 	size_t d_cand_bytes = 0;
 	void* d_strain_ws = nullptr; // Strain: sort keys / compact neighbour arrays / cub scratch
@@ -203,16 +210,39 @@ static int unstage_pois(ocb_ctx* ctx, void* host, size_t bytes) {
 // hides most of the POI traffic behind the kernels; results do not depend on the split (the POIs are independent).
 // dev_call launches on ctx->stream with ctx->d_counter, both of which are redirected per chunk.
 static const size_t OCB_PIPE_MIN = 16384;
+// Device-visible address of a host queue that is page-locked (cudaHostAlloc / cudaHostRegister / ocb_host_alloc), else NULL.
+static float* mapped_queue(const void* host) {
+	if (getenv("OCB_NO_ZEROCOPY")) return nullptr;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return (a.type == cudaMemoryTypeHost && a.devicePointer) ? (float*)a.devicePointer : nullptr;
+}
+
+static const int OCB_BANDS = 4;
+// fftcc_radius_y > 0: the call is FFT-CC right after a banded image upload -- a chunk only waits for the bands its windows touch
 template <class F>
-static int run_host_queue_2d(ocb_ctx* ctx, void* host, size_t n, F dev_call) {
+static int run_host_queue_2d(ocb_ctx* ctx, void* host, size_t n, F dev_call, bool allow_mapped = false, int fftcc_radius_y = 0) {
 	const size_t rec = OCB_POI2D_FLOATS * sizeof(float);
 	int rc;
+	const bool banded = fftcc_radius_y > 0 && ctx->bands_fresh && ctx->stream == ctx->own_stream;
+	ctx->bands_fresh = false;
+	// A page-locked queue is not copied at all: the kernels read each 100-byte record and write its results straight through
+	// PCIe (one coalesced load, one coalesced store per POI), which also keeps the copy engines free for the image upload.
+	float* const mapped = allow_mapped ? mapped_queue(host) : nullptr; // (only kernels that store a record with one coalesced write)
+	if (mapped && !(banded && n >= OCB_PIPE_MIN)) {
+		if ((rc = dev_call(mapped, n, (size_t)0))) return rc;
+		OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		return OCB_OK;
+	}
 	if (n < OCB_PIPE_MIN || getenv("OCB_NO_PIPELINE")) {
 		if ((rc = stage_pois(ctx, host, n * rec))) return rc;
 		if ((rc = dev_call((float*)ctx->d_poi, n, (size_t)0))) return rc;
 		return unstage_pois(ctx, host, n * rec);
 	}
-	if (n * rec > ctx->d_poi_bytes) {
+	if (!mapped && n * rec > ctx->d_poi_bytes) {
 		if (ctx->d_poi) cudaFree(ctx->d_poi);
 		ctx->d_poi = nullptr;
 		ctx->d_poi_bytes = 0;
@@ -233,9 +263,26 @@ static int run_host_queue_2d(ocb_ctx* ctx, void* host, size_t n, F dev_call) {
 		const size_t a = n * (size_t)c / K, b = n * (size_t)(c + 1) / K;
 		if (b == a) continue;
 		char* h = (char*)host + a * rec;
-		float* d = ctx->d_poi + a * OCB_POI2D_FLOATS;
-		cudaError_t e = cudaStreamWaitEvent(ctx->pipe[c], ctx->pipe_ready, 0);
-		if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, (b - a) * rec, cudaMemcpyHostToDevice, ctx->pipe[c]);
+		float* d = mapped ? mapped + a * OCB_POI2D_FLOATS : ctx->d_poi + a * OCB_POI2D_FLOATS;
+		cudaEvent_t gate = ctx->pipe_ready;
+		if (banded) { // last image row this chunk's windows read: max over its POIs of max(y, y + v0) + r (src/oc_fftcc.cpp:204-219)
+			float ymax = -1e30f;
+			bool finite = true;
+			const float* q = (const float*)h;
+			for (size_t i = 0; i < b - a; i++) {
+				const float y = q[i * OCB_POI2D_FLOATS + 1], v0 = q[i * OCB_POI2D_FLOATS + 2 + 6];
+				const float top = y > y + v0 ? y : y + v0;
+				if (!(top == top) || top > 1e9f) finite = false;
+				ymax = top > ymax ? top : ymax;
+			}
+			if (finite) {
+				const int need = (int)ymax + fftcc_radius_y + 1;
+				for (int k = 0; k < OCB_BANDS; k++)
+					if (ctx->band_end[k] >= need || k == OCB_BANDS - 1) { gate = ctx->band_done[k]; break; }
+			}
+		}
+		cudaError_t e = cudaStreamWaitEvent(ctx->pipe[c], gate, 0);
+		if (e == cudaSuccess && !mapped) e = cudaMemcpyAsync(d, h, (b - a) * rec, cudaMemcpyHostToDevice, ctx->pipe[c]);
 		if (e != cudaSuccess) { rc = set_error(ctx, OCB_ERR_CUDA, "pipelined upload failed: %s", cudaGetErrorString(e)); break; }
 		ctx->stream = ctx->pipe[c];
 		ctx->d_counter = saved_counter + c;
@@ -243,8 +290,10 @@ static int run_host_queue_2d(ocb_ctx* ctx, void* host, size_t n, F dev_call) {
 		ctx->stream = saved_stream;
 		ctx->d_counter = saved_counter;
 		if (rc != OCB_OK) break;
-		e = cudaMemcpyAsync(h, d, (b - a) * rec, cudaMemcpyDeviceToHost, ctx->pipe[c]);
-		if (e != cudaSuccess) rc = set_error(ctx, OCB_ERR_CUDA, "pipelined download failed: %s", cudaGetErrorString(e));
+		if (!mapped) {
+			e = cudaMemcpyAsync(h, d, (b - a) * rec, cudaMemcpyDeviceToHost, ctx->pipe[c]);
+			if (e != cudaSuccess) rc = set_error(ctx, OCB_ERR_CUDA, "pipelined download failed: %s", cudaGetErrorString(e));
+		}
 	}
 	for (int c = 0; c < K; c++) {
 		cudaError_t e = cudaStreamSynchronize(ctx->pipe[c]);
@@ -297,7 +346,10 @@ static int group_shard(ocb_ctx* g, void* queue, size_t n, size_t rec_bytes, size
 		return f(m, (void*)(base + a * rec_bytes), b - a, a);
 	});
 }
-static const size_t OCB_GROUP_MIN_2D = 2048, OCB_GROUP_MIN_3D = 64;
+// Smallest shard worth a device.  2D: a launch that cannot fill the GPU lets two warps share a POI (icgn2d_launch), which splits
+// its sums differently and changes the last bits of the result; shards of >= 8192 POIs take the same one-warp-per-POI path as
+// the undivided queue on one device, so sharded results stay bit-identical.
+static const size_t OCB_GROUP_MIN_2D = 8192, OCB_GROUP_MIN_3D = 64;
 #define OCB_NO_GROUP(ctx, what) \
 	if (is_group(ctx)) return set_error(ctx, OCB_ERR_ARG, what ": device-pointer / stream entry points need a single-device context (ocb_member)")
 
@@ -318,7 +370,98 @@ static ocb_ctx* create_group(const int* devices, int n) {
 		w->th = std::thread([w]() { w->loop(); });
 		g->workers.push_back(w);
 	}
+	// peer access between all members (NVLink through NVSwitch on an HGX board): images are then uploaded once, in slices, and
+	// exchanged between the devices instead of crossing PCIe once per device
+	g->peer_ok = n > 1 && !getenv("OCB_NO_PEER");
+	for (int i = 0; i < n && g->peer_ok; i++) {
+		cudaSetDevice(devices[i]);
+		for (int j = 0; j < n && g->peer_ok; j++) {
+			if (i == j) continue;
+			int can = 0;
+			if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can) { g->peer_ok = false; break; }
+			const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) g->peer_ok = false;
+			cudaGetLastError();
+		}
+	}
+	for (ocb_ctx* m : g->members) {
+		cudaSetDevice(m->device);
+		if (cudaEventCreateWithFlags(&m->ev_idle, cudaEventDisableTiming) != cudaSuccess
+			|| cudaEventCreateWithFlags(&m->ev_pushed, cudaEventDisableTiming) != cudaSuccess)
+			g->peer_ok = false;
+	}
+	cudaGetLastError();
 	return g;
+}
+
+// Image buffers of a single-device context (grow-only)
+static int ensure_buffers_2d(ocb_ctx* ctx, size_t elems) {
+	if (elems > ctx->own2_elems) {
+		cudaFree(ctx->own_ref2);
+		cudaFree(ctx->own_tar2);
+		ctx->own_ref2 = ctx->own_tar2 = nullptr;
+		ctx->own2_elems = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_ref2, elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_tar2, elems * sizeof(float)));
+		ctx->own2_elems = elems;
+	}
+	return OCB_OK;
+}
+static int ensure_buffers_3d(ocb_ctx* ctx, size_t elems) {
+	if (elems > ctx->own3_elems) {
+		cudaFree(ctx->own_ref3);
+		cudaFree(ctx->own_tar3);
+		ctx->own_ref3 = ctx->own_tar3 = nullptr;
+		ctx->own3_elems = 0;
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_ref3, elems * sizeof(float)));
+		OCB_CUDA(ctx, cudaMalloc(&ctx->own_tar3, elems * sizeof(float)));
+		ctx->own3_elems = elems;
+	}
+	return OCB_OK;
+}
+
+// GROUP upload of an image pair (elems floats each) into every member's buffers: member m copies ONLY slice m of both images
+// from the host (its own PCIe link, all members concurrently), then pushes the slice to every other member over NVLink
+// (cudaMemcpyPeerAsync); each member's stream finally waits for everybody's pushes.  Per device the PCIe traffic drops from the
+// whole pair to 1/G of it; the exchange runs at NVLink rate through the switch.  dim: 2 or 3 (which buffers).
+static int group_distribute_pair(ocb_ctx* g, const float* ref, const float* tar, size_t elems, int dim) {
+	const int G = (int)g->members.size();
+	int rc = OCB_OK;
+	for (ocb_ctx* m : g->members) { // buffers first: a peer may push into them as soon as the exchange starts
+		if (ensure_device(m)) return OCB_ERR_CUDA;
+		rc = dim == 2 ? ensure_buffers_2d(m, elems) : ensure_buffers_3d(m, elems);
+		if (rc == OCB_OK && cudaEventRecord(m->ev_idle, m->stream) != cudaSuccess) rc = set_error(m, OCB_ERR_CUDA, "cudaEventRecord failed");
+		if (rc) {
+			g->last_error = m->last_error;
+			return rc;
+		}
+	}
+	const size_t gran = 64; // floats: slices start on 256-byte boundaries
+	rc = group_run(g, G, [=](ocb_ctx* m, int i) {
+		if (ensure_device(m)) return (int)OCB_ERR_CUDA;
+		const size_t a = (elems * (size_t)i / (size_t)G) / gran * gran, b = i + 1 == G ? elems : (elems * (size_t)(i + 1) / (size_t)G) / gran * gran;
+		const size_t len = (b - a) * sizeof(float);
+		float* mine[2] = { dim == 2 ? m->own_ref2 : m->own_ref3, dim == 2 ? m->own_tar2 : m->own_tar3 };
+		const float* src[2] = { ref, tar };
+		if (len) {
+			for (int k = 0; k < 2; k++) OCB_CUDA(m, cudaMemcpyAsync(mine[k] + a, src[k] + a, len, cudaMemcpyHostToDevice, m->stream));
+			for (int jj = 1; jj < G; jj++) { // start with the next neighbour so that the pushes of all members spread over the peers
+				ocb_ctx* peer = g->members[(i + jj) % G];
+				OCB_CUDA(m, cudaStreamWaitEvent(m->stream, peer->ev_idle, 0)); // the peer is done with its old images
+				float* theirs[2] = { dim == 2 ? peer->own_ref2 : peer->own_ref3, dim == 2 ? peer->own_tar2 : peer->own_tar3 };
+				for (int k = 0; k < 2; k++) OCB_CUDA(m, cudaMemcpyPeerAsync(theirs[k] + a, peer->device, mine[k] + a, m->device, len, m->stream));
+			}
+		}
+		OCB_CUDA(m, cudaEventRecord(m->ev_pushed, m->stream));
+		return (int)OCB_OK;
+	});
+	if (rc) return rc;
+	for (ocb_ctx* m : g->members) { // nobody uses the pair before every slice has arrived
+		if (ensure_device(m)) return OCB_ERR_CUDA;
+		for (ocb_ctx* other : g->members)
+			if (other != m && cudaStreamWaitEvent(m->stream, other->ev_pushed, 0) != cudaSuccess) return set_error(g, OCB_ERR_CUDA, "cudaStreamWaitEvent failed");
+	}
+	return OCB_OK;
 }
 
 extern "C" {
@@ -455,7 +598,12 @@ void ocb_destroy(ocb_ctx* ctx) {
 			w->th.join();
 			delete w;
 		}
-		for (ocb_ctx* m : ctx->members) ocb_destroy(m);
+		for (ocb_ctx* m : ctx->members) {
+			cudaSetDevice(m->device);
+			if (m->ev_idle) cudaEventDestroy(m->ev_idle);
+			if (m->ev_pushed) cudaEventDestroy(m->ev_pushed);
+			ocb_destroy(m);
+		}
 		delete ctx;
 		return;
 	}
@@ -477,6 +625,8 @@ void ocb_destroy(ocb_ctx* ctx) {
 	for (int i = 0; i < 4; i++)
 		if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
 	if (ctx->pipe_ready) cudaEventDestroy(ctx->pipe_ready);
+	for (int i = 0; i < 4; i++)
+		if (ctx->band_done[i]) cudaEventDestroy(ctx->band_done[i]);
 	cudaFree(ctx->d_u8);
 	cudaFree(ctx->d_counter);
 	cudaStreamDestroy(ctx->own_stream);
@@ -519,28 +669,47 @@ int ocb_set_images_2d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, 
 	OCB_NO_GROUP(ctx, "set_images_2d_dev");
 	if (!ctx || !d_ref || !d_tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d: bad arguments");
 	ctx->img2 = ocb::Image2D{ d_ref, d_tar, width, height };
+	ctx->bands_fresh = false;
 	ctx->prepared2 = false;
 	ctx->prepared_nr2 = false;
 	return OCB_OK;
 }
 
 int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int width, int height, int col_major) {
-	if (is_group(ctx)) return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_2d(m, ref, tar, width, height, col_major); });
+	if (is_group(ctx)) {
+		if (ctx->peer_ok && !col_major && ref && tar && width >= 5 && height >= 5) {
+			int rc = group_distribute_pair(ctx, ref, tar, (size_t)width * height, 2);
+			if (rc) return rc;
+			for (ocb_ctx* m : ctx->members)
+				if ((rc = ocb_set_images_2d_dev(m, m->own_ref2, m->own_tar2, width, height))) return rc;
+			return OCB_OK;
+		}
+		return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_2d(m, ref, tar, width, height, col_major); });
+	}
 	if (!ctx || !ref || !tar || width < 5 || height < 5) return set_error(ctx, OCB_ERR_ARG, "set_images_2d: bad arguments");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	const size_t elems = (size_t)width * height;
-	if (elems > ctx->own2_elems) {
-		cudaFree(ctx->own_ref2);
-		cudaFree(ctx->own_tar2);
-		ctx->own_ref2 = ctx->own_tar2 = nullptr;
-		ctx->own2_elems = 0;
-		OCB_CUDA(ctx, cudaMalloc(&ctx->own_ref2, elems * sizeof(float)));
-		OCB_CUDA(ctx, cudaMalloc(&ctx->own_tar2, elems * sizeof(float)));
-		ctx->own2_elems = elems;
+	{
+		const int rcb = ensure_buffers_2d(ctx, elems);
+		if (rcb) return rcb;
 	}
+	bool banded = false;
 	if (!col_major) {
-		OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_ref2, ref, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-		OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_tar2, tar, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		if (ctx->stream == ctx->own_stream && elems >= ((size_t)1 << 20) && !getenv("OCB_NO_PIPELINE")) {
+			for (int b = 0; b < OCB_BANDS; b++) {
+				if (!ctx->band_done[b]) OCB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->band_done[b], cudaEventDisableTiming));
+				const size_t r0 = (size_t)height * b / OCB_BANDS, r1 = (size_t)height * (b + 1) / OCB_BANDS;
+				const size_t off = r0 * (size_t)width, len = (r1 - r0) * (size_t)width * sizeof(float);
+				OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_ref2 + off, ref + off, len, cudaMemcpyHostToDevice, ctx->stream));
+				OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_tar2 + off, tar + off, len, cudaMemcpyHostToDevice, ctx->stream));
+				OCB_CUDA(ctx, cudaEventRecord(ctx->band_done[b], ctx->stream));
+				ctx->band_end[b] = (int)r1;
+			}
+			banded = true;
+		} else {
+			OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_ref2, ref, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+			OCB_CUDA(ctx, cudaMemcpyAsync(ctx->own_tar2, tar, elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		}
 	} else {
 		float* tmp = nullptr;
 		OCB_CUDA(ctx, cudaMalloc(&tmp, elems * sizeof(float)));
@@ -555,7 +724,9 @@ int ocb_set_images_2d(ocb_ctx* ctx, const float* ref, const float* tar, int widt
 		OCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		cudaFree(tmp);
 	}
-	return ocb_set_images_2d_dev(ctx, ctx->own_ref2, ctx->own_tar2, width, height);
+	const int rc_dev = ocb_set_images_2d_dev(ctx, ctx->own_ref2, ctx->own_tar2, width, height);
+	ctx->bands_fresh = banded && rc_dev == OCB_OK;
+	return rc_dev;
 }
 
 // upload `elems` bytes twice (ref, tar) and widen into the context-owned float buffers dst_ref/dst_tar
@@ -628,7 +799,16 @@ int ocb_set_images_3d_dev(ocb_ctx* ctx, const float* d_ref, const float* d_tar, 
 }
 
 int ocb_set_images_3d(ocb_ctx* ctx, const float* ref, const float* tar, int dim_x, int dim_y, int dim_z) {
-	if (is_group(ctx)) return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_3d(m, ref, tar, dim_x, dim_y, dim_z); });
+	if (is_group(ctx)) {
+		if (ctx->peer_ok && ref && tar && dim_x >= 15 && dim_y >= 15 && dim_z >= 15) {
+			int rc = group_distribute_pair(ctx, ref, tar, (size_t)dim_x * dim_y * dim_z, 3);
+			if (rc) return rc;
+			for (ocb_ctx* m : ctx->members)
+				if ((rc = ocb_set_images_3d_dev(m, m->own_ref3, m->own_tar3, dim_x, dim_y, dim_z))) return rc;
+			return OCB_OK;
+		}
+		return group_each(ctx, [=](ocb_ctx* m) { return ocb_set_images_3d(m, ref, tar, dim_x, dim_y, dim_z); });
+	}
 	if (!ctx || !ref || !tar || dim_x < 15 || dim_y < 15 || dim_z < 15)
 		return set_error(ctx, OCB_ERR_ARG, "set_images_3d: bad arguments (each dimension must be >= 15)");
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
@@ -690,7 +870,8 @@ int ocb_fftcc2d(ocb_ctx* ctx, void* poi2d, size_t n, int rx, int ry) {
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "fftcc2d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
-	return run_host_queue_2d(ctx, poi2d, n, [&](float* d, size_t m, size_t) { return ocb_fftcc2d_dev(ctx, d, m, rx, ry); });
+	return run_host_queue_2d(ctx, poi2d, n, [&](float* d, size_t m, size_t) { return ocb_fftcc2d_dev(ctx, d, m, rx, ry); },
+		rx == 16 && ry == 16 && !getenv("OCB_FFTCC2D_GENERIC"), ry > 0 ? ry : 0);
 }
 
 int ocb_fftcc3d_dev(ocb_ctx* ctx, void* d_poi3d, size_t n, int rx, int ry, int rz) {
@@ -811,7 +992,7 @@ static int icgn2d_host(ocb_ctx* ctx, int np, void* poi2d, size_t n, int rx, int 
 	if (!ctx || (!poi2d && n)) return set_error(ctx, OCB_ERR_ARG, "icgn2d: bad arguments");
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
-	return run_host_queue_2d(ctx, poi2d, n, [&](float* d, size_t m, size_t) { return icgn2d_dev(ctx, np, d, m, rx, ry, conv, stop); });
+	return run_host_queue_2d(ctx, poi2d, n, [&](float* d, size_t m, size_t) { return icgn2d_dev(ctx, np, d, m, rx, ry, conv, stop); }, true);
 }
 int ocb_icgn2d1(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 6, p, n, rx, ry, conv, stop); }
 int ocb_icgn2d2(ocb_ctx* ctx, void* p, size_t n, int rx, int ry, float conv, float stop) { return icgn2d_host(ctx, 12, p, n, rx, ry, conv, stop); }
@@ -837,7 +1018,7 @@ static int icgn2d_host_group(ocb_ctx* ctx, int np, float* poi2d, size_t n, int r
 		d_off = ctx->d_off;
 	}
 	return run_host_queue_2d(ctx, poi2d, n,
-		[&](float* d, size_t m, size_t first) { return icgn2d_dev(ctx, np, d, m, rx, ry, conv, stop, d_off ? d_off + 2 * first : nullptr); });
+		[&](float* d, size_t m, size_t first) { return icgn2d_dev(ctx, np, d, m, rx, ry, conv, stop, d_off ? d_off + 2 * first : nullptr); }, true);
 }
 
 int ocb_icgn2d_ex(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, float conv, float stop, const float* center_offsets,
@@ -904,7 +1085,7 @@ int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, f
 	if (n == 0) return OCB_OK;
 	if (ensure_device(ctx)) return OCB_ERR_CUDA;
 	return run_host_queue_2d(ctx, poi2d, n,
-		[&](float* d, size_t m, size_t) { return ocb_iclm2d_dev(ctx, order, d, m, rx, ry, conv, stop, lambda, alpha, beta); });
+		[&](float* d, size_t m, size_t) { return ocb_iclm2d_dev(ctx, order, d, m, rx, ry, conv, stop, lambda, alpha, beta); }, true);
 }
 
 // ---- NR2D1 ---------------------------------------------------------------

@@ -252,3 +252,26 @@ def test_reference_dvc_example_runs_unchanged(tmp_path):
     assert np.abs(mine[same_it][:, 3:6] - cpu_tab[same_it][:, 3:6]).max() < 1e-4
     assert np.abs(mine[same_it, 9] - cpu_tab[same_it, 9]).max() < 5e-5
     assert (data / "al_foam4_1_fftcc_icgn1_r30_time.csv").exists()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "shim_bench")), reason="shim_bench not built")
+def test_shim_multi_device_matches_single_device(tmp_path):
+    """The C++ shim with OPENCORR_B200_DEVICES=all (a GROUP context: FFTCC2D::compute / ICGN2D1::compute shard their
+    std::vector<POI2D> over every visible GPU inside the C ABI) returns the same records as on one GPU: the unchanged 2D example
+    writes byte-identical result tables either way.  (On a one-GPU box the group has one member.)"""
+    tables = []
+    for env_extra in ({"OPENCORR_B200_DEVICE": "0"}, {"OPENCORR_B200_DEVICES": "all"}):
+        root = tmp_path / ("run_" + "_".join(env_extra.values()))
+        data = root / "d:" / "dic_tests" / "2d_dic"
+        data.mkdir(parents=True)
+        for name in ("oht_cfrp_0.bmp", "oht_cfrp_4.bmp"):
+            shutil.copyfile(os.path.join(util.GOLDEN, name), data / name)
+        env = dict(os.environ)
+        env.pop("OPENCORR_B200_DEVICE", None)
+        env.pop("OPENCORR_B200_DEVICES", None)
+        env.update(env_extra)
+        out = subprocess.run([os.path.join(BIN, "test_2d_dic_fftcc_icgn1")], cwd=root, stdin=subprocess.DEVNULL, capture_output=True, text=True,
+                             timeout=300, env=env)
+        assert out.returncode == 0, out.stdout + out.stderr
+        tables.append(open(data / "oht_cfrp_4_fftcc_icgn1_r16.csv", "rb").read())
+    assert tables[0] == tables[1]
