@@ -50,9 +50,15 @@ __global__ void __launch_bounds__(FFTW32_WARPS * 32) fftcc2d_w32_kernel(Image2D 
 	const int w = img.w, h = img.h;
 	const int plane = (32 - lane) & 31;
 
-	for (int poi = blockIdx.x * FFTW32_WARPS + warp; poi < n_poi; poi += gridDim.x * FFTW32_WARPS) {
+	// the record of the NEXT POI of this warp is requested one POI ahead: the queue may be read in place from page-locked host
+	// memory, a few microseconds away
+	const int poi_stride = gridDim.x * FFTW32_WARPS;
+	int poi = blockIdx.x * FFTW32_WARPS + warp;
+	float rec_next = (poi < n_poi && lane < P2_N) ? pois[(size_t)poi * P2_N + lane] : 0.f;
+	for (; poi < n_poi; poi += poi_stride) {
 		float* P = pois + (size_t)poi * P2_N;
-		const float rec = lane < P2_N ? P[lane] : 0.f;
+		const float rec = rec_next;
+		if (poi + poi_stride < n_poi && lane < P2_N) rec_next = pois[(size_t)(poi + poi_stride) * P2_N + lane];
 		const float px = __shfl_sync(0xffffffffu, rec, P2_X), py = __shfl_sync(0xffffffffu, rec, P2_Y);
 		const float u0 = __shfl_sync(0xffffffffu, rec, P2_DEF + D2_U), v0 = __shfl_sync(0xffffffffu, rec, P2_DEF + D2_V);
 		// border guard: the POI is left untouched (src/oc_fftcc.cpp:190-196)

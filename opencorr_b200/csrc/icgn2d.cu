@@ -276,10 +276,10 @@ __device__ __noinline__ bool icgn2d_exact_negative(const float* Aw, float pcx, f
 // sums (statistics, solve, warp update) is computed redundantly by every warp from the same totals, so the warps
 // never diverge in control flow.  With the slab unchanged this doubles the resident warps per SM (r=16: 22 instead
 // of 11), which is what the latency-bound row loops need.
-// (the second launch bound keeps the register file from limiting residency below what the slab allows:
-//  <= 96 registers for the 6-parameter kernels, <= 144 for the 12-parameter ones)
+// (the second launch bound keeps the register file from limiting residency below what the slab allows: 16 one-warp CTAs for the
+//  6-parameter kernels of any radius, 12 for the r = 16 specialisation, whose 20 KB slab admits 11)
 template <int NP, int RC, bool LM, int WPP>
-__global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
+__global__ void __launch_bounds__(32 * WPP, NP == 6 ? (RC == 16 ? 12 : ICGN2D_MINB) / WPP : 7) icgn2d_kernel(Image2D img, float* __restrict__ pois, int n_poi, int rx_arg, int ry_arg,
 	float conv_criterion, float stop_condition, int* __restrict__ work_counter, const __grid_constant__ CUtensorMap tm_ref,
 	const __grid_constant__ CUtensorMap tm_tar, int use_tma, const float* __restrict__ center_offsets, float lm_lambda, float lm_alpha,
 	float lm_beta) {
@@ -324,20 +324,34 @@ __global__ void __launch_bounds__(32 * WPP, NP == 6 ? ICGN2D_MINB / WPP : 7) icg
 	const bool lane_on = lane < ncol;
 	const int lane_c = lane_on ? lane : ncol - 1; // idle lanes (subsets narrower than 32) shadow the last column
 
+	// WPP == 1: the work counter is drawn and the record requested one POI AHEAD (the queue may be read in place from page-locked
+	// host memory; the round trip then hides behind the current POI)
+	int poi_next = 0;
+	float rec_next = 0.f;
+	if constexpr (WPP == 1) {
+		if (lane == 0) poi_next = atomicAdd(work_counter, 1);
+		poi_next = __shfl_sync(0xffffffffu, poi_next, 0);
+		if (poi_next < n_poi && lane < P2_N) rec_next = pois[(size_t)poi_next * P2_N + lane];
+	}
 	while (true) {
 		int poi = 0;
+		float rec;
 		if constexpr (WPP > 1) {
 			gsync(); // every warp is done with the previous POI (slab, s_poi)
 			if (threadIdx.x == 0) *s_poi = atomicAdd(work_counter, 1);
 			gsync();
 			poi = *s_poi;
+			if (poi >= n_poi) break;
+			rec = lane < P2_N ? pois[(size_t)poi * P2_N + lane] : 0.f;
 		} else {
-			if (lane == 0) poi = atomicAdd(work_counter, 1);
-			poi = __shfl_sync(0xffffffffu, poi, 0);
+			poi = poi_next;
+			if (poi >= n_poi) break;
+			rec = rec_next;
+			if (lane == 0) poi_next = atomicAdd(work_counter, 1);
+			poi_next = __shfl_sync(0xffffffffu, poi_next, 0);
+			if (poi_next < n_poi && lane < P2_N) rec_next = pois[(size_t)poi_next * P2_N + lane];
 		}
-		if (poi >= n_poi) break;
 		float* P = pois + (size_t)poi * P2_N;
-		const float rec = lane < P2_N ? P[lane] : 0.f;
 		const float px = __shfl_sync(0xffffffffu, rec, P2_X);
 		const float py = __shfl_sync(0xffffffffu, rec, P2_Y);
 		const float u_in = __shfl_sync(0xffffffffu, rec, P2_DEF + D2_U);
