@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -56,29 +57,48 @@ struct ocb_worker {
 	std::condition_variable cv;
 	std::function<int()> job;
 	int result = 0;
-	bool pending = false, stop = false;
+	std::atomic<int> state{ 0 }; // 0 idle, 1 job posted, 2 job done
+	bool stop = false;
+	// A call on a group context is a handful of sub-millisecond phases, so both sides first spin on `state` (a condition-variable
+	// round trip costs tens of microseconds per phase and member) and only then go to sleep.
+	static bool spin_until(const std::atomic<int>& st, int want) {
+		for (int i = 0; i < 20000; i++) {
+			if (st.load(std::memory_order_acquire) == want) return true;
+#if defined(__x86_64__)
+			__builtin_ia32_pause();
+#endif
+		}
+		return false;
+	}
 	void loop() {
-		std::unique_lock<std::mutex> lk(mu);
 		for (;;) {
-			cv.wait(lk, [&] { return pending || stop; });
-			if (stop) return;
-			lk.unlock();
-			const int r = job();
-			lk.lock();
-			result = r;
-			pending = false;
+			if (!spin_until(state, 1)) {
+				std::unique_lock<std::mutex> lk(mu);
+				cv.wait(lk, [&] { return state.load(std::memory_order_acquire) == 1 || stop; });
+			}
+			if (stop && state.load(std::memory_order_acquire) != 1) return;
+			result = job();
+			{
+				std::lock_guard<std::mutex> lk(mu);
+				state.store(2, std::memory_order_release);
+			}
 			cv.notify_all();
 		}
 	}
 	void post(std::function<int()> f) {
-		std::lock_guard<std::mutex> lk(mu);
 		job = std::move(f);
-		pending = true;
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			state.store(1, std::memory_order_release);
+		}
 		cv.notify_all();
 	}
 	int wait() {
-		std::unique_lock<std::mutex> lk(mu);
-		cv.wait(lk, [&] { return !pending; });
+		if (!spin_until(state, 2)) {
+			std::unique_lock<std::mutex> lk(mu);
+			cv.wait(lk, [&] { return state.load(std::memory_order_acquire) == 2; });
+		}
+		state.store(0, std::memory_order_release);
 		return result;
 	}
 };
@@ -89,7 +109,9 @@ struct ocb_ctx {
 	std::vector<ocb_ctx*> members;
 	std::vector<ocb_worker*> workers; // workers[i] serves members[i + 1]; member 0 runs on the calling thread
 	bool peer_ok = false;             // group: every member can address every other member's memory (NVLink / NVSwitch)
-	cudaEvent_t ev_idle = nullptr, ev_pushed = nullptr; // member of a group: see group_distribute
+	cudaEvent_t ev_idle = nullptr, ev_pushed = nullptr; // member of a group: see group_distribute_pair
+	ocb_ctx* group = nullptr;          // member: the group it belongs to
+	bool need_peer_wait = false;       // member: its stream has not yet been ordered after the peers' image pushes
 	int device = 0;
 	int sm_count = 0;
 	size_t smem_optin = 0;
@@ -307,14 +329,28 @@ static int run_host_queue_2d(ocb_ctx* ctx, void* host, size_t n, F dev_call, boo
 static inline bool is_group(const ocb_ctx* ctx) { return ctx && !ctx->members.empty(); }
 
 // Run f(member, index) on the first `used` members concurrently (member 0 on the calling thread); first failure wins.
+// (member, on its own thread) order the member's stream after every peer's image pushes, once per upload
+static int member_settle(ocb_ctx* m) {
+	if (!m->need_peer_wait) return OCB_OK;
+	m->need_peer_wait = false;
+	if (cudaSetDevice(m->device) != cudaSuccess) return set_error(m, OCB_ERR_CUDA, "cudaSetDevice failed");
+	for (ocb_ctx* other : m->group->members)
+		if (other != m && cudaStreamWaitEvent(m->stream, other->ev_pushed, 0) != cudaSuccess) return set_error(m, OCB_ERR_CUDA, "cudaStreamWaitEvent failed");
+	return OCB_OK;
+}
+
 template <class F>
 static int group_run(ocb_ctx* g, int used, F f) {
 	if (used > (int)g->members.size()) used = (int)g->members.size();
+	auto job = [f](ocb_ctx* m, int i) {
+		const int rc = member_settle(m);
+		return rc ? rc : f(m, i);
+	};
 	for (int i = 1; i < used; i++) {
 		ocb_ctx* m = g->members[i];
-		g->workers[i - 1]->post([f, m, i]() { return f(m, i); });
+		g->workers[i - 1]->post([job, m, i]() { return job(m, i); });
 	}
-	int rc = f(g->members[0], 0), bad = 0;
+	int rc = job(g->members[0], 0), bad = 0;
 	for (int i = 1; i < used; i++) {
 		const int r = g->workers[i - 1]->wait();
 		if (rc == OCB_OK && r != OCB_OK) { rc = r; bad = i; }
@@ -363,6 +399,7 @@ static ocb_ctx* create_group(const int* devices, int n) {
 			delete g;
 			return nullptr; // ocb_create left the message in the process-wide slot
 		}
+		m->group = g;
 		g->members.push_back(m);
 	}
 	for (int i = 1; i < n; i++) {
@@ -456,11 +493,9 @@ static int group_distribute_pair(ocb_ctx* g, const float* ref, const float* tar,
 		return (int)OCB_OK;
 	});
 	if (rc) return rc;
-	for (ocb_ctx* m : g->members) { // nobody uses the pair before every slice has arrived
-		if (ensure_device(m)) return OCB_ERR_CUDA;
-		for (ocb_ctx* other : g->members)
-			if (other != m && cudaStreamWaitEvent(m->stream, other->ev_pushed, 0) != cudaSuccess) return set_error(g, OCB_ERR_CUDA, "cudaStreamWaitEvent failed");
-	}
+	// nobody uses the pair before every slice has arrived: each member orders its stream after the peers' pushes at the start of
+	// its next job, on its own thread (member_settle)
+	for (ocb_ctx* m : g->members) m->need_peer_wait = true;
 	return OCB_OK;
 }
 
@@ -536,7 +571,9 @@ int ocb_member_count(const ocb_ctx* ctx) { return !ctx ? 0 : (is_group(ctx) ? (i
 ocb_ctx* ocb_member(ocb_ctx* ctx, int index) {
 	if (!ctx) return nullptr;
 	if (!is_group(ctx)) return index == 0 ? ctx : nullptr;
-	return (index >= 0 && index < (int)ctx->members.size()) ? ctx->members[index] : nullptr;
+	if (index < 0 || index >= (int)ctx->members.size()) return nullptr;
+	member_settle(ctx->members[index]); // the caller may go on with device-pointer calls on this member: its images must be complete
+	return ctx->members[index];
 }
 
 void* ocb_host_alloc_on(ocb_ctx* ctx, size_t bytes) {
@@ -593,8 +630,8 @@ void ocb_destroy(ocb_ctx* ctx) {
 			{
 				std::lock_guard<std::mutex> lk(w->mu);
 				w->stop = true;
-				w->cv.notify_all();
 			}
+			w->cv.notify_all();
 			w->th.join();
 			delete w;
 		}
@@ -959,7 +996,13 @@ int ocb_fftcc3d(ocb_ctx* ctx, void* poi3d, size_t n, int rx, int ry, int rz) {
 
 // ---- IC-GN -----------------------------------------------------------------------------------
 int ocb_icgn2d_prepare(ocb_ctx* ctx) {
-	if (is_group(ctx)) return group_each(ctx, [](ocb_ctx* m) { return ocb_icgn2d_prepare(m); });
+	if (is_group(ctx)) { // flag only: no need to wake the members' threads
+		for (ocb_ctx* m : ctx->members) {
+			const int rc = ocb_icgn2d_prepare(m);
+			if (rc) { ctx->last_error = m->last_error; return rc; }
+		}
+		return OCB_OK;
+	}
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "icgn2d_prepare: images not set");
 	ctx->prepared2 = true; // gradients and bicubic weights are recomputed on chip per POI
@@ -1090,7 +1133,13 @@ int ocb_iclm2d(ocb_ctx* ctx, int order, void* poi2d, size_t n, int rx, int ry, f
 
 // ---- NR2D1 ---------------------------------------------------------------
 int ocb_nr2d_prepare(ocb_ctx* ctx) {
-	if (is_group(ctx)) return group_each(ctx, [](ocb_ctx* m) { return ocb_nr2d_prepare(m); });
+	if (is_group(ctx)) {
+		for (ocb_ctx* m : ctx->members) {
+			const int rc = ocb_nr2d_prepare(m);
+			if (rc) { ctx->last_error = m->last_error; return rc; }
+		}
+		return OCB_OK;
+	}
 	if (!ctx) return set_error(nullptr, OCB_ERR_ARG, "null context");
 	if (!ctx->img2.ref) return set_error(ctx, OCB_ERR_STATE, "nr2d_prepare: images not set");
 	ctx->prepared_nr2 = true; // target gradients and the three interpolants are evaluated on chip per POI
