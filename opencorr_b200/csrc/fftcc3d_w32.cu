@@ -13,28 +13,46 @@
 //   phase C: warp per z-slice: DIT inverse along kx, transpose, DIT inverse along ky, running
 //            first-maximum argmax (linear index (z*32 + y)*32 + x).
 // The scratch volume (256 KB per CTA, 2 CTAs per SM -> 76 MB) stays L2-resident.
+// Phase A's slice loads go through TMA when the POI and its guess sit on whole voxels and the volume pitch allows it: one
+// cp.async.bulk.tensor.3d box of 36 x 32 x 1 floats per window and slice (x origin rounded down to 16 bytes), straight into the
+// warp's two transpose tiles, completion on a per-warp mbarrier; otherwise the lanes gather their columns (the reference's
+// float-coordinate truncation per voxel).  Same values either way.
+#include <stdlib.h>
+#include <string.h>
+
 #include "fft32.cuh"
 #include "ocb_kernels.h"
+#include "ocb_tma.cuh"
 
 namespace ocb {
 
 constexpr int F3_WARPS = 8;
 constexpr int F3_PITCH = 33;
+constexpr int F3_BOX_W = 36;              // TMA box: 32 columns + up to 3 of alignment slack
+constexpr int F3_TILE = 32 * F3_BOX_W;    // floats per tile: a TMA box (36 x 32) or a padded transpose tile (32 x 33)
 
 __device__ __forceinline__ void argmax_merge3(float& bv, int& bi, float v, int i) {
 	if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
 }
 
-__global__ void __launch_bounds__(F3_WARPS * 32, 2) fftcc3d_w32_kernel(Image3D img, float* __restrict__ pois, int n_poi, float2* __restrict__ scratch) {
-	extern __shared__ __align__(16) float f3_smem[]; // 2 x 8 padded 32x33 tiles (67.6 KB: above the static limit)
+__global__ void __launch_bounds__(F3_WARPS * 32, 2) fftcc3d_w32_kernel(Image3D img, float* __restrict__ pois, int n_poi, float2* __restrict__ scratch,
+	const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_tar, int use_tma) {
+	extern __shared__ __align__(128) float f3_smem[]; // 2 x 8 tiles of F3_TILE floats (73.7 KB: above the static limit)
+	__shared__ __align__(8) uint64_t s_bar[F3_WARPS];
 	float* s_re_all = f3_smem;
-	float* s_im_all = f3_smem + F3_WARPS * 32 * F3_PITCH;
+	float* s_im_all = f3_smem + F3_WARPS * F3_TILE;
 	__shared__ float red[4 * 32];
 	constexpr int R = 16, NW = 32;
 	constexpr int M = NW * NW * NW;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	float* sre = s_re_all + warp * 32 * F3_PITCH;
-	float* sim = s_im_all + warp * 32 * F3_PITCH;
+	float* sre = s_re_all + warp * F3_TILE;
+	float* sim = s_im_all + warp * F3_TILE;
+	uint64_t* bar = &s_bar[warp];
+	uint32_t bar_phase = 0;
+	if (use_tma) {
+		if (lane == 0) mbar_init(bar, 1);
+		__syncwarp();
+	}
 	const int dx = img.dx, dy = img.dy, dz = img.dz;
 	float2* S = scratch + (size_t)blockIdx.x * M; // S[z][kx][ky]
 
@@ -83,18 +101,42 @@ __global__ void __launch_bounds__(F3_WARPS * 32, 2) fftcc3d_w32_kernel(Image3D i
 
 		// ---- phase A: per z-slice forward 2D transform
 		float na = 0.f, nb = 0.f;
+		// whole-voxel POI and guess (CTA-uniform): every truncation is the identity, a slice of a window is one box
+		const bool boxes = use_tma && px == floorf(px) && py == floorf(py) && pz == floorf(pz) && u0 == floorf(u0) && v0 == floorf(v0) && w0 == floorf(w0);
 		for (int z = warp; z < NW; z += F3_WARPS) {
 			float re[32], im[32];
 			const float rpz = pz + z - R;
-			const float* pa = img.ref + (size_t)(int)rpz * dy * dx + ax;
-			const float* pb = img.tar + (size_t)(int)(rpz + w0) * dy * dx + bx;
+			if (boxes) {
+				const int x0r = (int)px - R, y0r = (int)py - R, x0t = (int)(px + u0) - R, y0t = (int)(py + v0) - R;
+				const int axr = floor4(x0r), axt = floor4(x0t);
+				if (lane == 0) {
+					fence_proxy_async(); // the previous slice's generic-proxy accesses to the tiles come first
+					mbar_expect_tx(bar, (uint32_t)(2 * F3_TILE * sizeof(float)));
+					tma_load_3d(sre, &tm_ref, axr, y0r, (int)rpz, bar);
+					tma_load_3d(sim, &tm_tar, axt, y0t, (int)(rpz + w0), bar);
+				}
+				mbar_wait(bar, bar_phase);
+				bar_phase ^= 1;
+				const float* cr = sre + (x0r - axr) + lane;
+				const float* ci = sim + (x0t - axt) + lane;
 #pragma unroll
-			for (int r = 0; r < 32; r++) {
-				const float rpy = py + r - R;
-				re[r] = __ldg(pa + (size_t)(int)rpy * dx) - ref_mean;
-				im[r] = __ldg(pb + (size_t)(int)(rpy + v0) * dx) - tar_mean;
-				na = fmaf(re[r], re[r], na);
-				nb = fmaf(im[r], im[r], nb);
+				for (int r = 0; r < 32; r++) {
+					re[r] = cr[r * F3_BOX_W] - ref_mean;
+					im[r] = ci[r * F3_BOX_W] - tar_mean;
+					na = fmaf(re[r], re[r], na);
+					nb = fmaf(im[r], im[r], nb);
+				}
+			} else {
+				const float* pa = img.ref + (size_t)(int)rpz * dy * dx + ax;
+				const float* pb = img.tar + (size_t)(int)(rpz + w0) * dy * dx + bx;
+#pragma unroll
+				for (int r = 0; r < 32; r++) {
+					const float rpy = py + r - R;
+					re[r] = __ldg(pa + (size_t)(int)rpy * dx) - ref_mean;
+					im[r] = __ldg(pb + (size_t)(int)(rpy + v0) * dx) - tar_mean;
+					na = fmaf(re[r], re[r], na);
+					nb = fmaf(im[r], im[r], nb);
+				}
 			}
 			fft32_dif<false>(re, im); // along y: register i holds ky = brev5(i), lane = x
 			__syncwarp();
@@ -151,8 +193,8 @@ __global__ void __launch_bounds__(F3_WARPS * 32, 2) fftcc3d_w32_kernel(Image3D i
 			__syncthreads();
 			if (work) {
 				const int pw = (kxa == kxb) ? warp : (warp ^ 1); // tile that holds column -kx
-				const float* pre = s_re_all + pw * 32 * F3_PITCH;
-				const float* pim = s_im_all + pw * 32 * F3_PITCH;
+				const float* pre = s_re_all + pw * F3_TILE;
+				const float* pim = s_im_all + pw * F3_TILE;
 				const int plane = (32 - lane) & 31;
 #pragma unroll
 				for (int i = 0; i < 32; i++) {
@@ -234,10 +276,15 @@ int fftcc3d_w32_grid(int sm_count) { return sm_count * 2; }
 int fftcc3d_w32_launch(const Image3D& img, float* d_pois, size_t n, float2* scratch, int grid, cudaStream_t stream, cudaError_t* err) {
 	if ((long long)grid > (long long)n) grid = (int)n;
 	if (grid < 1) grid = 1;
-	const size_t smem = (size_t)2 * F3_WARPS * 32 * F3_PITCH * sizeof(float);
+	const size_t smem = (size_t)2 * F3_WARPS * F3_TILE * sizeof(float);
+	CUtensorMap tm_ref, tm_tar;
+	memset(&tm_ref, 0, sizeof(tm_ref));
+	memset(&tm_tar, 0, sizeof(tm_tar));
+	const int dims[3] = { img.dx, img.dy, img.dz }, box[3] = { F3_BOX_W, 32, 1 };
+	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm_ref, img.ref, 3, dims, box) && tma_make_map(&tm_tar, img.tar, 3, dims, box);
 	*err = cudaFuncSetAttribute(fftcc3d_w32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
-	fftcc3d_w32_kernel<<<grid, F3_WARPS * 32, smem, stream>>>(img, d_pois, (int)n, scratch);
+	fftcc3d_w32_kernel<<<grid, F3_WARPS * 32, smem, stream>>>(img, d_pois, (int)n, scratch, tm_ref, tm_tar, use_tma);
 	*err = cudaGetLastError();
 	return *err == cudaSuccess ? 0 : -2;
 }

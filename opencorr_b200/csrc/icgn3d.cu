@@ -660,7 +660,7 @@ int icgn3d1_launch(const Image3D& img, float* d_pois, size_t n, int rx, int ry, 
 	const int use_tma = !getenv("OCB_NO_TMA") && tma_make_map(&tm, img.coef, 3, dims, box);
 	void (*kern)(Image3D, float*, int, int, int, int, float, float, int, int*, const CUtensorMap, int);
 	const int threads = ctas == 1 ? 512 : 256;
-	if (ctas == 1) kern = icgn3d1_kernel<0, 512>;
+	if (ctas == 1) kern = (rx == 30 && ry == 30 && rz == 30) ? icgn3d1_kernel<30, 512> : icgn3d1_kernel<0, 512>; // 61^3: the reference's own DVC example
 	else kern = (rx == 16 && ry == 16 && rz == 16) ? icgn3d1_kernel<16, 256> : icgn3d1_kernel<0, 256>;
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
