@@ -204,6 +204,9 @@ __device__ __noinline__ bool icgn3d_exact_negative(const float* A, float px, flo
 	return negative;
 }
 
+#ifndef ICGN3D_FACTORED_SETUP
+#define ICGN3D_FACTORED_SETUP 1 // setup pass with lanes along x and factored Hessian sums (0: the round-1 loop, for A/B runs)
+#endif
 #ifndef ICGN3D_PAIRS
 // 1: when a whole z-slab of samples has its support inside the staged tile (the normal case: one warp-uniform corner test
 // per slab replaces the per-sample range tests), every lane takes TWO y-adjacent samples per step.  Their 4x4x4 blocks
@@ -278,21 +281,11 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 			float acc[NSETUP];
 #pragma unroll
 			for (int k = 0; k < NSETUP; k++) acc[k] = 0.f;
-			// the loop body carries 104 accumulators, so the compiler keeps a single load in flight: fetch the next sample's
-			// constants one trip ahead (L2 latency, nothing in L1), or every trip waits for its own load
-			auto sample_offset = [&](int i) {
-				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
-				return goff + ((size_t)ii * dy + j) * dx + k;
-			};
-			float4 c_next = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (tid < N) c_next = __ldg(img.rg + sample_offset(tid));
-			for (int i = tid; i < N; i += ICGN3D_THREADS) {
-				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
-				const float4 c4 = c_next;
-				if (i + ICGN3D_THREADS < N) c_next = __ldg(img.rg + sample_offset(i + ICGN3D_THREADS));
+			// One sample's contribution, everything spelled out: 12 steepest-descent values, 78 Hessian products (tail column, and
+			// the whole subset when ICGN3D_FACTORED_SETUP is 0)
+			auto setup_sample = [&](const float4& c4, float xl, float yl, float zl) {
 				const float R = c4.x - c0;
 				const float gx = c4.y, gy = c4.z, gz = c4.w;
-				const float xl = (float)(k - rx), yl = (float)(j - ry), zl = (float)(ii - rz);
 				float sd[NP3];
 				sd[0] = gx; sd[1] = gx * xl; sd[2] = gx * yl; sd[3] = gx * zl;
 				sd[4] = gy; sd[5] = gy * xl; sd[6] = gy * yl; sd[7] = gy * zl;
@@ -306,7 +299,112 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) icgn3d1_kernel(Image3D
 				}
 				acc[NSETUP - 2] += R;
 				acc[NSETUP - 1] = fmaf(R, R, acc[NSETUP - 1]);
+			};
+#if ICGN3D_FACTORED_SETUP
+			// Lanes along x (lane = subset column, like the sampling loops), warps over the (y, z) rows: x is a per-lane constant, y and z
+			// are warp-uniform, so a lane accumulates the FACTORED sums  sum g_a g_b {1, y, z, y^2, yz, z^2}  (36 instead of 78 Hessian
+			// products per sample),  sum g_a {1, y, z}  and  sum g_a R {1, y, z},  and applies its powers of x once at the end.  The row's
+			// constants (one coalesced 512-byte request per warp) are requested one row ahead: nothing of this is in L1.
+			{
+				float aH[6][6], aS[3][3], aR[3][3], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+				for (int a = 0; a < 6; a++)
+#pragma unroll
+					for (int q = 0; q < 6; q++) aH[a][q] = 0.f;
+#pragma unroll
+				for (int a = 0; a < 3; a++)
+#pragma unroll
+					for (int q = 0; q < 3; q++) { aS[a][q] = 0.f; aR[a][q] = 0.f; }
+				const int nrows_all = sy * sz;
+				const bool col_on = lane < ncol;
+				auto row_offset = [&](int row) {
+					const int ii = fdiv3(row, inv_sy), j = row - ii * sy;
+					return goff + ((size_t)ii * dy + j) * dx + lane;
+				};
+				float4 c_next = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (warp < nrows_all && col_on) c_next = __ldg(img.rg + row_offset(warp));
+				for (int row = warp; row < nrows_all; row += ICGN3D_WARPS) {
+					const int ii = fdiv3(row, inv_sy), j = row - ii * sy;
+					const float4 c4 = c_next;
+					if (row + ICGN3D_WARPS < nrows_all && col_on) c_next = __ldg(img.rg + row_offset(row + ICGN3D_WARPS));
+					if (col_on) {
+						const float yl = (float)(j - ry), zl = (float)(ii - rz);
+						const float m[6] = { 1.f, yl, zl, yl * yl, yl * zl, zl * zl };
+						const float R = c4.x - c0;
+						const float g[3] = { c4.y, c4.z, c4.w };
+						const float p[6] = { g[0] * g[0], g[0] * g[1], g[0] * g[2], g[1] * g[1], g[1] * g[2], g[2] * g[2] };
+#pragma unroll
+						for (int a = 0; a < 6; a++) {
+							aH[a][0] += p[a];
+#pragma unroll
+							for (int q = 1; q < 6; q++) aH[a][q] = fmaf(p[a], m[q], aH[a][q]);
+						}
+#pragma unroll
+						for (int a = 0; a < 3; a++) {
+							const float gr = g[a] * R;
+							aS[a][0] += g[a];
+							aS[a][1] = fmaf(g[a], yl, aS[a][1]);
+							aS[a][2] = fmaf(g[a], zl, aS[a][2]);
+							aR[a][0] += gr;
+							aR[a][1] = fmaf(gr, yl, aR[a][1]);
+							aR[a][2] = fmaf(gr, zl, aR[a][2]);
+						}
+						r1 += R;
+						r2 = fmaf(R, R, r2);
+					}
+				}
+				// expand with this lane's powers of x: sd index 4a + i, phi = [1, x, y, z]; phi_i phi_j = x^px * (a monomial of y, z)
+				const float xl = (float)(lane - rx), xp[3] = { 1.f, xl, xl * xl };
+#pragma unroll
+				for (int a = 0; a < 3; a++)
+#pragma unroll
+					for (int i = 0; i < 4; i++) {
+						const int k = 4 * a + i;
+						const int pxi = i == 1 ? 1 : 0, qi = i == 2 ? 1 : (i == 3 ? 2 : 0); // x power and {1,y,z} index of phi_i
+						acc[NH3 + k] = xp[pxi] * aS[a][qi];
+						acc[NH3 + NP3 + k] = xp[pxi] * aR[a][qi];
+#pragma unroll
+						for (int b = 0; b < 3; b++)
+#pragma unroll
+							for (int jj = 0; jj < 4; jj++) {
+								const int l = 4 * b + jj;
+								if (l > k) continue;
+								const int pxj = jj == 1 ? 1 : 0, qj = jj == 2 ? 1 : (jj == 3 ? 2 : 0);
+								// monomial of (y, z) in phi_i phi_j: index into {1, y, z, yy, yz, zz}
+								const int ny = (qi == 1) + (qj == 1), nz_ = (qi == 2) + (qj == 2);
+								const int mq = ny == 0 ? (nz_ == 0 ? 0 : (nz_ == 1 ? 2 : 5)) : (ny == 1 ? (nz_ == 0 ? 1 : 4) : 3);
+								const int pa = a <= b ? a : b, pb = a <= b ? b : a;                 // symmetric gradient pair (pa <= pb)
+								const int pidx = pa == 0 ? pb : (pa == 1 ? 2 + pb : 5);             // xx xy xz yy yz zz
+								acc[k * (k + 1) / 2 + l] = xp[pxi + pxj] * aH[pidx][mq];
+							}
+					}
+				acc[NSETUP - 2] = r1;
+				acc[NSETUP - 1] = r2;
+				if (!col_on) {
+#pragma unroll
+					for (int k = 0; k < NSETUP; k++) acc[k] = 0.f;
+				}
+				// columns >= 32: a short tail, spelled-out sums
+				for (int i = tid; i < nrows_all * rem; i += ICGN3D_THREADS) {
+					const int row = fdiv3(i, inv_rem), k = 32 + (i - row * rem);
+					const int ii = fdiv3(row, inv_sy), j = row - ii * sy;
+					setup_sample(__ldg(img.rg + (goff + ((size_t)ii * dy + j) * dx + k)), (float)(k - rx), (float)(j - ry), (float)(ii - rz));
+				}
 			}
+#else
+			auto sample_offset = [&](int i) {
+				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
+				return goff + ((size_t)ii * dy + j) * dx + k;
+			};
+			float4 c_next = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (tid < N) c_next = __ldg(img.rg + sample_offset(tid));
+			for (int i = tid; i < N; i += ICGN3D_THREADS) {
+				const int ii = fdiv3(i, inv_slice), rem = i - ii * slice, j = fdiv3(rem, inv_sx), k = rem - j * sx;
+				const float4 c4 = c_next;
+				if (i + ICGN3D_THREADS < N) c_next = __ldg(img.rg + sample_offset(i + ICGN3D_THREADS));
+				setup_sample(c4, (float)(k - rx), (float)(j - ry), (float)(ii - rz));
+			}
+#endif
 #pragma unroll
 			for (int k = 0; k < NSETUP; k++) {
 				float v = warp_sum(acc[k]);
