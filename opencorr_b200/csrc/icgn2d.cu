@@ -1214,6 +1214,18 @@ __global__ void __launch_bounds__(TM ? 32 * ICGN2D_TM_WARPS : 32 * WPP, TM ? (NP
 		}
 		__syncwarp();
 	}
+	if constexpr (WPP == 1) {
+		// The queue head resets itself: the last worker to leave zeroes it (and the departure count 8 ints further on), so a
+		// launch needs no memset in front of it (2-3 us of an otherwise empty stream per launch).  The host zeroes both once.
+		if (lane == 0) {
+			const int workers = (int)gridDim.x * (TM ? ICGN2D_TM_WARPS : 1);
+			__threadfence();
+			if (atomicAdd(work_counter + 8, 1) == workers - 1) {
+				work_counter[0] = 0;
+				work_counter[8] = 0;
+			}
+		}
+	}
 	if constexpr (TM) { // every warp has drained the queue: release the CTA's Tensor-Memory columns
 		tmem_fence_before_sync();
 		__syncthreads();
@@ -1223,7 +1235,8 @@ __global__ void __launch_bounds__(TM ? 32 * ICGN2D_TM_WARPS : 32 * WPP, TM ? (NP
 
 // host-side launch ---------------------------------------------------------------------------
 // Returns 0, -1 when one warp's slab does not fit in shared memory, -2 on a CUDA error.
-// d_counter: one int of device memory owned by the context (work queue head).
+// d_counter: a work-queue head owned by the context (64 ints; see ocb_create: [k] is zeroed per launch, [32 + k] and [40 + k] are
+// the self-resetting head and departure count of the one-warp-per-POI kernels).
 typedef void (*Icgn2dKernel)(Image2D, float*, int, int, int, float, float, int*, const CUtensorMap, const CUtensorMap, int, const float*, float, float, float);
 
 template <int WPP>
@@ -1283,8 +1296,12 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	}
 	*err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (*err != cudaSuccess) return -2;
-	*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
-	if (*err != cudaSuccess) return -2;
+	if (wpp != 1) {
+		*err = cudaMemsetAsync(d_counter, 0, sizeof(int), stream);
+		if (*err != cudaSuccess) return -2;
+	} else {
+		d_counter += 32; // the one-warp-per-POI kernels reset their queue head themselves: a set of heads nobody else touches
+	}
 	long long resident = (long long)sm_count * blocks_per_sm;
 	if (use_tm && (long long)n < resident * ICGN2D_TM_WARPS) resident = ((long long)n + ICGN2D_TM_WARPS - 1) / ICGN2D_TM_WARPS;
 	int grid = (int)((long long)n < resident ? (long long)n : resident); // persistent: one wave, one POI per CTA (TM: per warp) at a time

@@ -543,7 +543,9 @@ ocb_ctx* ocb_create(int device) {
 	ctx->stream = ctx->own_stream;
 	ctx->sm_count = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
-	if ((e = cudaMalloc(&ctx->d_counter, 16 * sizeof(int))) != cudaSuccess) {
+	// work-queue heads: [0, 16) are zeroed by a memset in front of every launch that uses one; [32, 48) belong to the kernels that
+	// reset their head themselves (icgn2d, one warp per POI) and are zeroed once, here
+	if ((e = cudaMalloc(&ctx->d_counter, 64 * sizeof(int))) != cudaSuccess || (e = cudaMemset(ctx->d_counter, 0, 64 * sizeof(int))) != cudaSuccess) {
 		set_error(nullptr, OCB_ERR_CUDA, "context creation on device %d failed: %s", device, cudaGetErrorString(e));
 		cudaStreamDestroy(ctx->own_stream);
 		delete ctx;
