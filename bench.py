@@ -373,6 +373,21 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPU cores next to its GPU (NVML's ideal-CPU set), before any host buffer is allocated: page-locked
+    buffers then live in the memory of the socket the GPU's PCIe link hangs on, instead of crossing the inter-socket link on every
+    copy.  One line of deployment hygiene for one-process-per-GPU jobs; returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(ClockSampler._physical_index(index))
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return "rank bound to the %d CPUs NVML lists for its GPU (of %d)" % (len(os.sched_getaffinity(0)), before)
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%s)" % str(e)[:80]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -385,6 +400,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device; opencorr_b200 has no CPU fallback"}))
         return 2
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     idle_group = None
@@ -540,7 +556,11 @@ def run_ours(args):
         e2e_times.append(time.perf_counter() - t0)
     gc.enable()
     e2e_ms = torch.tensor([1e3 * sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
+    e2e_by_rank = [float(e2e_ms.item())]
     if world > 1:
+        gathered = [torch.zeros_like(e2e_ms) for _ in range(world)]
+        dist.all_gather(gathered, e2e_ms)
+        e2e_by_rank = [float(t.item()) for t in gathered]
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
     e2e_value = n_total / (e2e_ms * 1e-3)
@@ -675,9 +695,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": common_config(args.config, cfg, world),
             "wall_s_timed_region_incl_flush": wall,
+            "cpu_binding": numa,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
-                    "ms_per_step_spread_rank0": e2e_spread},
+                    "ms_per_step_by_rank": e2e_by_rank, "ms_per_step_spread_rank0": e2e_spread},
             "e2e_u8_images": e2e_u8,
             "e2e_shim": e2e_shim,
             "capi_multi": capi_multi,
