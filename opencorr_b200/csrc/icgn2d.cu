@@ -54,6 +54,10 @@ namespace ocb {
 #endif
 constexpr int ICGN2D_ROW_UNROLL = ICGN2D_UNROLL; // rows of the fast sampling loop in flight per lane
 constexpr int ICGN2D_PAIR_UNROLL_N = ICGN2D_PAIR_UNROLL;
+#ifndef ICGN2D_SETUP_UNROLL
+#define ICGN2D_SETUP_UNROLL 3 // row pairs of the setup pass in flight per lane (1 / 2 / 3: 0.651 / 0.647 / 0.641 ms on config B)
+#endif
+constexpr int ICGN2D_SETUP_UNROLL_N = ICGN2D_SETUP_UNROLL;
 constexpr int ICGN2D_TILE_MARGIN = 1; // slack (pixels) around subset+support in the target tile
 // TMA tile loads need the innermost coordinate 16-byte aligned (x multiple of 4 floats; measured: an
 // unaligned x raises 'illegal instruction'), so tile origins are rounded down to a multiple of 4 and
@@ -462,7 +466,7 @@ __global__ void __launch_bounds__(TM ? 32 * ICGN2D_TM_WARPS : 32 * WPP, TM ? (NP
 					for (int qq = 0; qq <= DEG; qq++) { accS2[a][qq] = r1p; accR2[a][qq] = r1p; }
 				const float2 f1 = bcast2(1.f / 12.f), f2 = bcast2(2.f / 3.f);
 				const int npair = (r_hi - r_lo) >> 1;
-#pragma unroll 2
+#pragma unroll ICGN2D_SETUP_UNROLL_N
 				for (int pr = 0; pr < npair; pr++) {
 					const int r = r_lo + 2 * pr;
 					const int yg = y0 + r;
