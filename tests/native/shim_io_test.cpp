@@ -27,6 +27,27 @@ int main(int argc, char** argv)
 		CHECK(img.width == 16 && img.height == 12);
 		for (int r = 0; r < img.height; r++)
 			for (int c = 0; c < img.width; c++) CHECK(img.eg_mat(r, c) == (float)((7 * r + 3 * c) % 251));
+		{ // every load / construction gets its own generation, also when a new image lands on the address of a destroyed one
+			// (the engine's "is this pair already on the device?" test relies on it), and pixel buffers copy by value
+			unsigned long long seen[4];
+			const void* where[4];
+			for (int i = 0; i < 4; i++) {
+				Image2D again(dir + "/img.tif");
+				seen[i] = again.generation;
+				where[i] = &again;
+				CHECK(again.eg_mat(3, 5) == (float)((7 * 3 + 3 * 5) % 251));
+			}
+			CHECK(where[0] == where[1]); // same stack slot ...
+			for (int i = 1; i < 4; i++) CHECK(seen[i] != seen[i - 1] && seen[i] > img.generation); // ... never the same generation
+			Image2D blank(16, 12);
+			CHECK(blank.generation > seen[3] && blank.eg_mat(0, 0) == 0.f);
+			Image2D copy = img;
+			copy.eg_mat(2, 2) = -7.f;
+			CHECK(img.eg_mat(2, 2) == (float)((7 * 2 + 3 * 2) % 251) && copy.eg_mat(2, 2) == -7.f);
+			const unsigned long long g0 = blank.generation;
+			blank.load(dir + "/img.tif");
+			CHECK(blank.generation > g0 && blank.width == 16);
+		}
 		Image3D stack(dir + "/stack.tif");
 		CHECK(stack.dim_x == 8 && stack.dim_y == 6 && stack.dim_z == 4);
 		Image3D vol(dir + "/vol.bin");

@@ -17,6 +17,11 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["config"]["workload"].startswith("A:")
+    # the CPU arm names its CPU, its core and thread counts, and reports best-of-N next to the mean
+    cb = d["cpu_baseline"]
+    assert cb["cpu_model"] and cb["logical_cpus"] >= cb["cores"] and cb["value"] >= cb["value_mean"] > 0
+    assert "OMP_PROC_BIND=close" in cb["sample"] and "best of" in cb["sample"]
+    assert set(d["config"]) == {"workload", "pois_per_gpu", "conv", "stop", "parallelism", "l2"}  # the GPU arm's keys
 
 
 def test_product_arm_needs_a_gpu():
