@@ -248,10 +248,11 @@ _default_engines = {}
 def default_engine(device=0):
     """Process-wide engine per device, shared by the operator objects below (the reference's
     objects all borrow the same Image2D/Image3D; here they share one device copy)."""
-    eng = _default_engines.get(device)
+    key = tuple(device) if isinstance(device, (list, tuple)) else device
+    eng = _default_engines.get(key)
     if eng is None or not eng._ctx:
         eng = Engine(device)
-        _default_engines[device] = eng
+        _default_engines[key] = eng
     return eng
 
 

@@ -5,6 +5,12 @@
 // ICGN2D2::compute(POI2D*) (src/oc_icgn.cpp:685-898), including what ICGN2D*::prepare() feeds
 // them (Gradient2D4, src/oc_gradient.cpp:37-79; BicubicBspline, src/oc_cubic_bspline.cpp:84-181).
 //
+// Round-2 structure in one paragraph: the setup pass and the sampling loop take TWO subset rows per lane and step in packed
+// f32x2 arithmetic (ICGN2D_PAIRS), and in the Tensor-Memory variant (template flag TM: wide-enough subsets, queues that fill the
+// GPU) a lane's per-sample constants live in its own TMEM lane instead of shared memory, which lifts the resident warps per SM
+// from 11 to 16 at r = 16.  The reference's `any sample < 0` rejection is re-decided in the reference's own arithmetic when the
+// smallest sample is borderline (icgn2d_exact_negative).  What follows describes the common skeleton.
+//
 // Mapping: ONE WARP PER POI, persistent warps pulling POIs from an atomic counter, no CTA barrier.
 // Lanes run along x: lane c owns column c of the subset for every row (columns >= 32 are a short
 // tail), so x-dependent factors are per-lane constants and y-dependent ones are warp-uniform.
@@ -1275,8 +1281,11 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	// Tensor-Memory variant: when the queue fills the machine, the subset is >= 32 columns wide and <= 42 rows high (3 TMEM columns
 	// per row, 128 per CTA).  OCB_ICGN2D_TMEM=0 switches it off (A/B runs).
 	const char* tm_env = getenv("OCB_ICGN2D_TMEM");
+	// (and four such CTAs must fit the SM's shared memory, or the point of the variant -- 16 resident warps -- is lost)
+	const size_t tm_cta_smem = (size_t)ICGN2D_TM_WARPS * icgn2d_tm_slab_floats(rx, ry) * sizeof(float);
 	const bool use_tm = !lm && np == 6 && wpp == 1 && icgn2d_tm_supported(rx, ry) && !(tm_env && atoi(tm_env) == 0)
-		&& (long long)n >= (long long)sm_count * ICGN2D_TM_WARPS * 4 && ICGN2D_PAIRS;
+		&& (long long)n >= (long long)sm_count * ICGN2D_TM_WARPS * 4 && ICGN2D_PAIRS && tm_cta_smem <= smem_optin
+		&& 4 * (tm_cta_smem + 1024) <= (size_t)(228 * 1024);
 	int blocks_per_sm = slots(wpp);
 	if (blocks_per_sm < 1) blocks_per_sm = 1;
 	if (const char* cap = getenv("OCB_ICGN2D_MAX_WARPS")) { // tuning knob: cap the resident warps per SM
@@ -1294,7 +1303,7 @@ int icgn2d_launch(int np, const Image2D& img, float* d_pois, size_t n, int rx, i
 	if (use_tm) {
 		// (6-parameter kernels only: the 12-parameter ones need ~250 registers, which already limits them to 8 warps per SM)
 		kern = (rx == 16 && ry == 16) ? icgn2d_kernel<6, 16, false, 1, true> : icgn2d_kernel<6, 0, false, 1, true>;
-		smem = (size_t)ICGN2D_TM_WARPS * icgn2d_tm_slab_floats(rx, ry) * sizeof(float);
+		smem = tm_cta_smem;
 		threads = ICGN2D_TM_WARPS * 32;
 		blocks_per_sm = 512 / ICGN2D_TM_COLS; // Tensor Memory: 512 columns per SM
 	}

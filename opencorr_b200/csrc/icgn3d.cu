@@ -5,6 +5,12 @@
 // (src/oc_gradient.cpp:143-231) and TricubicBspline::prepare/compute
 // (src/oc_cubic_bspline.cpp:214-405).
 //
+// Round-2 structure in one paragraph: the setup pass runs with lanes along x and accumulates FACTORED Hessian sums
+// (ICGN3D_FACTORED_SETUP); when a whole z-slab of samples lies inside the staged tile (one warp-uniform corner test) every lane
+// takes TWO y-adjacent samples per step, their 4x4x4 blocks fetched as one 4x5x4 block and evaluated in packed f32x2
+// arithmetic (ICGN3D_PAIRS); the `any sample < 0` rejection is re-decided in the reference's own arithmetic when the smallest
+// sample is borderline (icgn3d_exact_negative).  What follows describes the common skeleton.
+//
 // Mapping: ONE CTA (256 threads) PER POI, persistent CTAs pulling POIs from an atomic counter; the
 // (2r+1)^3 samples are strided over the CTA with x fastest, so the reference-volume reads (value + 3
 // gradient volumes) are coalesced.  The 64-tap tricubic evaluation reads a B-spline coefficient TILE
