@@ -19,8 +19,9 @@ PCIe link).
   e2e_shim: the same step through the C++ shim (examples/shim_bench.cpp: the reference's class API, the caller's pageable
            Image2D / std::vector<POI2D>), rank 0 only, 2D configs
   capi_multi: ONE process driving all N devices through a GROUP context of the C ABI (ocb_create_multi): the weak
-           workload as one queue of N x 50k POIs, and BASELINE.json's strong-scaling configs E (4096^2, 500k POIs) and D
-           (256^3, 20k POIs) sharded over the N devices, each with host buffers (e2e); rank 0 only, the other ranks idle
+           workload as one queue of N x 50k POIs, and BASELINE.json's other configs -- C (2048^2, 50k POIs, ICGN2D2), E (4096^2, 500k POIs)
+           and D (256^3, 20k POIs) -- sharded over the N devices (strong scaling), each with host buffers (e2e); rank 0 only, the
+           other ranks idle
   cold_start: a fresh process's ocb_create() and first calls (rank 0, N=1 only)
   roofline: dominant kernel (IC-GN) algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS hbm_gbs; `traffic` and
            `binding_resources_ncu` (issue-slot / FMA / shared-memory pipe utilisation) come from the committed ncu capture
@@ -678,7 +679,7 @@ def run_ours(args):
                     capi_multi["weak_%s" % args.config] = group_e2e(ob, torch, devices, args.config, world, sub_steps, 2, dev)
                     if kind == "2d":
                         capi_multi["shim_weak_%s_pageable" % args.config] = shim_e2e(cfg, ref, tar, sub_steps, 2, {"OPENCORR_B200_DEVICES": ",".join(map(str, devices))})
-                for name in ("E", "D"):
+                for name in ("C", "E", "D"):  # BASELINE.json configs[2], [4], [3]: whole queue on N devices (strong scaling; N = 1: one device)
                     if name != args.config or world > 1:
                         capi_multi["strong_%s" % name] = group_e2e(ob, torch, devices, name, 0, sub_steps, 2, dev)
             except Exception as e:  # noqa: BLE001
