@@ -26,8 +26,13 @@
  *     available from ocb_last_error().  There is NO CPU fallback: without a usable CUDA
  *     device ocb_create() fails (returns NULL) and says why.
  *   - Functions taking host POI arrays copy host->device, run, copy back and synchronise
- *     (the reference's blocking compute()).  The *_dev variants take a device pointer,
+ *     (the reference's blocking compute()); a page-locked array (cudaHostAlloc, ocb_host_alloc,
+ *     ocb_host_register) is not copied by the 2D FFT-CC (r = 16) / IC-GN / IC-LM calls: the kernels
+ *     read and write the caller's records in place.  The *_dev variants take a device pointer,
  *     enqueue on the context's stream and return without synchronising.
+ *   - ocb_set_images_* return once the copies are enqueued: the host images must stay valid and
+ *     unchanged until the next call that synchronises (any host-queue call, or ocb_sync()).
+ *   - A context (single-device or group) is not to be used from two host threads at the same time.
  */
 #ifndef OPENCORR_B200_H_
 #define OPENCORR_B200_H_
