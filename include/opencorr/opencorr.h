@@ -419,6 +419,16 @@ namespace opencorr
 			load(file_path);
 		}
 		~Image2D() = default;
+		// a copy is a new image as far as the engine is concerned (it may be edited independently of the original)
+		inline Image2D(const Image2D& o) : height(o.height), width(o.width), size(o.size), file_path(o.file_path), eg_mat(o.eg_mat), generation(b200::nextGeneration()) {}
+		inline Image2D& operator=(const Image2D& o)
+		{
+			if (this != &o) {
+				height = o.height; width = o.width; size = o.size; file_path = o.file_path; eg_mat = o.eg_mat;
+				generation = b200::nextGeneration();
+			}
+			return *this;
+		}
 
 		// cv::imread(path, IMREAD_GRAYSCALE) for what the reference's examples feed it: uncompressed
 		// 8-bit palettised / 24-bit / 32-bit BMP (src/oc_image.cpp:37-57).  Binary PGM (P5) is accepted too.

@@ -42,6 +42,7 @@ int main(int argc, char** argv)
 			Image2D blank(16, 12);
 			CHECK(blank.generation > seen[3] && blank.eg_mat(0, 0) == 0.f);
 			Image2D copy = img;
+			CHECK(copy.generation != img.generation); // a copy may be edited on its own: the engine must not take it for the original
 			copy.eg_mat(2, 2) = -7.f;
 			CHECK(img.eg_mat(2, 2) == (float)((7 * 2 + 3 * 2) % 251) && copy.eg_mat(2, 2) == -7.f);
 			const unsigned long long g0 = blank.generation;
