@@ -576,3 +576,28 @@ def test_two_operators_with_different_pairs_interleaved(engine):
     qb = seed_b.copy()
     b.compute(qb)  # and again after a third object took the engine
     assert np.array_equal(qb, want_b)
+
+
+def test_large_deformation_gradient_tensor_memory_variant(engine):
+    """The 12 % stretch of test_large_deformation_gradient_falls_back_to_global_reads on a queue of 3 136 POIs: the
+    Tensor-Memory variant of the kernel, whose row-by-row path fetches a lane's constants from TMEM one row at a time."""
+    ref, _ = synth.speckle_pair_2d(704, 704)
+    yy, xx = np.mgrid[0:704, 0:704].astype(np.float32)
+    o_ref = Oracle2D(ref, ref)
+    o_ref.prepare()
+    src = np.stack([(352 + (xx - 352) / 1.12).ravel(), (352 + (yy - 352) / 1.12).ravel()], 1)
+    tar = np.clip(o_ref.bicubic(src), 0, 255).reshape(704, 704).astype(np.float32)
+    xy = synth.grid_2d(100, 100, 56, 56, 9, 9)
+    q = ob.make_poi2d(xy)
+    q[:, 2] = (xy[:, 0] - 352) * 0.12
+    q[:, 8] = (xy[:, 1] - 352) * 0.12
+    q[:, 3] = 0.12
+    q[:, 10] = 0.12
+    q_gpu, q_cpu = q.copy(), q.copy()
+    engine.set_images_2d(ref, tar)
+    engine.icgn2d_prepare()
+    engine.icgn2d1(q_gpu, 16, 16, 0.001, 10)
+    Oracle2D(ref, tar).icgn2d1(q_cpu, 16, 16, 0.001, 10)
+    assert (q_cpu[:, 16] > 0.9).all()
+    stats = util.compare_2d(q_gpu, q_cpu, "stretch, TM variant", max_iter_mismatch_frac=0.05)
+    assert stats["n_compared"] > 0.9 * len(q)

@@ -85,3 +85,26 @@ def test_negative_interpolated_sample_rule_3d(engine):
         seen_rejected += int(rej.sum())
         seen_kept += int((~rej).sum())
     assert seen_rejected > 300 and seen_kept > 50
+
+
+def test_negative_interpolated_sample_rule_tensor_memory_variant(engine):
+    """The same rule on a queue long enough (4 900 POIs >= 16 warps per SM) for the Tensor-Memory variant of the ICGN2D1 kernel."""
+    ref, tar = synth.speckle_pair_2d(704, 704)
+    holes = _discs((704, 704), 60, 4, 14, 3)
+    ref, tar = np.where(holes, 0, ref).astype(np.float32), np.where(holes, 0, tar).astype(np.float32)
+    xy = synth.grid_2d(40, 40, 70, 70, 9, 9)
+    q = ob.make_poi2d(xy)
+    o = Oracle2D(ref, tar)
+    o.fftcc2d(q, 16, 16)
+    q_gpu, q_cpu = q.copy(), q.copy()
+    engine.set_images_2d(ref, tar)
+    engine.icgn2d_prepare()
+    engine.icgn2d1(q_gpu, 16, 16, 0.001, 10)
+    o.icgn2d1(q_cpu, 16, 16, 0.001, 10)
+    a, b = q_gpu[:, 16], q_cpu[:, 16]
+    assert (b == -3).sum() > 500 and (b >= 0).sum() > 2000
+    differ = np.where((a == -3) != (b == -3))[0]
+    assert len(differ) == 0, "-3 decided differently at POIs %s" % differ[:10]
+    assert np.array_equal(q_gpu[b == -3], q_cpu[b == -3])
+    ok = (a >= 0) & (b >= 0) & (q_gpu[:, 17] == q_cpu[:, 17])
+    assert np.abs(q_gpu[ok][:, [2, 8]] - q_cpu[ok][:, [2, 8]]).max() < 1e-4 and np.abs(a[ok] - b[ok]).max() < 1e-5
